@@ -1,0 +1,196 @@
+#!/usr/bin/env python3
+"""oracle/build_ref.py -- TEST INFRASTRUCTURE: build the *reference itself* as a CPU oracle.
+
+Compiles the reference's own hot-path translation units from where they lie under
+/root/reference (nothing is copied into the repository) together with oracle/ref_shim.cpp into
+
+    oracle/_ref/libckd_ref_720.so     (kResX x kResY = 1280 x 720, the reference as shipped)
+    oracle/_ref/libckd_ref_2160.so    (3840 x 2160, resolution constants patched)
+
+and prepares the shared input data next to them (git-ignored, but shipped to the GPU box):
+
+    oracle/_ref/data/sync/*.track           binary GNU Rocket tracks (target/sync)
+    oracle/_ref/data/directors-cut.rocket   the XML Rocket project (target/directors-cut.rocket)
+    oracle/_ref/assets.npz                  art/maps decoded once with Pillow (BGRA / L8), shared by both sides
+
+Patch list (applied on the fly to a throw-away symlink tree in a temp dir):
+    P1  fx-blitter.cpp:48-49   _mm_load_si128 on a 4-byte aligned address -> _mm_loadu_si128 (x86 #GP)
+    P2  polar.cpp:113,161      clamp tile rows to kResY (720 % 32 != 0 -> heap overflow)
+    P3a boxblur.cpp:18         kMaxRes 2048 -> 4096 (4K scratch)
+    P3b shadertoy.cpp:185      blur-map scratch (1280*720)/2 px -> kFxMapBytes
+    P3c main.h:37-38           kResX/kResY (4K build only)
+The reference's CMake build is not used (it needs SDL2/DevIL/BASS); flags per SURVEY 8c:
+    g++ -std=c++20 -O3 -msse4.1 -fopenmp -fno-exceptions -DSYNC_PLAYER ; gcc -O3 -DSYNC_PLAYER for Rocket's C.
+"""
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+REF = os.environ.get("CKD_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+
+CPP_UNITS = [
+    "shadertoy.cpp", "landscape.cpp", "tunnelscape.cpp", "ball.cpp", "torus-twister.cpp",
+    "polar.cpp", "boxblur.cpp", "deprecated/boxblur.cpp", "fx-blitter.cpp", "util.cpp",
+    "shared-resources.cpp", "sincos-lut.cpp", "fast-cosine.cpp", "rocket.cpp",
+]
+C_UNITS = ["track.c", "device.c"]  # 3rdparty/rocket-stripped/lib
+
+CXXFLAGS = ["-std=c++20", "-O3", "-msse4.1", "-fopenmp", "-fno-exceptions", "-DSYNC_PLAYER", "-w", "-fPIC"]
+CFLAGS = ["-O3", "-DSYNC_PLAYER", "-w", "-fPIC"]
+
+# images the five X_Create() calls + Shared_Create() load (path as passed to Image_Load*, is 8-bit?)
+ASSETS = [
+    ("assets/shadertoy/nytrik-hextexture.png", False),
+    ("assets/shadertoy/nytrik-hextexture-fx.png", False),
+    ("assets/shadertoy/close-up-blur-map-1.png", False),
+    ("assets/shadertoy/close-up-blur-map-2.png", False),
+    ("assets/scape/D17.png", True),
+    ("assets/scape/C17W-edit.png", False),
+    ("assets/scape/foggradient.jpg", False),
+    ("assets/scape/tscape-D7-edit.png", True),
+    ("assets/ball/hmap_1_1k.jpg", True),
+    ("assets/ball/hmap_2_1k.jpg", True),
+    ("assets/ball/hmap_3_1k.jpg", True),
+    ("assets/ball/hmap_4_1k.jpg", True),
+    ("assets/ball/hmap_5_1k.jpg", True),
+    ("assets/ball/colormap_1k.jpg", False),
+    ("assets/ball/colormap_2_1k.jpg", False),
+    ("assets/ball/beammap_1k_1.jpg", False),
+    ("assets/ball/beammap_1k_2.jpg", False),
+    ("assets/ball/beammap_1k_3-2.jpg", False),
+    ("assets/ball/envmap3_1k.jpg", False),
+    ("assets/ball/nytrik-background_1280x720.png", False),
+    ("assets/ball/nytrik-background-2-1280x720.png", False),
+    ("assets/ball/halo.png", False),
+    ("assets/twister/hmap_2_1k.jpg", True),
+    ("assets/twister/colormap_1k.jpg", False),
+    ("assets/twister/nytrik-background_1280x720.png", False),
+]
+
+
+def _patch(text, pattern, repl, count, what):
+    new, n = re.subn(pattern, repl, text)
+    if n != count:
+        raise RuntimeError(f"patch '{what}' applied {n} times, expected {count}")
+    return new
+
+
+def make_tree(tmp, res_x, res_y):
+    """symlink tree of code/ (+ real copies of the few patched files) so that every TU sees the patched main.h"""
+    code = os.path.join(tmp, "code")
+    os.makedirs(os.path.join(code, "deprecated"))
+    os.symlink(os.path.join(REF, "3rdparty"), os.path.join(tmp, "3rdparty"))
+    src = os.path.join(REF, "code")
+    for name in os.listdir(src):
+        p = os.path.join(src, name)
+        if name == "deprecated":
+            for sub in os.listdir(p):
+                os.symlink(os.path.join(p, sub), os.path.join(code, "deprecated", sub))
+        else:
+            os.symlink(p, os.path.join(code, name))
+
+    def rewrite(rel, fn):
+        dst = os.path.join(code, rel)
+        with open(os.path.join(src, rel), "r", encoding="utf-8", errors="replace") as f:
+            text = f.read()
+        os.unlink(dst)
+        with open(dst, "w", encoding="utf-8") as f:
+            f.write(fn(text))
+
+    # P1
+    rewrite("fx-blitter.cpp", lambda t: _patch(
+        t, r"_mm_load_si128\(reinterpret_cast<const __m128i\*>\(&pSrc\[", "_mm_loadu_si128(reinterpret_cast<const __m128i*>(&pSrc[", 2, "P1"))
+    # P2
+    rewrite("polar.cpp", lambda t: _patch(
+        t, r"for \(unsigned iY = tY; iY < tY \+ tileSize; \+\+iY\)", "for (unsigned iY = tY; iY < tY + tileSize && iY < kResY; ++iY)", 2, "P2"))
+    # P3a, P3b (harmless at 720p; applied to both builds so the two oracles share one code base)
+    rewrite("boxblur.cpp", lambda t: _patch(t, r"constexpr size_t kMaxRes = 2048;", "constexpr size_t kMaxRes = 4096;", 1, "P3a"))
+    rewrite("shadertoy.cpp", lambda t: _patch(
+        t, r"mallocAligned\(\(1280\*720\)/2 \* sizeof\(uint32_t\), kAlignTo\)", "mallocAligned(kFxMapBytes, kAlignTo)", 1, "P3b"))
+    # P3c
+    if (res_x, res_y) != (1280, 720):
+        def p3c(t):
+            t = _patch(t, r"constexpr size_t kResX = 1280;", f"constexpr size_t kResX = {res_x};", 1, "P3c-x")
+            return _patch(t, r"constexpr size_t kResY = 720;", f"constexpr size_t kResY = {res_y};", 1, "P3c-y")
+        rewrite("main.h", p3c)
+    return code
+
+
+def run(cmd, cwd=None):
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: " + " ".join(cmd) + "\n" + r.stdout)
+
+
+def build_lib(res_x, res_y):
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, f"libckd_ref_{res_y}.so")
+    with tempfile.TemporaryDirectory(prefix="ckd_ref_") as tmp:
+        code = make_tree(tmp, res_x, res_y)
+        jobs = []
+        objs = []
+        for unit in CPP_UNITS:
+            obj = os.path.join(tmp, unit.replace("/", "_") + ".o")
+            objs.append(obj)
+            jobs.append(["g++", *CXXFLAGS, "-c", os.path.join(code, unit), "-o", obj])
+        for unit in C_UNITS:
+            obj = os.path.join(tmp, unit + ".o")
+            objs.append(obj)
+            jobs.append(["gcc", *CFLAGS, "-c", os.path.join(tmp, "3rdparty/rocket-stripped/lib", unit), "-o", obj])
+        shim_obj = os.path.join(tmp, "ref_shim.o")
+        objs.append(shim_obj)
+        jobs.append(["g++", *CXXFLAGS, "-I", code, "-iquote", code, "-c", os.path.join(HERE, "ref_shim.cpp"), "-o", shim_obj])
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+            list(ex.map(run, jobs))
+        run(["g++", "-shared", "-fopenmp", "-o", lib, *objs, "-lm"])
+    return lib
+
+
+def prepare_data():
+    data = os.path.join(OUT, "data")
+    sync = os.path.join(data, "sync")
+    os.makedirs(sync, exist_ok=True)
+    src_sync = os.path.join(REF, "target", "sync")
+    for name in os.listdir(src_sync):
+        if name.endswith(".track"):
+            shutil.copyfile(os.path.join(src_sync, name), os.path.join(sync, name))
+    shutil.copyfile(os.path.join(REF, "target", "directors-cut.rocket"), os.path.join(data, "directors-cut.rocket"))
+
+
+def prepare_assets():
+    import numpy as np
+    from PIL import Image
+
+    arrays = {}
+    for path, is_gray in ASSETS:
+        img = Image.open(os.path.join(REF, "target", path))
+        if is_gray:
+            arr = np.asarray(img.convert("L"), dtype=np.uint8)
+        else:
+            rgba = np.asarray(img.convert("RGBA"), dtype=np.uint8)
+            arr = np.ascontiguousarray(rgba[..., [2, 1, 0, 3]])  # -> B,G,R,A bytes == little-endian 0xAARRGGBB (code/image.cpp:53-54)
+            arr = arr.view(np.uint32).reshape(arr.shape[0], arr.shape[1])
+        arrays[path] = arr
+    np.savez_compressed(os.path.join(OUT, "assets.npz"), **arrays)
+
+
+def main():
+    if not os.path.isdir(os.path.join(REF, "code")):
+        print(f"build_ref: reference not found at {REF}; keeping prebuilt oracle/_ref (if any)")
+        return 0
+    libs = [build_lib(1280, 720), build_lib(3840, 2160)]
+    prepare_data()
+    prepare_assets()
+    for lib in libs:
+        print("built", lib)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
