@@ -1,0 +1,420 @@
+// ckd_context.cu -- context, device buffers, tables, copies.
+//
+// Replaces the reference's start-up allocations and tables: Shared_Create (shared-resources.cpp:14-37),
+// FxBlitter_Create (fx-blitter.cpp:10-20), Polar_Create/CalculateMaps (polar.cpp:18-72), BoxBlur_Create
+// (boxblur.cpp:23-28), CalculateCosLUT (sincos-lut.cpp:9-16).  Tables that the reference computes with the host's
+// libm or CPU (cos LUT, polar UV maps, the RSQRTPS approximation) are computed the same way here, on the host,
+// once, and uploaded.
+
+#include "ckd_internal.h"
+#include "ckd_hostmath.h"
+
+#include <xmmintrin.h>
+#include <vector>
+#include <mutex>
+
+static thread_local std::string t_lastError;
+static std::string g_lastError;
+static std::mutex g_errMutex;
+
+void ckd_set_error(const std::string &message)
+{
+	t_lastError = message;
+	std::lock_guard<std::mutex> lock(g_errMutex);
+	g_lastError = message;
+}
+
+int ckd_cuda_fail(cudaError_t err, const char *what, const char *file, int line)
+{
+	ckd_set_error(std::string("CUDA error '") + cudaGetErrorString(err) + "' in " + what + " (" + file + ":" + std::to_string(line) + ")");
+	return CKD_ERR_CUDA;
+}
+
+extern "C" const char *ckd_last_error(void)
+{
+	if (!t_lastError.empty())
+		return t_lastError.c_str();
+	return g_lastError.c_str();
+}
+
+extern "C" const char *ckd_version(void) { return "cookiedough_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-side table builders
+// ---------------------------------------------------------------------------------------------------------------
+
+// CalculateCosLUT, sincos-lut.cpp:9-16 (host cosf, like the reference)
+static void BuildCosLUT(float *lut)
+{
+	for (unsigned i = 0; i < kCkdCosTabSize; ++i)
+		lut[i] = cosf(float(i)*(ckdh::k2PI/kCkdCosTabSize));
+	lut[kCkdCosTabSize] = lut[0];
+}
+
+static inline uint32_t HostRsqrtBits(uint32_t bits)
+{
+	float x, r;
+	memcpy(&x, &bits, 4);
+	_mm_store_ss(&r, _mm_rsqrt_ss(_mm_set_ss(x)));
+	uint32_t out;
+	memcpy(&out, &r, 4);
+	return out;
+}
+
+// Enumerates the host CPU's RSQRTSS over both exponent parities and all 2^23 mantissas, finds the widest aligned
+// power-of-two mantissa bin on which the instruction is constant and returns the table (hard part 1).
+static void ProbeHostRsqrt(std::vector<uint32_t> &table, int &log2Bin)
+{
+	std::vector<uint32_t> full(size_t(2) << 23);
+	for (unsigned parity = 0; parity < 2; ++parity)
+		for (uint32_t mant = 0; mant < (1u<<23); ++mant)
+			full[(size_t(parity)<<23) + mant] = HostRsqrtBits(((126u+parity)<<23) | mant);
+
+	log2Bin = 0;
+	for (int bits = 23; bits >= 1; --bits)
+	{
+		const uint32_t bin = 1u<<bits;
+		bool constant = true;
+		for (size_t base = 0; base < full.size() && constant; base += bin)
+		{
+			const uint32_t v = full[base];
+			for (uint32_t i = 1; i < bin; ++i)
+				if (full[base+i] != v) { constant = false; break; }
+		}
+		if (constant) { log2Bin = bits; break; }
+	}
+
+	const size_t entries = size_t(2) << (23-log2Bin);
+	table.resize(entries);
+	for (size_t i = 0; i < entries; ++i)
+		table[i] = full[i << log2Bin];
+}
+
+// CalculateMaps, polar.cpp:18-59 (host sqrtf/atan2f, like the reference)
+static void BuildPolarMaps(int32_t *pDest, int32_t *pInvDest, unsigned srcResX, unsigned srcResY, unsigned destResX, unsigned destResY)
+{
+	const float halfResX = destResX/2.f;
+	const float halfResY = destResY/2.f;
+
+	size_t iPixel = 0;
+	const float maxDist = sqrtf(halfResX*halfResX + halfResY*halfResY);
+	for (float Y = -halfResY; Y < halfResY; Y += 1.f)
+	{
+		for (float X = -halfResX + ckdh::kEpsilon; X < halfResX; X += 1.f)
+		{
+			const float distance = sqrtf(X*X + Y*Y) / maxDist;
+			float theta = atan2f(Y, X);
+			theta += ckdh::kPI;
+			theta /= ckdh::kPI*2.f;
+			const float U    = distance*(srcResX-1.f);
+			const float invU = (1.f-distance) * (srcResX-1.f);
+			const float V    = theta * (srcResY-1.f);
+
+			if (U >= srcResX-1.f)
+				pDest[iPixel] = ((srcResX-2)<<8) | 0xff;
+			else
+				pDest[iPixel] = ckdh::ftofp24(U);
+
+			if (invU >= srcResX-1.f)
+				pInvDest[iPixel] = ((srcResX-2)<<8) | 0xff;
+			else
+				pInvDest[iPixel] = ckdh::ftofp24(invU);
+
+			if (V >= srcResY-1.f)
+				pInvDest[iPixel+1] = pDest[iPixel+1] = ((srcResY-2)<<8) | 0xff;
+			else
+				pInvDest[iPixel+1] = pDest[iPixel+1] = ckdh::ftofp24(V);
+
+			iPixel += 2;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------
+
+static size_t AlignUp(size_t v, size_t a) { return (v + a - 1)/a*a; }
+
+extern "C" int ckd_set_cos_lut(ckd_ctx *ctx, const float *lut2049)
+{
+	CKD_REQUIRE(ctx && lut2049, "null argument");
+	memcpy(ctx->h_cosLUT, lut2049, sizeof(ctx->h_cosLUT));
+	std::vector<float2> pairs(kCkdCosTabSize);
+	for (int i = 0; i < kCkdCosTabSize; ++i)
+		pairs[i] = make_float2(lut2049[i], lut2049[i+1]);
+	CKD_CUDA(cudaMemcpy(ctx->d_cosLUT2, pairs.data(), pairs.size()*sizeof(float2), cudaMemcpyHostToDevice));
+	return CKD_OK;
+}
+
+extern "C" int ckd_set_rsqrt_table(ckd_ctx *ctx, const uint32_t *table, int log2_bin)
+{
+	CKD_REQUIRE(ctx && table, "null argument");
+	CKD_REQUIRE(log2_bin >= 0 && log2_bin <= 23, "log2_bin out of range");
+	const size_t entries = size_t(2) << (23-log2_bin);
+	if (ctx->d_rsqrtTab) { cudaFree(ctx->d_rsqrtTab); ctx->d_rsqrtTab = nullptr; }
+	free(ctx->h_rsqrtTab);
+	ctx->h_rsqrtTab = static_cast<uint32_t *>(malloc(entries*sizeof(uint32_t)));
+	memcpy(ctx->h_rsqrtTab, table, entries*sizeof(uint32_t));
+	CKD_CUDA(cudaMalloc(&ctx->d_rsqrtTab, entries*sizeof(uint32_t)));
+	CKD_CUDA(cudaMemcpy(ctx->d_rsqrtTab, table, entries*sizeof(uint32_t), cudaMemcpyHostToDevice));
+	ctx->rsqrtLog2Bin = log2_bin;
+	ctx->rsqrtEntries = entries;
+	return CKD_OK;
+}
+
+extern "C" int ckd_get_rsqrt_table(ckd_ctx *ctx, uint32_t *out_table, size_t max_entries, int *out_log2_bin, size_t *out_entries)
+{
+	CKD_REQUIRE(ctx, "null context");
+	if (out_log2_bin) *out_log2_bin = ctx->rsqrtLog2Bin;
+	if (out_entries) *out_entries = ctx->rsqrtEntries;
+	if (out_table)
+	{
+		CKD_REQUIRE(max_entries >= ctx->rsqrtEntries, "table buffer too small");
+		memcpy(out_table, ctx->h_rsqrtTab, ctx->rsqrtEntries*sizeof(uint32_t));
+	}
+	return CKD_OK;
+}
+
+extern "C" int ckd_set_polar_maps(ckd_ctx *ctx, const int32_t *map, const int32_t *inv_map)
+{
+	CKD_REQUIRE(ctx && map && inv_map, "null argument");
+	const size_t bytes = size_t(ctx->resX)*ctx->resY*2*sizeof(int32_t);
+	CKD_CUDA(cudaMemcpy(ctx->d_polarMap, map, bytes, cudaMemcpyHostToDevice));
+	CKD_CUDA(cudaMemcpy(ctx->d_polarInvMap, inv_map, bytes, cudaMemcpyHostToDevice));
+	return CKD_OK;
+}
+
+extern "C" int ckd_get_polar_maps(ckd_ctx *ctx, int32_t *out_map, int32_t *out_inv_map)
+{
+	CKD_REQUIRE(ctx, "null context");
+	const size_t bytes = size_t(ctx->resX)*ctx->resY*2*sizeof(int32_t);
+	if (out_map) CKD_CUDA(cudaMemcpy(out_map, ctx->d_polarMap, bytes, cudaMemcpyDeviceToHost));
+	if (out_inv_map) CKD_CUDA(cudaMemcpy(out_inv_map, ctx->d_polarInvMap, bytes, cudaMemcpyDeviceToHost));
+	return CKD_OK;
+}
+
+extern "C" int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device)
+{
+	CKD_REQUIRE(out_ctx, "null out_ctx");
+	*out_ctx = nullptr;
+	CKD_REQUIRE(res_x >= 64 && res_y >= 64 && res_x <= 16384 && res_y <= 16384, "resolution out of range");
+	CKD_REQUIRE(0 == (res_x & 7) && 0 == (res_y & 7), "resolution must be a multiple of 8");
+
+	int numDevices = 0;
+	cudaError_t err = cudaGetDeviceCount(&numDevices);
+	if (err != cudaSuccess || numDevices <= 0)
+	{
+		ckd_set_error(std::string("ckd_create: no usable CUDA device (") + cudaGetErrorString(err) + "); this library has no CPU fallback");
+		return CKD_ERR_CUDA;
+	}
+	CKD_REQUIRE(device >= 0 && device < numDevices, "device index out of range");
+	CKD_CUDA(cudaSetDevice(device));
+
+	cudaDeviceProp prop;
+	CKD_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10)
+	{
+		ckd_set_error(std::string("ckd_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this library ships sm_100a code only");
+		return CKD_ERR_CUDA;
+	}
+
+	ckd_ctx *ctx = new ckd_ctx;
+	ctx->device = device;
+	ctx->resX = res_x;
+	ctx->resY = res_y;
+	ctx->fxX = res_x/2 + 4; // fx-blitter.h:16-17
+	ctx->fxY = res_y/2 + 4;
+	ctx->numSMs = prop.multiProcessorCount;
+
+	const size_t outPixels = size_t(res_x)*res_y;
+	const size_t fxPixels = size_t(ctx->fxX)*ctx->fxY;
+	const size_t guard = size_t(res_x)*4; // guard rows: the reference reads/writes a little past several buffers
+	const size_t outBytes = AlignUp((outPixels + guard)*4, 256);
+	const size_t fxBytes = AlignUp((fxPixels + guard)*4, 256);
+	const size_t mapBytes = AlignUp(outPixels*2*sizeof(int32_t), 256);
+	const size_t ballMapPixels = 1024*1024;
+
+	size_t total = 0;
+	auto carve = [&](size_t bytes) { size_t off = total; total += AlignUp(bytes, 256); return off; };
+	const size_t offFrame = carve(outBytes);
+	size_t offRT[kCkdNumRenderTargets], offFx[kCkdNumFxMaps], offScratch[2];
+	for (auto &o : offRT) o = carve(outBytes);
+	for (auto &o : offFx) o = carve(fxBytes);
+	for (auto &o : offScratch) o = carve(outBytes);
+	const size_t offSpikeBlur = carve(fxBytes);
+	const size_t offBallH = carve(ballMapPixels + 4096);
+	const size_t offBallB = carve(ballMapPixels*4 + 4096);
+	const size_t offMap = carve(mapBytes), offInvMap = carve(mapBytes);
+	const size_t offCos = carve(kCkdCosTabSize*sizeof(float2));
+	const size_t offVox = carve(8192*sizeof(int));
+	const size_t offRay = carve(size_t(res_y)*8*sizeof(float) + 4096);
+
+	err = cudaMalloc(&ctx->d_pool, total);
+	if (err != cudaSuccess) { delete ctx; return ckd_cuda_fail(err, "cudaMalloc(pool)", __FILE__, __LINE__); }
+	err = cudaMemset(ctx->d_pool, 0, total);
+	if (err != cudaSuccess) { cudaFree(ctx->d_pool); delete ctx; return ckd_cuda_fail(err, "cudaMemset(pool)", __FILE__, __LINE__); }
+
+	uint8_t *base = static_cast<uint8_t *>(ctx->d_pool);
+	ctx->d_frame = reinterpret_cast<uint32_t *>(base + offFrame);
+	for (int i = 0; i < kCkdNumRenderTargets; ++i) ctx->d_renderTarget[i] = reinterpret_cast<uint32_t *>(base + offRT[i]);
+	for (int i = 0; i < kCkdNumFxMaps; ++i) ctx->d_fxMap[i] = reinterpret_cast<uint32_t *>(base + offFx[i]);
+	for (int i = 0; i < 2; ++i) ctx->d_scratch[i] = reinterpret_cast<uint32_t *>(base + offScratch[i]);
+	ctx->d_spikeBlurMap = reinterpret_cast<uint32_t *>(base + offSpikeBlur);
+	ctx->d_ballHeightMix = base + offBallH;
+	ctx->d_ballBeamMix = reinterpret_cast<uint32_t *>(base + offBallB);
+	ctx->d_polarMap = reinterpret_cast<int32_t *>(base + offMap);
+	ctx->d_polarInvMap = reinterpret_cast<int32_t *>(base + offInvMap);
+	ctx->d_cosLUT2 = reinterpret_cast<float2 *>(base + offCos);
+	ctx->d_voxelTables = reinterpret_cast<int *>(base + offVox);
+	ctx->d_rayParams = reinterpret_cast<float *>(base + offRay);
+
+	int rc = CKD_OK;
+	do
+	{
+		if (cudaSuccess != (err = cudaEventCreate(&ctx->evStart)) || cudaSuccess != (err = cudaEventCreate(&ctx->evStop)))
+		{ rc = ckd_cuda_fail(err, "cudaEventCreate", __FILE__, __LINE__); break; }
+
+		float lut[kCkdCosTabSize+1];
+		BuildCosLUT(lut);
+		if (CKD_OK != (rc = ckd_set_cos_lut(ctx, lut))) break;
+
+		std::vector<uint32_t> rsqrtTab;
+		int log2Bin = 0;
+		ProbeHostRsqrt(rsqrtTab, log2Bin);
+		if (CKD_OK != (rc = ckd_set_rsqrt_table(ctx, rsqrtTab.data(), log2Bin))) break;
+
+		std::vector<int32_t> map(outPixels*2), invMap(outPixels*2);
+		BuildPolarMaps(map.data(), invMap.data(), res_x, res_y, res_x, res_y); // kTargetRes == kRes (shared-resources.h:22-23)
+		if (CKD_OK != (rc = ckd_set_polar_maps(ctx, map.data(), invMap.data()))) break;
+	}
+	while (false);
+
+	if (rc != CKD_OK)
+	{
+		ckd_destroy(ctx);
+		return rc;
+	}
+
+	*out_ctx = ctx;
+	return CKD_OK;
+}
+
+extern "C" void ckd_destroy(ckd_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	for (auto &slot : ctx->images)
+		if (slot.d_pixels) cudaFree(slot.d_pixels);
+	if (ctx->d_rsqrtTab) cudaFree(ctx->d_rsqrtTab);
+	free(ctx->h_rsqrtTab);
+	if (ctx->evStart) cudaEventDestroy(ctx->evStart);
+	if (ctx->evStop) cudaEventDestroy(ctx->evStop);
+	if (ctx->d_pool) cudaFree(ctx->d_pool);
+	delete ctx;
+}
+
+extern "C" int ckd_set_stream(ckd_ctx *ctx, void *cuda_stream)
+{
+	CKD_REQUIRE(ctx, "null context");
+	ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+	return CKD_OK;
+}
+
+extern "C" int ckd_sync(ckd_ctx *ctx)
+{
+	CKD_REQUIRE(ctx, "null context");
+	CKD_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CKD_OK;
+}
+
+extern "C" int ckd_res_x(const ckd_ctx *ctx) { return ctx ? ctx->resX : 0; }
+extern "C" int ckd_res_y(const ckd_ctx *ctx) { return ctx ? ctx->resY : 0; }
+extern "C" int ckd_fxmap_res_x(const ckd_ctx *ctx) { return ctx ? ctx->fxX : 0; }
+extern "C" int ckd_fxmap_res_y(const ckd_ctx *ctx) { return ctx ? ctx->fxY : 0; }
+extern "C" uint32_t *ckd_frame(ckd_ctx *ctx) { return ctx ? ctx->d_frame : nullptr; }
+extern "C" uint32_t *ckd_fxmap(ckd_ctx *ctx, int index) { return (ctx && index >= 0 && index < kCkdNumFxMaps) ? ctx->d_fxMap[index] : nullptr; }
+extern "C" uint32_t *ckd_render_target(ckd_ctx *ctx, int index) { return (ctx && index >= 0 && index < kCkdNumRenderTargets) ? ctx->d_renderTarget[index] : nullptr; }
+extern "C" unsigned long long ckd_launch_count(const ckd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ckd_malloc(ckd_ctx *ctx, void **out_d_ptr, size_t bytes)
+{
+	CKD_REQUIRE(ctx && out_d_ptr, "null argument");
+	CKD_CUDA(cudaSetDevice(ctx->device));
+	CKD_CUDA(cudaMalloc(out_d_ptr, bytes));
+	return CKD_OK;
+}
+
+extern "C" int ckd_free(ckd_ctx *ctx, void *d_ptr)
+{
+	CKD_REQUIRE(ctx, "null context");
+	CKD_CUDA(cudaFree(d_ptr));
+	return CKD_OK;
+}
+
+extern "C" int ckd_malloc_host(void **out_h_ptr, size_t bytes)
+{
+	CKD_REQUIRE(out_h_ptr, "null argument");
+	CKD_CUDA(cudaMallocHost(out_h_ptr, bytes));
+	return CKD_OK;
+}
+
+extern "C" int ckd_free_host(void *h_ptr)
+{
+	CKD_CUDA(cudaFreeHost(h_ptr));
+	return CKD_OK;
+}
+
+extern "C" int ckd_upload(ckd_ctx *ctx, void *d_dst, const void *h_src, size_t bytes)
+{
+	CKD_REQUIRE(ctx && d_dst && h_src, "null argument");
+	CKD_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	return CKD_OK;
+}
+
+extern "C" int ckd_download(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
+{
+	CKD_REQUIRE(ctx && h_dst && d_src, "null argument");
+	CKD_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	return CKD_OK;
+}
+
+extern "C" int ckd_timer_start(ckd_ctx *ctx)
+{
+	CKD_REQUIRE(ctx, "null context");
+	CKD_CUDA(cudaEventRecord(ctx->evStart, ctx->stream));
+	return CKD_OK;
+}
+
+extern "C" int ckd_timer_stop_ms(ckd_ctx *ctx, float *out_ms)
+{
+	CKD_REQUIRE(ctx && out_ms, "null argument");
+	CKD_CUDA(cudaEventRecord(ctx->evStop, ctx->stream));
+	CKD_CUDA(cudaEventSynchronize(ctx->evStop));
+	CKD_CUDA(cudaEventElapsedTime(out_ms, ctx->evStart, ctx->evStop));
+	return CKD_OK;
+}
+
+extern "C" int ckd_set_image(ckd_ctx *ctx, ckd_image slot, const void *h_pixels, int width, int height, int bytes_per_pixel)
+{
+	CKD_REQUIRE(ctx && h_pixels, "null argument");
+	CKD_REQUIRE(slot >= 0 && slot < CKD_IMG_COUNT, "bad image slot");
+	CKD_REQUIRE(width > 0 && height > 0 && (bytes_per_pixel == 1 || bytes_per_pixel == 4), "bad image geometry");
+	ckd_image_slot &s = ctx->images[slot];
+	if (s.d_pixels) { cudaFree(s.d_pixels); s.d_pixels = nullptr; }
+	const size_t bytes = size_t(width)*height*bytes_per_pixel;
+	CKD_CUDA(cudaMalloc(&s.d_pixels, bytes + 256)); // slack like the harness' loader
+	CKD_CUDA(cudaMemset(s.d_pixels, 0, bytes + 256));
+	CKD_CUDA(cudaMemcpy(s.d_pixels, h_pixels, bytes, cudaMemcpyHostToDevice));
+	s.width = width; s.height = height; s.bpp = bytes_per_pixel;
+	s.firstPixel = 0;
+	memcpy(&s.firstPixel, h_pixels, std::min<size_t>(4, bytes));
+	return CKD_OK;
+}
+
+extern "C" const void *ckd_get_image(ckd_ctx *ctx, ckd_image slot)
+{
+	if (!ctx || slot < 0 || slot >= CKD_IMG_COUNT) return nullptr;
+	return ctx->images[slot].d_pixels;
+}

@@ -1,0 +1,62 @@
+// ckd_internal.h -- context layout and helpers shared by the translation units of libckd_b200.so
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/ckd.h"
+
+constexpr int kCkdNumFxMaps = 4;         // fx-blitter.h:14
+constexpr int kCkdNumRenderTargets = 4;  // shared-resources.h:11
+constexpr int kCkdCosTabSize = 2048;     // sincos-lut.h:8
+
+struct ckd_image_slot {
+	void *d_pixels = nullptr;
+	int width = 0, height = 0, bpp = 0;
+	uint32_t firstPixel = 0; // host copy of the first 4 bytes (the voxel effects clear with s_pFogGradient[0])
+};
+
+struct ckd_ctx {
+	int device = 0;
+	int resX = 0, resY = 0;     // kResX, kResY
+	int fxX = 0, fxY = 0;       // kFxMapResX, kFxMapResY
+	int numSMs = 148;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr;
+	unsigned long long launches = 0;
+
+	// device twins of the reference's global buffers (all carved out of one allocation, with guard rows)
+	uint32_t *d_frame = nullptr;
+	uint32_t *d_fxMap[kCkdNumFxMaps] = {};
+	uint32_t *d_renderTarget[kCkdNumRenderTargets] = {};
+	uint32_t *d_scratch[2] = {};    // blur / effect scratch, output sized (+guard)
+	uint32_t *d_spikeBlurMap = nullptr; // s_pSpikeBlurMap (shadertoy.cpp:99,185), FX-map sized
+	uint8_t *d_ballHeightMix = nullptr; // s_heightMapMix (ball.cpp:21), 1024x1024
+	uint32_t *d_ballBeamMix = nullptr;  // s_pBeamMapMix (ball.cpp:22), 1024x1024
+	void *d_pool = nullptr;
+
+	// tables
+	float h_cosLUT[kCkdCosTabSize+1];
+	float2 *d_cosLUT2 = nullptr;      // [i] = (LUT[i], LUT[i+1]) so one 8-byte load feeds the lerp
+	uint32_t *d_rsqrtTab = nullptr;   // host RSQRTPS table
+	uint32_t *h_rsqrtTab = nullptr;
+	int rsqrtLog2Bin = 13;
+	size_t rsqrtEntries = 0;
+	int32_t *d_polarMap = nullptr, *d_polarInvMap = nullptr; // 2 ints per pixel
+	int *d_voxelTables = nullptr;     // per-frame projection / lighting tables for ball & twister
+	float *d_rayParams = nullptr;     // per-ray host-computed parameters (ball fan deltas, twister origins)
+
+	ckd_image_slot images[CKD_IMG_COUNT];
+};
+
+void ckd_set_error(const std::string &message);
+int ckd_cuda_fail(cudaError_t err, const char *what, const char *file, int line);
+
+#define CKD_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return ckd_cuda_fail(_e, #expr, __FILE__, __LINE__); } while (0)
+#define CKD_CHECK_LAUNCH(ctx) do { (ctx)->launches++; cudaError_t _e = cudaPeekAtLastError(); if (_e != cudaSuccess) return ckd_cuda_fail(_e, "kernel launch", __FILE__, __LINE__); } while (0)
+#define CKD_REQUIRE(cond, msg) do { if (!(cond)) { ckd_set_error(std::string(__func__) + ": " + (msg)); return CKD_ERR_INVALID; } } while (0)
+#define CKD_TRY(expr) do { int _r = (expr); if (_r != CKD_OK) return _r; } while (0)
+
+static inline unsigned ckd_div_up(size_t a, size_t b) { return unsigned((a + b - 1)/b); }

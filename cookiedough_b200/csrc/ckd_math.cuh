@@ -1,0 +1,328 @@
+// ckd_math.cuh -- device math layer: x86/SSE arithmetic semantics restated for sm_100a.
+//
+// The reference is an SSE4.1 + glibc program; its pixels depend on x86 conversion rules, SSE min/max NaN rules,
+// the Cephes-derived log_ps/exp_ps polynomials, the CPU's RSQRTPS approximation and on the absence of FMA contraction
+// (SURVEY.md appendix A).  Everything here is written so that, compiled with -fmad=false (and the default
+// -prec-div=true -prec-sqrt=true -ftz=false), each function returns the same bits as its x86 counterpart.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ckd {
+
+constexpr float kPI = 3.1415926535897932384626433832795f;   // Std3DMath-stripped/Math.h:17
+constexpr float k2PI = 2.f*kPI;
+constexpr float kEpsilon = 1.1920928955078125e-07f;          // FLT_EPSILON (Math.h:20)
+constexpr float kGoldenRatio = 1.61803398875f;
+constexpr float kGoldenAngle = 2.39996f;
+
+// ---- conversions --------------------------------------------------------------------------------------------------
+
+// cvttss2si (C cast on x86): truncate; out of range or NaN -> 0x80000000
+__device__ __forceinline__ int cvtt_x86(float f)
+{
+	const int r = __float2int_rz(f);
+	return (f >= -2147483648.f && f < 2147483648.f) ? r : int(0x80000000u);
+}
+
+// cvtps2dq (_mm_cvtps_epi32): round to nearest even; out of range or NaN -> 0x80000000
+__device__ __forceinline__ int cvtn_x86(float f)
+{
+	const int r = __float2int_rn(f);
+	return (f >= -2147483648.f && f < 2147483648.f) ? r : int(0x80000000u);
+}
+
+// gcc x86-64 'unsigned(float)': 64-bit cvttss2si, low 32 bits
+__device__ __forceinline__ unsigned f2u_x86(float f)
+{
+	if (!(f >= -9223372036854775808.f && f < 9223372036854775808.f))
+		return 0u;
+	return unsigned(__float2ll_rz(f));
+}
+
+__device__ __forceinline__ int ftofp24(float value) { return cvtt_x86(value*256.f); } // util.h:195-197
+
+// ---- scalar helpers with the reference's NaN behaviour ------------------------------------------------------------
+
+__device__ __forceinline__ float stdmax(float a, float b) { return (a < b) ? b : a; } // std::max<float>(a, b)
+__device__ __forceinline__ float stdmin(float a, float b) { return (b < a) ? b : a; } // std::min<float>(a, b)
+__device__ __forceinline__ float sse_min(float a, float b) { return (a < b) ? a : b; } // MINPS: 2nd operand on NaN / equal
+__device__ __forceinline__ float sse_max(float a, float b) { return (a > b) ? a : b; } // MAXPS
+__device__ __forceinline__ float clampf(float mn, float mx, float v) { return stdmax(mn, stdmin(mx, v)); } // Math.h:37-40
+__device__ __forceinline__ float fracf(float v) { return v - truncf(v); }               // Math.h:49
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return a + (b-a)*t; } // Math.h:52-56
+__device__ __forceinline__ float smoothstepf(float a, float b, float t)                 // Math.h:59-63
+{
+	t = t*t * (3.f - 2.f*t);
+	return lerpf(a, b, t);
+}
+
+// ---- interpolated cosine LUT (sincos-lut.h:13-26) -----------------------------------------------------------------
+// The 2049-entry table is staged in shared memory as 2048 (LUT[i], LUT[i+1]) pairs: one 8-byte LDS per call.
+
+__device__ __forceinline__ float lutcosf(const float2 *__restrict__ lut2, float angle)
+{
+	angle = fabsf(angle);
+	angle *= (1.f/k2PI)*2048; // constant folds in float exactly like the reference's (1.f/k2PI)*kCosTabSize
+	const int index = cvtt_x86(angle) & 2047;
+	const float2 pair = lut2[index];
+	return lerpf(pair.x, pair.y, fracf(angle));
+}
+
+// ARRESTED_DEV_LEGACY (main.h:9): lutsinf(a) = lutcosf(a + pi/2)
+__device__ __forceinline__ float lutsinf(const float2 *__restrict__ lut2, float angle)
+{
+	return lutcosf(lut2, angle + kPI*0.5f);
+}
+
+__device__ __forceinline__ void stage_cos_lut(float2 *s_lut2, const float2 *__restrict__ g_lut2)
+{
+	for (int i = threadIdx.y*blockDim.x + threadIdx.x; i < 2048; i += blockDim.x*blockDim.y)
+		s_lut2[i] = g_lut2[i];
+}
+
+// ---- RSQRTPS emulation (shadertoy-util.h:89,260,265) --------------------------------------------------------------
+// table[parity][mantissa >> log2Bin] = result bits for x = 2^(parity-1)*1.m captured from the host CPU at start-up.
+// rsqrt(x * 4^k) = rsqrt(x) * 2^-k is exact for the hardware approximation, so other exponents only shift the exponent.
+
+struct RsqrtTab { const uint32_t *__restrict__ table; int log2Bin; };
+
+__device__ __forceinline__ float rsqrt_x86(const RsqrtTab tab, float x)
+{
+	const uint32_t bits = __float_as_uint(x);
+	const uint32_t exponent = (bits >> 23) & 0xff;
+	const uint32_t mantissa = bits & 0x7fffff;
+
+	if (exponent == 0xff)
+	{
+		if (mantissa) return __uint_as_float(bits | 0x00400000u);    // NaN -> quiet NaN
+		return (bits >> 31) ? __uint_as_float(0xffc00000u) : 0.f;     // -inf -> NaN, +inf -> +0
+	}
+	if (exponent == 0)                                               // zero / denormal -> signed infinity (denormals are treated as zero)
+		return __uint_as_float((bits & 0x80000000u) | 0x7f800000u);
+	if (bits >> 31)
+		return __uint_as_float(0xffc00000u);                         // negative -> default NaN
+
+	const int k = (int(exponent) - 126) >> 1;                       // floor
+	const uint32_t parity = (exponent - 126u) & 1u;
+	const uint32_t entry = __ldg(tab.table + ((size_t(parity) << (23 - tab.log2Bin)) + (mantissa >> tab.log2Bin)));
+	return __uint_as_float(entry - (uint32_t(k) << 23));
+}
+
+// ---- Cephes log / exp as restated by sse_mathfun.h (3rdparty/sse_mathfun.h:128-214, 230-306), one lane ------------
+
+__device__ __forceinline__ float log_ps1(float x)
+{
+	const bool invalid = (x <= 0.f); // cmple: false for NaN
+
+	x = sse_max(x, __uint_as_float(0x00800000u)); // cut off denormalized stuff (NaN -> min_norm_pos)
+
+	int emm0 = int(__float_as_uint(x) >> 23);
+	x = __uint_as_float((__float_as_uint(x) & ~0x7f800000u) | 0x3f000000u); // keep mantissa, or 0.5
+
+	emm0 -= 0x7f;
+	float e = float(emm0);
+	e = e + 1.f;
+
+	const bool mask = (x < 0.707106781186547524f);
+	const float tmp = mask ? x : 0.f;
+	x = x - 1.f;
+	e = e - (mask ? 1.f : 0.f);
+	x = x + tmp;
+
+	const float z = x*x;
+
+	float y = 7.0376836292E-2f;
+	y = y*x; y = y + -1.1514610310E-1f;
+	y = y*x; y = y + 1.1676998740E-1f;
+	y = y*x; y = y + -1.2420140846E-1f;
+	y = y*x; y = y + 1.4249322787E-1f;
+	y = y*x; y = y + -1.6668057665E-1f;
+	y = y*x; y = y + 2.0000714765E-1f;
+	y = y*x; y = y + -2.4999993993E-1f;
+	y = y*x; y = y + 3.3333331174E-1f;
+	y = y*x;
+
+	y = y*z;
+
+	float t = e * -2.12194440e-4f;
+	y = y + t;
+
+	t = z * 0.5f;
+	y = y - t;
+
+	t = e * 0.693359375f;
+	x = x + y;
+	x = x + t;
+	return invalid ? __uint_as_float(0xffffffffu) : x; // or with all-ones mask
+}
+
+__device__ __forceinline__ float exp_ps1(float x)
+{
+	x = sse_min(x, 88.3762626647949f);  // NaN -> exp_hi
+	x = sse_max(x, -88.3762626647949f);
+
+	float fx = x * 1.44269504088896341f;
+	fx = fx + 0.5f;
+
+	// floorf via truncation (cvttps2dq) + correction
+	const int emm0 = cvtt_x86(fx);
+	float tmp = float(emm0);
+	const float mask = (tmp > fx) ? 1.f : 0.f;
+	fx = tmp - mask;
+
+	tmp = fx * 0.693359375f;
+	float z = fx * -2.12194440e-4f;
+	x = x - tmp;
+	x = x - z;
+
+	z = x*x;
+
+	float y = 1.9875691500E-4f;
+	y = y*x; y = y + 1.3981999507E-3f;
+	y = y*x; y = y + 8.3334519073E-3f;
+	y = y*x; y = y + 4.1665795894E-2f;
+	y = y*x; y = y + 1.6666665459E-1f;
+	y = y*x; y = y + 5.0000001201E-1f;
+	y = y*z;
+	y = y + x;
+	y = y + 1.f;
+
+	// build 2^n
+	int n = cvtt_x86(fx);
+	n = n + 0x7f;
+	n = int(uint32_t(n) << 23);
+	return y * __int_as_float(n);
+}
+
+// Shadertoy::GammaAdj, shadertoy-util.h:186-190 (one lane)
+__device__ __forceinline__ float gamma_adj1(float c, float gamma) { return exp_ps1(gamma * log_ps1(c)); }
+
+// ---- pixel packing ------------------------------------------------------------------------------------------------
+
+// one lane of ToPixel4 (shadertoy-util.h:136-146): max(0, cvtps2dq(255*c)) -> packus32 -> packus16
+__device__ __forceinline__ uint32_t to_chan(float c)
+{
+	int v = cvtn_x86(255.f * c);
+	v = max(0, v);
+	v = min(v, 65535);  // packus_epi32 (signed 32 -> unsigned 16, v >= 0 here)
+	return (v > 32767) ? 0u : uint32_t(min(v, 255)); // packus_epi16 reads the word as signed: >= 0x8000 -> 0
+}
+
+__device__ __forceinline__ uint32_t to_pixel(float b, float g, float r, float a)
+{
+	return to_chan(b) | (to_chan(g) << 8) | (to_chan(r) << 16) | (to_chan(a) << 24);
+}
+
+// one lane of ToPixel4_NoConv (shadertoy-util.h:148-157): cvtps2dq -> packus32 -> packus16
+__device__ __forceinline__ uint32_t to_chan_noconv(float c)
+{
+	int v = cvtn_x86(c);
+	v = max(0, min(v, 65535));
+	return (v > 32767) ? 0u : uint32_t(min(v, 255));
+}
+
+// ---- libm calls of the reference (host glibc): evaluated in double and rounded once -------------------------------
+// glibc's powf/expf are computed in double internally and are correctly rounded in all but rare cases; atan2f is
+// within 1 ulp.  Remaining last-bit differences are far below the 8-bit output quantisation (tolerance).
+
+__device__ __forceinline__ float powf_ref(float x, float y) { return float(pow(double(x), double(y))); }
+__device__ __forceinline__ float expf_ref(float x) { return float(exp(double(x))); }
+__device__ __forceinline__ float atan2f_ref(float y, float x) { return float(atan2(double(y), double(x))); }
+
+// Shadertoy::ExpFog, shadertoy-util.h:237-241
+__device__ __forceinline__ float exp_fog(float distance, float scale)
+{
+	return 1.f - (expf_ref(-scale*distance*distance*distance));
+}
+
+// Q3_rsqrtf<2>, q3-rsqrt.h:22-42
+__device__ __forceinline__ float q3_rsqrtf2(float x)
+{
+	const float half = 0.5f*x;
+	int iX = __float_as_int(x);
+	iX = 0x5f3759df - (iX >> 1);
+	x = __int_as_float(iX);
+	x = x*(1.5f - half*x*x);
+	x = x*(1.5f - half*x*x);
+	return x;
+}
+
+// ---- 3-vectors with the reference's evaluation order ---------------------------------------------------------------
+
+struct vec3 { float x, y, z; };
+
+// _mm_dp_ps(v, v, 0xff) with the Vector3 padding lane = 0: (x*x + y*y) + (z*z + 0*0)
+__device__ __forceinline__ float dp_ps3(const vec3 &a, const vec3 &b) { return (a.x*b.x + a.y*b.y) + (a.z*b.z + 0.f); }
+// Vector3::Dot, Vector3.h:21-24
+__device__ __forceinline__ float dot3(const vec3 &a, const vec3 &b) { return a.x*b.x + a.y*b.y + a.z*b.z; }
+
+// Shadertoy::vNorm4 / vFastNorm3, shadertoy-util.h:78-101
+__device__ __forceinline__ void fast_norm3(const RsqrtTab tab, vec3 &v)
+{
+	const float oneOverLen = rsqrt_x86(tab, dp_ps3(v, v));
+	v.x *= oneOverLen; v.y *= oneOverLen; v.z *= oneOverLen;
+}
+
+// Shadertoy::vFastLen3, shadertoy-util.h:69-76
+__device__ __forceinline__ float fast_len3(const vec3 &v) { return sqrtf(dp_ps3(v, v)); }
+
+// Shadertoy::rotX/rotY/rotZ, shadertoy-util.h:31-59
+__device__ __forceinline__ void rotX(const float2 *lut, float angle, float &Y, float &Z)
+{
+	const float cosine = lutcosf(lut, angle), sine = lutsinf(lut, angle);
+	const float rY = cosine*Y + -sine*Z;
+	const float rZ = sine*Y + cosine*Z;
+	Y = rY; Z = rZ;
+}
+__device__ __forceinline__ void rotY(const float2 *lut, float angle, float &X, float &Z)
+{
+	const float cosine = lutcosf(lut, angle), sine = lutsinf(lut, angle);
+	const float rX = cosine*X + sine*Z;
+	const float rZ = -sine*X + cosine*Z;
+	X = rX; Z = rZ;
+}
+__device__ __forceinline__ void rotZ(const float2 *lut, float angle, float &X, float &Y)
+{
+	const float cosine = lutcosf(lut, angle), sine = lutsinf(lut, angle);
+	const float rX = cosine*X + sine*Y;
+	const float rY = -sine*X + cosine*Y;
+	X = rX; Y = rY;
+}
+
+// ---- integer pixel helpers ------------------------------------------------------------------------------------------
+
+// 8-bit lerp used by every bilinear sampler (bilinear.h:34-125): ((a<<8) + (b-a)*f) >> 8, two channels per 32-bit word.
+// a*(256-f) + b*f is the same non-negative 16-bit value, so the packed form is exact.
+__device__ __forceinline__ uint32_t lerp8x2(uint32_t a, uint32_t b, uint32_t f)
+{
+	return ((a*(256u - f) + b*f) >> 8) & 0x00ff00ffu;
+}
+
+// bsamp32_16 / bsamp32_32 (bilinear.h:58-125) on packed ARGB: returns packed 8-bit channels
+__device__ __forceinline__ uint32_t bilerp_argb(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t fu, uint32_t fv)
+{
+	const uint32_t rb01 = lerp8x2(s0 & 0x00ff00ffu, s1 & 0x00ff00ffu, fu);
+	const uint32_t ag01 = lerp8x2((s0 >> 8) & 0x00ff00ffu, (s1 >> 8) & 0x00ff00ffu, fu);
+	const uint32_t rb23 = lerp8x2(s2 & 0x00ff00ffu, s3 & 0x00ff00ffu, fu);
+	const uint32_t ag23 = lerp8x2((s2 >> 8) & 0x00ff00ffu, (s3 >> 8) & 0x00ff00ffu, fu);
+	const uint32_t rb = lerp8x2(rb01, rb23, fv);
+	const uint32_t ag = lerp8x2(ag01, ag23, fv);
+	return rb | (ag << 8);
+}
+
+// bsamp8 (bilinear.h:34-53); signed arithmetic shifts as in the reference
+__device__ __forceinline__ unsigned bilerp_u8(int s0, int s1, int s2, int s3, int fu, int fv)
+{
+	const int s01 = ((s0 << 8) + (s1 - s0)*fu) >> 8;
+	const int s23 = ((s2 << 8) + (s3 - s2)*fu) >> 8;
+	return unsigned(((s01 << 8) + (s23 - s01)*fv) >> 8);
+}
+
+// per-byte helpers (SIMD-in-a-word; compile to native video / LOP3 / PRMT sequences)
+__device__ __forceinline__ uint32_t avg_u8x4(uint32_t a, uint32_t b) { return __vavgu4(a, b); }   // pavgb: (a+b+1)>>1
+__device__ __forceinline__ uint32_t adds_u8x4(uint32_t a, uint32_t b) { return __vaddus4(a, b); } // packus(add_epi16)
+__device__ __forceinline__ uint32_t subs_u8x4(uint32_t a, uint32_t b) { return __vsubus4(a, b); } // packus(sub_epi16)
+
+} // namespace ckd

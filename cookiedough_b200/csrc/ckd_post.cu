@@ -1,0 +1,463 @@
+// ckd_post.cu -- the integer 2D post chain: Fx_Blit_2x2, blend ops, rectangular blits, memset32, polar remap, TapeWarp32.
+//
+// All of these are HBM-bound byte shuffles: one thread produces 4 (or 2x4) output pixels, loads/stores are 128-bit,
+// grids are sized from the pixel count, and no shared memory is needed (no reuse beyond what L1/L2 give for free).
+// Results are bit-exact with the reference's SSE code (16-bit lane arithmetic restated on packed 32-bit words).
+
+#include "ckd_internal.h"
+#include "ckd_math.cuh"
+#include "ckd_hostmath.h"
+
+using namespace ckd;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fx_Blit_2x2 -- fx-blitter.cpp:27-75
+// ---------------------------------------------------------------------------------------------------------------
+// Each thread takes 2 horizontally adjacent FX-map pixels (plus their right/down neighbours from the guard band)
+// and writes 4 output pixels on each of 2 output rows with one 128-bit store per row.
+
+__global__ void __launch_bounds__(256) fx_blit_2x2_kernel(uint32_t *__restrict__ pDest, const uint32_t *__restrict__ pSrc, int fxX, int resX, int halfX, int halfY)
+{
+	const int pairX = blockIdx.x*blockDim.x + threadIdx.x; // index of the source pixel pair
+	const int iY = blockIdx.y*blockDim.y + threadIdx.y;
+	if (pairX*2 >= halfX || iY >= halfY)
+		return;
+
+	const int sx = pairX*2;
+	const uint32_t *row0 = pSrc + size_t(iY)*fxX + sx;
+	const uint32_t *row1 = row0 + fxX;
+
+	const uint2 a01 = *reinterpret_cast<const uint2 *>(row0); // sx is even and fxX is a multiple of 4: 8-byte aligned
+	const uint32_t a2 = row0[2];
+	const uint2 b01 = *reinterpret_cast<const uint2 *>(row1);
+	const uint32_t b2 = row1[2];
+
+	const uint32_t avgH0_0 = avg_u8x4(a01.x, a01.y), avgH0_1 = avg_u8x4(a01.y, a2);
+	const uint32_t avgH1_0 = avg_u8x4(b01.x, b01.y), avgH1_1 = avg_u8x4(b01.y, b2);
+	const uint32_t avgV0_0 = avg_u8x4(a01.x, b01.x), avgV0_1 = avg_u8x4(a01.y, b01.y);
+	const uint32_t center0 = avg_u8x4(avgH0_0, avgH1_0), center1 = avg_u8x4(avgH0_1, avgH1_1);
+
+	uint32_t *top = pDest + size_t(iY*2)*resX + sx*2;
+	*reinterpret_cast<uint4 *>(top) = make_uint4(a01.x, avgH0_0, a01.y, avgH0_1);
+	*reinterpret_cast<uint4 *>(top + resX) = make_uint4(avgV0_0, center0, avgV0_1, center1);
+}
+
+extern "C" int ckd_fx_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src)
+{
+	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
+	CKD_REQUIRE(0 == (reinterpret_cast<uintptr_t>(d_dest) & 15) && 0 == (reinterpret_cast<uintptr_t>(d_src) & 15), "buffers must be 16-byte aligned (fx-blitter.cpp:29-30)");
+	const int halfX = ctx->fxX - 4, halfY = ctx->fxY - 4;
+	const dim3 block(64, 4);
+	const dim3 grid(ckd_div_up(halfX/2, block.x), ckd_div_up(halfY, block.y));
+	fx_blit_2x2_kernel<<<grid, block, 0, ctx->stream>>>(d_dest, d_src, ctx->fxX, ctx->resX, halfX, halfY);
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// blend ops -- util.cpp:83-812
+// ---------------------------------------------------------------------------------------------------------------
+
+struct BlendParams { uint32_t u0, u1; };
+
+// SoftLightBlend, util.cpp:227-240 (A = src channel, B = dest channel; int arithmetic, returned as unsigned)
+__device__ __forceinline__ unsigned soft_light(unsigned A, unsigned B)
+{
+	const int dA = int(A/2) + 64;
+	if (B < 128)
+		return unsigned((2*dA*int(B))/256);
+	return unsigned(255 - (2*(255-dA)*(255-int(B)))/256);
+}
+
+// Overlay channel, util.cpp:450-452
+__device__ __forceinline__ unsigned overlay_chan(unsigned bottom, unsigned top)
+{
+	return bottom < 128 ? (2*bottom*top/255) : (255 - 2*(255-bottom)*(255-top)/255);
+}
+
+template <int OP> __device__ __forceinline__ uint32_t blend_px(uint32_t d, uint32_t s, const BlendParams &p)
+{
+	const unsigned A2 = d >> 24, R2 = (d >> 16) & 0xff, G2 = (d >> 8) & 0xff, B2 = d & 0xff;
+	const unsigned A1 = s >> 24, R1 = (s >> 16) & 0xff, G1 = (s >> 8) & 0xff, B1 = s & 0xff;
+
+	if (OP == CKD_MIX32 || OP == CKD_FADE32 || OP == CKD_MIXSRC32)
+	{
+		// (dest<<8 + alpha*(src-dest)) >> 8 in 16-bit lanes == (dest*(256-alpha) + src*alpha) >> 8  (util.cpp:92-95, 672-675, 808-810)
+		const uint32_t alpha = (OP == CKD_MIXSRC32) ? A1 : p.u0;
+		const uint32_t src = (OP == CKD_FADE32) ? p.u1 : s;
+		const uint32_t rb = lerp8x2(d & 0x00ff00ffu, src & 0x00ff00ffu, alpha);
+		const uint32_t ag = lerp8x2((d >> 8) & 0x00ff00ffu, (src >> 8) & 0x00ff00ffu, alpha);
+		return rb | (ag << 8);
+	}
+	if (OP == CKD_ADD32) return adds_u8x4(d, s); // util.cpp:141-143
+	if (OP == CKD_SUB32) return subs_u8x4(d, s); // util.cpp:188-190
+	if (OP == CKD_MIXOVER32)
+	{
+		// util.cpp:148-177
+		const unsigned iA1 = 0xff - A1;
+		unsigned R = ((R1*(0xff-iA1))>>8) + ((R2*iA1)>>8);
+		unsigned G = ((G1*(0xff-iA1))>>8) + ((G2*iA1)>>8);
+		unsigned B = ((B1*(0xff-iA1))>>8) + ((B2*iA1)>>8);
+		if (R > 255) R = 255;
+		if (G > 255) G = 255;
+		if (B > 255) B = 255;
+		return (R<<16)|(G<<8)|B;
+	}
+	if (OP == CKD_EXCL32)
+	{
+		// util.cpp:194-223
+		const unsigned R = R1 + R2 - ((2*R1*R2)>>8);
+		const unsigned G = G1 + G2 - ((2*G1*G2)>>8);
+		const unsigned B = B1 + B2 - ((2*B1*B2)>>8);
+		return (A2<<24)|(R<<16)|(G<<8)|B;
+	}
+	if (OP == CKD_SOFTLIGHT32)
+	{
+		// util.cpp:242-271
+		const unsigned R = soft_light(R1, R2), G = soft_light(G1, G2), B = soft_light(B1, B2);
+		return (A2<<24)|(R<<16)|(G<<8)|B;
+	}
+	if (OP == CKD_SOFTLIGHT32A || OP == CKD_SOFTLIGHT32AA)
+	{
+		// util.cpp:274-346: the lerp runs in *unsigned* 32-bit arithmetic; wrapped bits spill into the neighbouring fields
+		unsigned R = soft_light(R1, R2), G = soft_light(G1, G2), B = soft_light(B1, B2);
+		const unsigned a = (OP == CKD_SOFTLIGHT32A) ? A1 : p.u0;
+		R = R2 + (((R-R2)*a)>>8);
+		G = G2 + (((G-G2)*a)>>8);
+		B = B2 + (((B-B2)*a)>>8);
+		if (OP == CKD_SOFTLIGHT32A)
+			return (R<<16)|(G<<8)|B;
+		return (a<<24)|(R<<16)|(G<<8)|B;
+	}
+	if (OP == CKD_OVERLAY32)
+	{
+		// util.cpp:434-456
+		return (overlay_chan(R2, R1)<<16)|(overlay_chan(G2, G1)<<8)|overlay_chan(B2, B1);
+	}
+	if (OP == CKD_OVERLAY32A)
+	{
+		// util.cpp:485-513
+		const unsigned nR = overlay_chan(R2, R1), nG = overlay_chan(G2, G1), nB = overlay_chan(B2, B1);
+		const unsigned R = R2 + (((nR-R2)*A1)>>8);
+		const unsigned G = G2 + (((nG-G2)*A1)>>8);
+		const unsigned B = B2 + (((nB-B2)*A1)>>8);
+		return (R<<16)|(G<<8)|B;
+	}
+	if (OP == CKD_DARKEN32_50)
+	{
+		// util.cpp:518-549
+		const unsigned R = (R2 + min(R1, R2))>>1, G = (G2 + min(G1, G2))>>1, B = (B2 + min(B1, B2))>>1;
+		return (A2<<24)|(R<<16)|(G<<8)|B;
+	}
+	if (OP == CKD_MULSRC32)
+	{
+		// util.cpp:605-618: (src*dest)>>8 per channel, alpha included
+		return ((A1*A2)>>8)<<24 | ((R1*R2)>>8)<<16 | ((G1*G2)>>8)<<8 | ((B1*B2)>>8);
+	}
+	if (OP == CKD_MULSRC32A)
+	{
+		// util.cpp:620-634: (srcAlpha*dest)>>8 per channel
+		return ((A1*A2)>>8)<<24 | ((A1*R2)>>8)<<16 | ((A1*G2)>>8)<<8 | ((A1*B2)>>8);
+	}
+	return d;
+}
+
+template <int OP> __global__ void __launch_bounds__(256) blend_kernel(uint32_t *pDest, const uint32_t *pSrc, unsigned numQuads, unsigned numPixels, BlendParams p)
+{
+	// pDest/pSrc are not __restrict__: the reference allows them to alias exactly (same pointer)
+	const unsigned stride = gridDim.x*blockDim.x;
+	for (unsigned q = blockIdx.x*blockDim.x + threadIdx.x; q < numQuads; q += stride)
+	{
+		uint4 d = reinterpret_cast<const uint4 *>(pDest)[q];
+		uint4 s = (OP == CKD_FADE32) ? d : reinterpret_cast<const uint4 *>(pSrc)[q];
+		d.x = blend_px<OP>(d.x, s.x, p);
+		d.y = blend_px<OP>(d.y, s.y, p);
+		d.z = blend_px<OP>(d.z, s.z, p);
+		d.w = blend_px<OP>(d.w, s.w, p);
+		reinterpret_cast<uint4 *>(pDest)[q] = d;
+	}
+	// tail (numPixels not a multiple of 4)
+	const unsigned tail = numQuads*4 + blockIdx.x*blockDim.x + threadIdx.x;
+	if (tail < numPixels)
+		pDest[tail] = blend_px<OP>(pDest[tail], (OP == CKD_FADE32) ? 0u : pSrc[tail], p);
+}
+
+// unaligned fallback (sub-rectangles of larger images): one pixel per thread
+template <int OP> __global__ void __launch_bounds__(256) blend_kernel_scalar(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels, BlendParams p)
+{
+	const unsigned stride = gridDim.x*blockDim.x;
+	for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < numPixels; i += stride)
+		pDest[i] = blend_px<OP>(pDest[i], (OP == CKD_FADE32) ? 0u : pSrc[i], p);
+}
+
+template <int OP> static int LaunchBlend(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned numPixels, BlendParams p)
+{
+	if (0 == numPixels)
+		return CKD_OK;
+	const bool aligned = 0 == ((reinterpret_cast<uintptr_t>(d_dest) | reinterpret_cast<uintptr_t>(d_src)) & 15);
+	const unsigned maxBlocks = unsigned(ctx->numSMs)*16;
+	if (aligned)
+	{
+		const unsigned numQuads = numPixels/4;
+		const unsigned blocks = std::max(1u, std::min(maxBlocks, ckd_div_up(std::max(numQuads, 1u), 256)));
+		blend_kernel<OP><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, numQuads, numPixels, p);
+	}
+	else
+	{
+		const unsigned blocks = std::max(1u, std::min(maxBlocks, ckd_div_up(numPixels, 256)));
+		blend_kernel_scalar<OP><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, numPixels, p);
+	}
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}
+
+extern "C" int ckd_blend(ckd_ctx *ctx, ckd_blend_op op, uint32_t *d_dest, const uint32_t *d_src, unsigned num_pixels, float f_param, unsigned u_param)
+{
+	CKD_REQUIRE(ctx && d_dest, "null argument");
+	CKD_REQUIRE(op == CKD_FADE32 || d_src, "null source");
+	if (op == CKD_FADE32)
+		d_src = d_dest;
+
+	BlendParams p = { 0, 0 };
+	switch (op)
+	{
+	case CKD_MIX32:         p.u0 = u_param & 0xff; return LaunchBlend<CKD_MIX32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_MIXOVER32:     return LaunchBlend<CKD_MIXOVER32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_ADD32:         return LaunchBlend<CKD_ADD32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_SUB32:         return LaunchBlend<CKD_SUB32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_EXCL32:        return LaunchBlend<CKD_EXCL32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_SOFTLIGHT32:   return LaunchBlend<CKD_SOFTLIGHT32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_SOFTLIGHT32A:  return LaunchBlend<CKD_SOFTLIGHT32A>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_SOFTLIGHT32AA:
+		// util.cpp:311-312: alpha = saturatef(alpha)*255.f; iA = unsigned(alpha)
+		p.u0 = ckdh::x86_f2u(ckdh::saturatef(f_param)*255.f);
+		return LaunchBlend<CKD_SOFTLIGHT32AA>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_OVERLAY32:     return LaunchBlend<CKD_OVERLAY32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_OVERLAY32A:    return LaunchBlend<CKD_OVERLAY32A>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_DARKEN32_50:   return LaunchBlend<CKD_DARKEN32_50>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_MULSRC32:      return LaunchBlend<CKD_MULSRC32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_MULSRC32A:     return LaunchBlend<CKD_MULSRC32A>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_MIXSRC32:      return LaunchBlend<CKD_MIXSRC32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_FADE32:        p.u0 = u_param >> 24; p.u1 = u_param & 0xffffff; return LaunchBlend<CKD_FADE32>(ctx, d_dest, d_src, num_pixels, p);
+	}
+	CKD_REQUIRE(false, "unknown blend op");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rectangular blits -- util.cpp:636-659 (MixSrc32S), 707-796 (BlitSrc32/A, BlitAdd32/A)
+// ---------------------------------------------------------------------------------------------------------------
+
+enum { kRectMixSrc = 0, kRectBlitSrcA = 1, kRectBlitAdd = 2, kRectBlitAddA = 3 };
+
+// fa = the four bytes of 0x01010101*unsigned(alpha*255.f) (c2vISSE16 of that word: one 16-bit lane per byte)
+template <int OP> __device__ __forceinline__ uint32_t rect_px(uint32_t d, uint32_t s, uint32_t fa)
+{
+	if (OP == kRectMixSrc)
+	{
+		const uint32_t a = s >> 24;
+		return lerp8x2(d & 0x00ff00ffu, s & 0x00ff00ffu, a) | (lerp8x2((d >> 8) & 0x00ff00ffu, (s >> 8) & 0x00ff00ffu, a) << 8);
+	}
+	if (OP == kRectBlitAdd)
+		return adds_u8x4(d, s);
+
+	uint32_t out = 0;
+	const uint32_t srcA = s >> 24;
+	#pragma unroll
+	for (int c = 0; c < 4; ++c)
+	{
+		const uint32_t f = (fa >> (8*c)) & 0xff;
+		const uint32_t sc = (s >> (8*c)) & 0xff, dc = (d >> (8*c)) & 0xff;
+		uint32_t r;
+		if (OP == kRectBlitSrcA)
+		{
+			const uint32_t a = (srcA*f) >> 8;                 // util.cpp:743
+			r = (((dc << 8) + a*(sc - dc)) & 0xffff) >> 8;    // 16-bit lane arithmetic, util.cpp:745-746
+			r = min(r, 255u);
+		}
+		else
+		{
+			const uint32_t mod = (sc*f) >> 8;                 // util.cpp:788
+			r = min(dc + mod, 255u);                          // add_epi16 + packus
+		}
+		out |= r << (8*c);
+	}
+	return out;
+}
+
+template <int OP> __global__ void __launch_bounds__(256) rect_kernel(uint32_t *pDest, const uint32_t *pSrc, unsigned destStride, unsigned srcStride, unsigned width, unsigned height, uint32_t fa)
+{
+	const unsigned x = blockIdx.x*blockDim.x + threadIdx.x;
+	const unsigned y = blockIdx.y*blockDim.y + threadIdx.y;
+	if (x >= width || y >= height)
+		return;
+	const size_t di = size_t(y)*destStride + x;
+	pDest[di] = rect_px<OP>(pDest[di], pSrc[size_t(y)*srcStride + x], fa);
+}
+
+template <int OP> static int LaunchRect(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned destStride, unsigned srcStride, unsigned width, unsigned height, uint32_t fa)
+{
+	if (0 == width || 0 == height)
+		return CKD_OK;
+	const dim3 block(64, 4);
+	const dim3 grid(ckd_div_up(width, block.x), ckd_div_up(height, block.y));
+	rect_kernel<OP><<<grid, block, 0, ctx->stream>>>(d_dest, d_src, destStride, srcStride, width, height, fa);
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}
+
+extern "C" int ckd_blit(ckd_ctx *ctx, ckd_blit_op op, uint32_t *d_dest, const uint32_t *d_src, unsigned dest_res_x, unsigned src_res_x, unsigned y_res, float alpha)
+{
+	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
+	const uint32_t fa = 0x01010101u * ckdh::x86_f2u(alpha*255.f); // util.cpp:734, 778
+	switch (op)
+	{
+	case CKD_BLITSRC32:  return LaunchRect<kRectMixSrc>(ctx, d_dest, d_src, dest_res_x, src_res_x, src_res_x, y_res, 0);
+	case CKD_BLITSRC32A: return LaunchRect<kRectBlitSrcA>(ctx, d_dest, d_src, dest_res_x, src_res_x, src_res_x, y_res, fa);
+	case CKD_BLITADD32:  return LaunchRect<kRectBlitAdd>(ctx, d_dest, d_src, dest_res_x, src_res_x, src_res_x, y_res, 0);
+	case CKD_BLITADD32A: return LaunchRect<kRectBlitAddA>(ctx, d_dest, d_src, dest_res_x, src_res_x, src_res_x, y_res, fa);
+	}
+	CKD_REQUIRE(false, "unknown blit op");
+}
+
+extern "C" int ckd_mix_src_s(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned dest_res_x, unsigned dest_res_y, unsigned src_stride)
+{
+	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
+	return LaunchRect<kRectMixSrc>(ctx, d_dest, d_src, dest_res_x, src_stride, dest_res_x, dest_res_y, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// memset32 -- util.h:57-67
+// ---------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) memset32_kernel(uint32_t *__restrict__ pDest, uint32_t value, size_t numQuads, size_t numInts)
+{
+	const size_t stride = size_t(gridDim.x)*blockDim.x;
+	const uint4 v = make_uint4(value, value, value, value);
+	for (size_t q = size_t(blockIdx.x)*blockDim.x + threadIdx.x; q < numQuads; q += stride)
+		reinterpret_cast<uint4 *>(pDest)[q] = v;
+	const size_t tail = numQuads*4 + size_t(blockIdx.x)*blockDim.x + threadIdx.x;
+	if (tail < numInts)
+		pDest[tail] = value;
+}
+
+extern "C" int ckd_memset32(ckd_ctx *ctx, uint32_t *d_dest, uint32_t value, size_t num_ints)
+{
+	CKD_REQUIRE(ctx && d_dest, "null argument");
+	CKD_REQUIRE(0 == (reinterpret_cast<uintptr_t>(d_dest) & 15), "destination must be 16-byte aligned");
+	if (0 == num_ints)
+		return CKD_OK;
+	const size_t numQuads = num_ints/4;
+	const unsigned blocks = unsigned(std::max<size_t>(1, std::min<size_t>(size_t(ctx->numSMs)*16, ckd_div_up(std::max<size_t>(numQuads, 1), 256))));
+	memset32_kernel<<<blocks, 256, 0, ctx->stream>>>(d_dest, value, numQuads, num_ints);
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// polar remap -- polar.cpp:82-198
+// ---------------------------------------------------------------------------------------------------------------
+// One thread per 4 destination pixels: 2x 128-bit map loads (8 B/px, the dominant stream), 16 texel gathers from the
+// source (L2 resident at 33 MB), one 128-bit store.  ALPHA adds a 128-bit read of the destination.
+
+__device__ __forceinline__ uint32_t polar_fetch(const uint32_t *__restrict__ pSrc, int U, int V, unsigned resX)
+{
+	// Fetch32/Fetch16, polar.cpp:82-106
+	const unsigned U0 = unsigned(U >> 8);
+	const unsigned V0 = unsigned(V >> 8)*resX;
+	const uint32_t fu = U & 0xff, fv = V & 0xff;
+	const uint32_t *p = pSrc + U0 + V0;
+	const uint32_t s0 = __ldg(p), s1 = __ldg(p + 1), s2 = __ldg(p + resX), s3 = __ldg(p + resX + 1);
+	return bilerp_argb(s0, s1, s2, s3, fu, fv);
+}
+
+__device__ __forceinline__ uint32_t polar_blend(uint32_t d, uint32_t s)
+{
+	// Polar_Blit_TileA, polar.cpp:169-174: lerp every channel by the fetched alpha
+	const uint32_t a = s >> 24;
+	return lerp8x2(d & 0x00ff00ffu, s & 0x00ff00ffu, a) | (lerp8x2((d >> 8) & 0x00ff00ffu, (s >> 8) & 0x00ff00ffu, a) << 8);
+}
+
+template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel(uint32_t *pDest, const uint32_t *__restrict__ pSrc, const int4 *__restrict__ pMap, unsigned numQuads, unsigned resX)
+{
+	const unsigned q = blockIdx.x*blockDim.x + threadIdx.x;
+	if (q >= numQuads)
+		return;
+	const int4 m0 = __ldg(pMap + size_t(q)*2), m1 = __ldg(pMap + size_t(q)*2 + 1);
+	uint4 out;
+	out.x = polar_fetch(pSrc, m0.x, m0.y, resX);
+	out.y = polar_fetch(pSrc, m0.z, m0.w, resX);
+	out.z = polar_fetch(pSrc, m1.x, m1.y, resX);
+	out.w = polar_fetch(pSrc, m1.z, m1.w, resX);
+	if (ALPHA)
+	{
+		const uint4 d = reinterpret_cast<const uint4 *>(pDest)[q];
+		out.x = polar_blend(d.x, out.x);
+		out.y = polar_blend(d.y, out.y);
+		out.z = polar_blend(d.z, out.z);
+		out.w = polar_blend(d.w, out.w);
+	}
+	reinterpret_cast<uint4 *>(pDest)[q] = out;
+}
+
+static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse, bool alpha)
+{
+	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
+	CKD_REQUIRE(d_dest != d_src, "polar blit cannot run in place");
+	CKD_REQUIRE(0 == (reinterpret_cast<uintptr_t>(d_dest) & 15), "destination must be 16-byte aligned");
+	const unsigned numQuads = unsigned(size_t(ctx->resX)*ctx->resY/4);
+	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap : ctx->d_polarMap);
+	const unsigned blocks = ckd_div_up(numQuads, 256);
+	if (alpha)
+		polar_blit_kernel<true><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
+	else
+		polar_blit_kernel<false><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}
+
+extern "C" int ckd_polar_blit(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse) { return LaunchPolar(ctx, d_dest, d_src, inverse, false); }
+extern "C" int ckd_polar_blit_a(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse) { return LaunchPolar(ctx, d_dest, d_src, inverse, true); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// TapeWarp32 -- util.cpp:552-603
+// ---------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) tape_warp_kernel(uint32_t *__restrict__ pDest, const uint32_t *__restrict__ pSrc, const float2 *__restrict__ g_lut2,
+	unsigned xRes, unsigned yRes, unsigned globalResX, float strength, float speed)
+{
+	// 2 LUT reads per pixel and 1 KB of output per block: the 16 KB table is read through L1 instead of being staged
+	const float2 *s_lut2 = g_lut2;
+
+	const unsigned iX = blockIdx.x*blockDim.x + threadIdx.x;
+	const int iY = int(blockIdx.y*blockDim.y + threadIdx.y);
+	if (iX >= xRes || unsigned(iY) >= yRes)
+		return;
+
+	const float dX = lutsinf(s_lut2, float(iY)*speed)*strength*1.f;
+	const float dY = lutcosf(s_lut2, float(iX)*speed)*strength*1.f;
+	float tX = float(iX) + dX;
+	float tY = float(iY) + dY;
+
+	if (tX < 0.f) tX = 0.f;
+	else if (tX >= float(xRes)-1.f) tX = float(xRes) - 2.f;
+	if (tY < 0.f) tY = 0.f;
+	else if (tY >= float(yRes)-1.f) tY = float(yRes) - 2.f;
+
+	const int U = ftofp24(tX), V = ftofp24(tY);
+	const unsigned U0 = unsigned(U >> 8);
+	const unsigned V0 = unsigned(V >> 8)*globalResX; // the reference strides by kResX, not xRes (util.cpp:594)
+	const uint32_t *p = pSrc + U0 + V0;
+	const uint32_t s0 = __ldg(p), s1 = __ldg(p + 1), s2 = __ldg(p + globalResX), s3 = __ldg(p + globalResX + 1);
+	pDest[size_t(iY)*xRes + iX] = bilerp_argb(s0, s1, s2, s3, U & 0xff, V & 0xff);
+}
+
+extern "C" int ckd_tape_warp(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength, float speed)
+{
+	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
+	CKD_REQUIRE(d_dest != d_src, "TapeWarp32 cannot run in place");
+	const dim3 block(64, 4);
+	const dim3 grid(ckd_div_up(x_res, block.x), ckd_div_up(y_res, block.y));
+	tape_warp_kernel<<<grid, block, 0, ctx->stream>>>(d_dest, d_src, ctx->d_cosLUT2, x_res, y_res, unsigned(ctx->resX), strength, speed);
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}

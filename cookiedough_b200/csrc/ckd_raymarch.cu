@@ -1,0 +1,877 @@
+// ckd_raymarch.cu -- the Shadertoy-style raymarchers of shadertoy.cpp as sm_100a kernels.
+//
+// One thread per FX-map pixel (the reference renders 4 pixels per SSE store; here a pixel is a thread), 32x8 pixel
+// tiles walked by a persistent grid (a multiple of the SM count) so the interpolated-cosine LUT is staged into shared
+// memory once per CTA.  The march loops are FP32 FMUL/FADD chains (no FMA contraction: the reference has none) plus
+// LDS for the LUT; pow/exp/atan2 are the only double-precision ops.  Output goes to the FX map exactly like the
+// reference; Fx_Blit_2x2 and the optional blur/blend chain follow as separate HBM-bound kernels (ckd_post.cu).
+
+#include "ckd_internal.h"
+#include "ckd_math.cuh"
+#include "ckd_hostmath.h"
+
+using namespace ckd;
+
+namespace {
+
+constexpr int kTileX = 32, kTileY = 8;
+
+struct FrameGeom
+{
+	int fxX, fxY;
+	float invFxX, invFxY;     // 1.f/kFxMapResX, 1.f/kFxMapResY (shadertoy-util.h:125-128)
+	float aspect, oneOverAspect; // kAspect, kOneOverAspect (main.h:43-44)
+};
+
+// Shadertoy::ToUV_FxMap, shadertoy-util.h:123-130
+__device__ __forceinline__ void to_uv_fxmap(const FrameGeom &g, unsigned iX, unsigned iY, float scale, float &u, float &v)
+{
+	float fX = float(iX), fY = float(iY);
+	fX *= g.invFxX;
+	fY *= g.invFxY;
+	u = (fX-0.5f)*scale*g.oneOverAspect;
+	v = (fY-0.5f)*scale;
+}
+
+struct Rot { float cosine, sine; }; // lutcosf(angle), lutsinf(angle) evaluated once per frame on the host
+
+__device__ __forceinline__ void rot_z(const Rot r, float &X, float &Y) { const float rX = r.cosine*X + r.sine*Y, rY = -r.sine*X + r.cosine*Y; X = rX; Y = rY; }
+__device__ __forceinline__ void rot_x(const Rot r, float &Y, float &Z) { const float rY = r.cosine*Y + -r.sine*Z, rZ = r.sine*Y + r.cosine*Z; Y = rY; Z = rZ; }
+__device__ __forceinline__ void rot_y(const Rot r, float &X, float &Z) { const float rX = r.cosine*X + r.sine*Z, rZ = -r.sine*X + r.cosine*Z; X = rX; Z = rZ; }
+
+// lerp to a constant per lane: Shadertoy::vLerp4(A, B, f) = A + f*(B-A), shadertoy-util.h:62-67
+__device__ __forceinline__ float vlerp(float a, float b, float f) { return a + f*(b-a); }
+
+struct Env
+{
+	const float2 *lut;   // shared-memory cosine LUT
+	RsqrtTab rsqrt;
+	FrameGeom geom;
+};
+
+// -------------------------------------------------------------------------------------------------------------
+// Plasma -- shadertoy.cpp:201-274
+// -------------------------------------------------------------------------------------------------------------
+
+struct PlasmaFrame
+{
+	float time;                 // time*speed
+	float dirCos, dirSin;
+	float colMulA[3], colMulB[3];
+	float gamma;
+};
+
+__device__ __forceinline__ float fPlasma(const float2 *lut, float px, float py, float pz, float time)
+{
+	const float sine = 0.2f*lutsinf(lut, px-py);
+	const float fX = sine + lutcosf(lut, px*0.33f);
+	const float fY = sine + lutcosf(lut, py*0.43f);
+	const float fZ = sine + lutcosf(lut, (5.f*time+pz)*0.53f);
+	return sqrtf(fX*fX + fY*fY + fZ*fZ)-0.8f;
+}
+
+struct PlasmaEffect
+{
+	PlasmaFrame f;
+	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	{
+		float u, v;
+		to_uv_fxmap(e.geom, iX, iY, 4.f, u, v);
+
+		const float dx = f.dirCos*u*e.geom.aspect - f.dirSin*0.75f;
+		const float dy = v;
+		const float dz = f.dirSin*u + f.dirCos*0.75f;
+
+		float total = 0.f, march = 0.f;
+		float hx = 0.f, hy = 0.f, hz = 0.f;
+		#pragma unroll 1
+		for (int iStep = 0; iStep < 24; ++iStep)
+		{
+			march = fPlasma(e.lut, hx, hy, hz, f.time);
+			total += march*(0.5f*kGoldenRatio);
+			hx = dx*total;
+			hy = dy*total;
+			hz = dz*total;
+		}
+
+		const float second = fPlasma(e.lut, hx*0.5f, hy*0.5f, hz*0.5f, f.time);
+		const float mul = 8.f - dx*0.5f;
+		const float b = (f.colMulA[0]*march + f.colMulB[0]*second)*mul;
+		const float g = (f.colMulA[1]*march + f.colMulB[1]*second)*mul;
+		const float r = (f.colMulA[2]*march + f.colMulB[2]*second)*mul;
+
+		// the 4th lane of a Vector3 colour is 0: log_ps(0) = NaN -> exp_ps -> huge -> converts to 0
+		return to_pixel(gamma_adj1(b, f.gamma), gamma_adj1(g, f.gamma), gamma_adj1(r, f.gamma), gamma_adj1(0.f, f.gamma));
+	}
+};
+
+// -------------------------------------------------------------------------------------------------------------
+// Nautilus -- shadertoy.cpp:288-393
+// -------------------------------------------------------------------------------------------------------------
+
+struct NautilusFrame
+{
+	float time;               // time*speed
+	float gx, gy, gz;         // fNautilus_global
+	float diffColor[3];
+	float cosHitOffs, funkCos;
+	Rot roll;
+};
+
+__device__ __forceinline__ float fNautilus(const float2 *lut, const NautilusFrame &f, float px, float py, float pz)
+{
+	const float cosX = lutcosf(lut, lutcosf(lut, px + f.gx)*px - lutcosf(lut, py + f.gy)*py);
+	const float cosY = lutcosf(lut, pz*0.33f*px - f.gz*py);
+	const float cosZ = lutcosf(lut, px + py + pz*0.8f + f.time);
+	const float dotted = cosX*cosX + cosY*cosY + cosZ*cosZ;
+	return dotted*0.5f - .7f;
+}
+
+struct NautilusEffect
+{
+	NautilusFrame f;
+	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	{
+		float u, v;
+		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
+
+		vec3 dir = { u*e.geom.aspect, v, 1.f };
+		rot_z(f.roll, dir.x, dir.y);
+		fast_norm3(e.rsqrt, dir);
+
+		float hx = 0.f, hy = 0.f, hz = 0.f;
+		float total = 0.01f, march = 1.f;
+		#pragma unroll 1
+		for (int iStep = 0; march > 0.01f && iStep < 48; ++iStep)
+		{
+			hx = dir.x*total;
+			hy = dir.y*total;
+			hz = dir.z*total;
+			march = fNautilus(e.lut, f, hx, hy, hz);
+			total += march*0.628f;
+		}
+
+		constexpr float nOffs = 0.15f;
+		vec3 normal = {
+			march-fNautilus(e.lut, f, hx+nOffs, hy, hz),
+			march-fNautilus(e.lut, f, hx, hy+nOffs, hz),
+			march-fNautilus(e.lut, f, hx, hy, hz+nOffs) };
+		fast_norm3(e.rsqrt, normal);
+
+		float diffuse = normal.z*0.1f;
+		const float specular = powf_ref(stdmax(0.f, dot3(normal, dir)), 16.f);
+
+		const float ox = hx + f.cosHitOffs, oy = hy + f.cosHitOffs, oz = hz + f.cosHitOffs;
+		vec3 funk = {
+			march-fNautilus(e.lut, f, ox+nOffs, oy, oz),
+			march-fNautilus(e.lut, f, ox, oy+nOffs, oz),
+			march-fNautilus(e.lut, f, ox, oy, oz+nOffs) };
+		fast_norm3(e.rsqrt, funk);
+
+		const float yMod = fracf(hy*0.3f + funk.x*0.628f + funk.y*f.funkCos);
+		diffuse *= yMod*yMod*yMod;
+
+		const float s = 1.56f*total + specular;
+		const float add = specular*kGoldenRatio*0.2f;
+		const float b = (diffuse + f.diffColor[0]*s) + add;
+		const float g = (diffuse + f.diffColor[1]*s) + add;
+		const float r = (diffuse + f.diffColor[2]*s) + add;
+
+		return to_pixel(gamma_adj1(b, 1.44f), gamma_adj1(g, 1.44f), gamma_adj1(r, 1.44f), gamma_adj1(0.f, 1.44f));
+	}
+};
+
+// -------------------------------------------------------------------------------------------------------------
+// Spikey (close / distant / specular only) -- shadertoy.cpp:416-659
+// -------------------------------------------------------------------------------------------------------------
+
+struct SpikeyFrame
+{
+	float gx, gy, gz;         // fSpike_global.xyz
+	float diffColor[4];       // all four lanes feed the pixel
+	Rot roll;
+	float specPow, gamma;
+	float xOffs, yOffs, zTerm; // close: dir.z = 1+zOffsFinal; distant: origin.z = -2.614+zOffs
+	float normalGrain;
+	float warmup;
+};
+
+template <bool GOLDEN_ANGLE>
+__device__ __forceinline__ float fSpikey(const float2 *lut, const SpikeyFrame &f, float px, float py, float pz)
+{
+	// fSpikey1 (kGoldenAngle) / fSpikey2 (kGoldenRatio), shadertoy.cpp:418-430
+	constexpr float scale = (GOLDEN_ANGLE ? kGoldenAngle : kGoldenRatio)*0.1f;
+	const float radius = 1.35f + scale*lutcosf(lut, f.gy*py - f.gx) + scale*lutcosf(lut, f.gz*px + f.gx);
+	const vec3 p = { px, py, pz };
+	return fast_len3(p) - radius;
+}
+
+struct SpikeyCloseEffect
+{
+	SpikeyFrame f;
+	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	{
+		float u, v;
+		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
+
+		const float ox = 0.2f, oy = 0.f, oz = -2.23f;
+		vec3 dir = { (u+f.xOffs)*e.geom.aspect, v + f.yOffs, f.zTerm };
+		rot_z(f.roll, dir.x, dir.y);
+		fast_norm3(e.rsqrt, dir);
+
+		float hx = 0.f, hy = 0.f, hz = 0.f;
+		float march = 1.f, total = 0.f;
+		#pragma unroll 1
+		for (int iStep = 0; march > 0.0001f && iStep < 32; ++iStep)
+		{
+			hx = ox + dir.x*total;
+			hy = oy + dir.y*total;
+			hz = oz + dir.z*total;
+			march = fSpikey<true>(e.lut, f, hx, hy, hz);
+			total += march*(0.05f*kPI);
+		}
+
+		const float nOffs = f.normalGrain;
+		vec3 normal = {
+			march-fSpikey<true>(e.lut, f, hx+nOffs, hy, hz),
+			march-fSpikey<true>(e.lut, f, hx, hy+nOffs, hz),
+			march-fSpikey<true>(e.lut, f, hx, hy, hz+nOffs) };
+		fast_norm3(e.rsqrt, normal);
+
+		// the 'rim' branch (shadertoy.cpp:504-511) multiplies by max(1, min(0, rim)) == 1: a no-op kept out of the kernel
+		const float diffuse = normal.z;
+		const float specular = powf_ref(stdmax(0.f, dot3(normal, dir)), f.specPow);
+		const float distance = hz-oz;
+		const float fog = exp_fog(distance, kGoldenRatio*0.1f);
+
+		float c[4];
+		#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			c[i] = gamma_adj1(vlerp((f.diffColor[i] + specular)*diffuse, 1.f, fog), f.gamma);
+		return to_pixel(c[0], c[1], c[2], c[3]);
+	}
+};
+
+struct SpikeyDistantEffect
+{
+	SpikeyFrame f;
+	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	{
+		float u, v;
+		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
+
+		const float ox = 0.f, oy = 0.f, oz = f.zTerm;
+		vec3 dir = { u + f.xOffs, v + f.yOffs, 1.f };
+		rot_z(f.roll, dir.x, dir.y);
+		fast_norm3(e.rsqrt, dir);
+
+		float hx = 0.f, hy = 0.f, hz = 0.f;
+		float march = 1.f, total = 0.f;
+		#pragma unroll 1
+		for (int iStep = 0; march > 0.001f && iStep < 48; ++iStep)
+		{
+			hx = ox + dir.x*total;
+			hy = oy + dir.y*total;
+			hz = oz + dir.z*total;
+			march = fSpikey<false>(e.lut, f, hx, hy, hz);
+			march *= 0.314f;
+			total += march;
+		}
+
+		constexpr float nOffs = kPI*0.02f;
+		vec3 normal = {
+			march-fSpikey<false>(e.lut, f, hx+nOffs, hy, hz),
+			march-fSpikey<false>(e.lut, f, hx, hy+nOffs, hz),
+			march-fSpikey<false>(e.lut, f, hx, hy, hz+nOffs) };
+		fast_norm3(e.rsqrt, normal);
+
+		const float diffuse = stdmax(0.f, normal.z*0.8f + normal.y*0.2f);
+		const float fakeSpecular = powf_ref(dot3(normal, dir), f.specPow); // unclamped base on purpose (shadertoy.cpp:586)
+		const float distance = hz-oz;
+		const float fog = exp_fog(distance, 0.133f);
+
+		float c[4];
+		#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			c[i] = gamma_adj1(vlerp((f.diffColor[i] + fakeSpecular)*diffuse, 1.f, fog), f.gamma);
+		return to_pixel(c[0], c[1], c[2], c[3]);
+	}
+};
+
+struct SpikeySpecOnlyEffect
+{
+	SpikeyFrame f;
+	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	{
+		float u, v;
+		to_uv_fxmap(e.geom, iX, iY, kGoldenRatio, u, v);
+
+		const float ox = 0.f, oy = 0.f, oz = -3.314f;
+		vec3 dir = { u*e.geom.aspect, v, 1.f };
+		rot_z(f.roll, dir.x, dir.y);
+		fast_norm3(e.rsqrt, dir);
+
+		float hx = 0.f, hy = 0.f, hz = 0.f;
+		float march = 1.f, total = 0.f;
+		#pragma unroll 1
+		for (int iStep = 0; iStep < 36; ++iStep)
+		{
+			hx = ox + dir.x*total;
+			hy = oy + dir.y*total;
+			hz = oz + dir.z*total;
+			march = fSpikey<false>(e.lut, f, hx, hy, hz);
+			total += march*0.075f*kGoldenRatio;
+		}
+
+		constexpr float nOffs = 0.01f;
+		vec3 normal = {
+			march-fSpikey<false>(e.lut, f, hx+nOffs, hy, hz),
+			march-fSpikey<false>(e.lut, f, hx, hy+nOffs, hz),
+			march-fSpikey<false>(e.lut, f, hx, hy, hz+nOffs) };
+		fast_norm3(e.rsqrt, normal);
+
+		const float distance = hz-oz;
+		const float fakeSpecular = f.warmup*powf_ref(stdmax(0.f, dot3(normal, dir)), f.specPow);
+		const float fogged = vlerp(fakeSpecular, 0.f, exp_fog(distance, 0.0133f));
+		const uint32_t chan = to_chan(fogged);
+		return chan*0x01010101u;
+	}
+};
+
+// -------------------------------------------------------------------------------------------------------------
+// Sinuses -- shadertoy.cpp:870-982
+// -------------------------------------------------------------------------------------------------------------
+
+struct SinusesFrame
+{
+	float origin[3];
+	float diffColor[4];
+	Rot roll;
+	float specPow, gamma, offsX;
+};
+
+__device__ __forceinline__ float fSinMap(const float2 *lut, float px0, float py0, float pZ)
+{
+	const float zMod = pZ*0.314f;
+	const float pathCos = lutcosf(lut, zMod);
+	const float pathCos2 = lutcosf(lut, zMod+(k2PI/4.f))*kGoldenRatio;
+	const float pX = px0-(pathCos2*2.f - pathCos*1.5f);
+	const float pY = py0-(pathCos*3.14f + pathCos2);
+
+	const float aX = pX*0.315f*1.25f + lutsinf(lut, pZ*(0.814f*1.25f));
+	const float aY = pY*0.315f*1.25f + lutsinf(lut, pX*(0.814f*1.25f));
+	const float aZ = pZ*0.315f*1.25f + lutsinf(lut, pY*(0.814f*1.25f));
+
+	const float cosX = lutcosf(lut, aX);
+	const float cosY = lutcosf(lut, aY);
+	const float cosZ = lutcosf(lut, aZ);
+
+	const float length = sqrtf(cosX*cosX + cosY*cosY + cosZ*cosZ);
+	return (length - 1.025f)*1.33f;
+}
+
+struct SinusesEffect
+{
+	SinusesFrame f;
+	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	{
+		float u, v;
+		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
+
+		vec3 dir = { (u+f.offsX)*e.geom.aspect, v, 0.314f };
+		rot_z(f.roll, dir.x, dir.y);
+		fast_norm3(e.rsqrt, dir);
+
+		float hx = 0.f, hy = 0.f, hz = 0.f;
+		float march = 1.f, total = 0.f;
+		#pragma unroll 1
+		for (int iStep = 0; march > 0.01f && iStep < 32; ++iStep)
+		{
+			hx = f.origin[0] + dir.x*total;
+			hy = f.origin[1] + dir.y*total;
+			hz = f.origin[2] + dir.z*total;
+			march = fSinMap(e.lut, hx, hy, hz);
+			total += march*0.814f;
+		}
+
+		constexpr float nOffs = 0.2f;
+		vec3 normal = {
+			march-fSinMap(e.lut, hx+nOffs, hy, hz),
+			march-fSinMap(e.lut, hx, hy+nOffs, hz),
+			march-fSinMap(e.lut, hx, hy, hz+nOffs) };
+		fast_norm3(e.rsqrt, normal);
+
+		float diffuse = normal.z*0.7f + 0.3f*normal.y;
+		diffuse = 0.2f + 0.8f*diffuse;
+
+		const float specDot = dot3(normal, dir);
+		const float fakeSpecular = powf_ref(specDot, f.specPow);
+		const float distance = hz-f.origin[2];
+		const float fog = exp_fog(distance, 0.03f);
+
+		float c[4];
+		#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			c[i] = gamma_adj1(vlerp((f.diffColor[i] + fakeSpecular)*diffuse, 1.f, fog), f.gamma);
+		return to_pixel(c[0], c[1], c[2], c[3]);
+	}
+};
+
+// -------------------------------------------------------------------------------------------------------------
+// Laura -- shadertoy.cpp:998-1103, Shadertoy::Specular shadertoy-util.h:252-280
+// -------------------------------------------------------------------------------------------------------------
+
+struct LauraFrame
+{
+	float originZ;
+	float diffColor[4];
+	Rot yaw, pitch, roll;
+};
+
+__device__ __forceinline__ float fLaura(const float2 *lut, float px, float py, float pz)
+{
+	return lutcosf(lut, px)+lutcosf(lut, py)+lutcosf(lut, pz) + 1.f;
+}
+
+struct LauraEffect
+{
+	LauraFrame f;
+	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	{
+		float u, v;
+		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
+
+		vec3 dir = { u*e.geom.aspect, v, kPI };
+		rot_y(f.yaw, dir.x, dir.z);
+		rot_x(f.pitch, dir.y, dir.z);
+		rot_z(f.roll, dir.x, dir.y);
+		fast_norm3(e.rsqrt, dir);
+
+		const vec3 origin = { 0.f, 0.f, f.originZ };
+		vec3 hit = { 0.f, 0.f, 0.f };
+		float march = 0.f, total = 0.f;
+		#pragma unroll 1
+		for (int iStep = 0; iStep < 32; ++iStep)
+		{
+			hit.x = origin.x + dir.x*total;
+			hit.y = origin.y + dir.y*total;
+			hit.z = origin.z + dir.z*total;
+			march = fLaura(e.lut, hit.x, hit.y, hit.z);
+			total += march*0.5f;
+		}
+
+		// LauraNormal, shadertoy.cpp:1003-1015
+		constexpr float nOffs = 0.1628f;
+		vec3 normal = {
+			fLaura(e.lut, hit.x+nOffs, hit.y, hit.z)-march,
+			fLaura(e.lut, hit.x, hit.y+nOffs, hit.z)-march,
+			fLaura(e.lut, hit.x, hit.y, hit.z+nOffs)-march };
+		fast_norm3(e.rsqrt, normal);
+
+		const vec3 lightPos = { origin.x-dir.x, origin.y-dir.y, origin.z-dir.z };
+		vec3 lightDir = { lightPos.x-hit.x, lightPos.y-hit.y, lightPos.z-hit.z };
+		fast_norm3(e.rsqrt, lightDir);
+
+		float diffuse = stdmax(0.3f, dot3(normal, lightDir));
+		const float distance = hit.z-origin.z;
+
+		// Shadertoy::Specular(origin, hit, normal, lightDir, 4.f)
+		float specular;
+		{
+			vec3 V = { origin.x-hit.x, origin.y-hit.y, origin.z-hit.z };
+			const float oneOverLenV = rsqrt_x86(e.rsqrt, dp_ps3(V, V));
+			V.x *= oneOverLenV; V.y *= oneOverLenV; V.z *= oneOverLenV;
+			vec3 H = { lightDir.x+V.x, lightDir.y+V.y, lightDir.z+V.z };
+			const float oneOverLenH = rsqrt_x86(e.rsqrt, dp_ps3(H, H));
+			H.x *= oneOverLenH; H.y *= oneOverLenH; H.z *= oneOverLenH;
+			const float cosAng = dp_ps3(normal, H);
+			specular = (0 == (__float_as_uint(cosAng) >> 31)) ? powf_ref(cosAng, 4.f) : 0.f;
+		}
+
+		// rim (shadertoy.cpp:1085-1088) evaluates to max(1, min(0, rim)) == 1
+		diffuse *= 1.f;
+
+		const float fogColor = q3_rsqrtf2(specular+diffuse);
+		const float fog = exp_fog(distance, 0.001f);
+		const float lit = diffuse+specular;
+
+		float c[4];
+		#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			c[i] = gamma_adj1(vlerp(f.diffColor[i]*lit, fogColor, fog), 1.44f);
+		return to_pixel(c[0], c[1], c[2], c[3]);
+	}
+};
+
+// -------------------------------------------------------------------------------------------------------------
+// generic persistent tile kernel
+// -------------------------------------------------------------------------------------------------------------
+
+template <class Effect>
+__global__ void __launch_bounds__(kTileX*kTileY) raymarch_kernel(const Effect effect, uint32_t *__restrict__ pDest, const FrameGeom geom,
+	const float2 *__restrict__ g_lut2, const RsqrtTab rsqrt, int tilesX, int numTiles)
+{
+	__shared__ float2 s_lut2[2048];
+	stage_cos_lut(s_lut2, g_lut2);
+	__syncthreads();
+
+	Env env = { s_lut2, rsqrt, geom };
+
+	for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x)
+	{
+		const int tY = tile / tilesX, tX = tile - tY*tilesX;
+		const unsigned iX = tX*kTileX + threadIdx.x;
+		const unsigned iY = tY*kTileY + threadIdx.y;
+		if (iX < unsigned(geom.fxX) && iY < unsigned(geom.fxY))
+			pDest[size_t(iY)*geom.fxX + iX] = effect.shade(env, iX, iY);
+	}
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Free-directional tunnel -- shadertoy.cpp:746-838 (writes two maps)
+// -------------------------------------------------------------------------------------------------------------
+
+struct TunnelFrame
+{
+	float boxy, flowerScale, flowerFreq, flowerPhase;
+	float timeSpeed;          // (time*speed)*speed: 'time *= speed' then 'time*speed' (shadertoy.cpp:767,802)
+	Rot roll, pitch;
+	float radius, uMul, vMul;
+	float fog0, fog1;
+};
+
+__device__ __forceinline__ void tunnel_sample(const uint32_t *__restrict__ tex, int fpU, int fpV, float out[4])
+{
+	// bsamp_prepUVs(…, 1023, 10, …) + bsamp32_32f, bilinear.h:10-31, 86-135
+	const unsigned U0 = unsigned(fpU >> 8), V0 = unsigned(fpV >> 8);
+	const unsigned u0 = U0 & 1023, u1 = (U0+1) & 1023;
+	const unsigned v0 = (V0 & 1023) << 10, v1 = ((V0+1) & 1023) << 10;
+	const uint32_t s = bilerp_argb(__ldg(tex + u0 + v0), __ldg(tex + u1 + v0), __ldg(tex + u0 + v1), __ldg(tex + u1 + v1), fpU & 0xff, fpV & 0xff);
+	out[0] = float(s & 0xff); out[1] = float((s >> 8) & 0xff); out[2] = float((s >> 16) & 0xff); out[3] = float(s >> 24);
+}
+
+__global__ void __launch_bounds__(kTileX*kTileY) tunnel_kernel(const TunnelFrame f, uint32_t *__restrict__ pDest, uint32_t *__restrict__ pGlowDest,
+	const uint32_t *__restrict__ tex, const uint32_t *__restrict__ texGlow, const FrameGeom geom, const float2 *__restrict__ g_lut2, const RsqrtTab rsqrt, int tilesX, int numTiles)
+{
+	__shared__ float2 s_lut2[2048];
+	stage_cos_lut(s_lut2, g_lut2);
+	__syncthreads();
+
+	for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x)
+	{
+		const int tY = tile / tilesX, tX = tile - tY*tilesX;
+		const unsigned iX = tX*kTileX + threadIdx.x;
+		const unsigned iY = tY*kTileY + threadIdx.y;
+		if (iX >= unsigned(geom.fxX) || iY >= unsigned(geom.fxY))
+			continue;
+
+		float u, v;
+		to_uv_fxmap(geom, iX, iY, 2.f, u, v);
+		vec3 dir = { u, v, 1.f };
+		rot_x(f.pitch, dir.y, dir.z);
+		rot_z(f.roll, dir.x, dir.y);
+		fast_norm3(rsqrt, dir);
+
+		float A = dir.x*dir.x + dir.y*dir.y;
+		A += f.flowerScale*lutcosf(s_lut2, atan2f_ref(dir.y, dir.x)*f.flowerFreq + f.flowerPhase);
+
+		const float absX = fabsf(dir.x), absY = fabsf(dir.y);
+		const float box = absX > absY ? absX : absY;
+		A = smoothstepf(A, box, f.boxy);
+		A += kEpsilon;
+		A = 1.f/A;
+		const float T = f.radius*A;
+		const float T2 = T*0.912f;
+		const float ix = dir.x*T, iy = dir.y*T, iz = dir.z*T;
+		const float ix2 = dir.x*T2, iy2 = dir.y*T2, iz2 = dir.z*T2;
+
+		const float U = atan2f_ref(iy, ix)/kPI;
+		const float V = iz + f.timeSpeed;
+		const float U2 = atan2f_ref(iy2, ix2)/kPI;
+		const float V2 = iz2 + f.timeSpeed;
+
+		const int fpU = ftofp24(U*f.uMul), fpV = ftofp24(V*f.vMul);
+		const int fpU2 = ftofp24(U2*f.uMul), fpV2 = ftofp24(V2*f.vMul);
+
+		const float shade = clampf(0.f, 1.f, 1.f-expf_ref(-0.006f*T*T));
+
+		float color[4], glow[4];
+		tunnel_sample(tex, fpU, fpV, color);
+		tunnel_sample(texGlow, fpU2, fpV2, glow);
+
+		uint32_t px = 0, gpx = 0;
+		#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			px |= to_chan_noconv(vlerp(color[i], f.fog0, shade)) << (8*i);
+			gpx |= to_chan_noconv(vlerp(glow[i], f.fog1, shade)) << (8*i);
+		}
+
+		const size_t index = size_t(iY)*geom.fxX + iX;
+		pDest[index] = px;
+		pGlowDest[index] = gpx;
+	}
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------------------
+
+FrameGeom MakeGeom(const ckd_ctx *ctx)
+{
+	FrameGeom g;
+	g.fxX = ctx->fxX;
+	g.fxY = ctx->fxY;
+	g.invFxX = 1.f/float(ctx->fxX);
+	g.invFxY = 1.f/float(ctx->fxY);
+	g.aspect = float(ctx->resY)/float(ctx->resX);
+	g.oneOverAspect = 1.f/g.aspect;
+	return g;
+}
+
+Rot MakeRot(const ckd_ctx *ctx, float angle)
+{
+	return { ckdh::lutcosf(ctx->h_cosLUT, angle), ckdh::lutsinf(ctx->h_cosLUT, angle) };
+}
+
+template <class Effect> int LaunchRaymarch(ckd_ctx *ctx, const Effect &effect, uint32_t *d_fxmap)
+{
+	const FrameGeom geom = MakeGeom(ctx);
+	const int tilesX = ckd_div_up(geom.fxX, kTileX), tilesY = ckd_div_up(geom.fxY, kTileY);
+	const int numTiles = tilesX*tilesY;
+	const int blocks = std::min(numTiles, ctx->numSMs*8);
+	const RsqrtTab rsqrt = { ctx->d_rsqrtTab, ctx->rsqrtLog2Bin };
+	raymarch_kernel<Effect><<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(effect, d_fxmap, geom, ctx->d_cosLUT2, rsqrt, tilesX, numTiles);
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}
+
+void CopyColor(float *dst, const ckdh::vec4 &c, int n)
+{
+	const float src[4] = { c.x, c.y, c.z, c.w };
+	for (int i = 0; i < n; ++i) dst[i] = src[i];
+}
+
+} // namespace
+
+// Plasma_Draw, shadertoy.cpp:276-280
+extern "C" int ckd_plasma_draw(ckd_ctx *ctx, const ckd_plasma_params *p, float time, uint32_t *d_dest)
+{
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	const float *lut = ctx->h_cosLUT;
+
+	PlasmaEffect fx;
+	const ckdh::vec4 colMulA = ckdh::Desaturate(ckdh::MichielPal(lut, p->hue), p->desaturation);
+	const ckdh::vec4 colMulB = ckdh::Desaturate(colMulA, 0.8f);
+	CopyColor(fx.f.colMulA, colMulA, 3);
+	CopyColor(fx.f.colMulB, colMulB, 3);
+	time = time*p->speed;
+	const float angle = time*0.314f*0.5f;
+	fx.f.time = time;
+	fx.f.dirCos = ckdh::lutcosf(lut, angle);
+	fx.f.dirSin = ckdh::lutsinf(lut, angle);
+	fx.f.gamma = p->gamma;
+
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+}
+
+// Nautilus_Draw, shadertoy.cpp:395-407
+extern "C" int ckd_nautilus_draw(ckd_ctx *ctx, const ckd_nautilus_params *p, float time, uint32_t *d_dest)
+{
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	const float *lut = ctx->h_cosLUT;
+
+	NautilusEffect fx;
+	time = time*p->speed;
+	fx.f.time = time;
+	fx.f.gx = time*0.125f;
+	fx.f.gy = time/9.f;
+	fx.f.gz = ckdh::lutcosf(lut, time*0.1428f);
+	const ckdh::vec4 colorization = { .1f-ckdh::lutcosf(lut, p->hue/3.f)/19.f, .1f, .1f+ckdh::lutcosf(lut, p->hue/14.f)/8.f, 0.f };
+	CopyColor(fx.f.diffColor, ckdh::Desaturate(colorization, p->desaturation), 3);
+	fx.f.cosHitOffs = ckdh::lutcosf(lut, time*0.314f*0.5f);
+	fx.f.funkCos = ckdh::lutcosf(lut, time*ckdh::kGoldenRatio*0.1f);
+	fx.f.roll = MakeRot(ctx, p->roll*time);
+
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	CKD_TRY(ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]));
+	const float blur = ckdh::BoxBlurScale(p->blur);
+	if (0.f != blur)
+		CKD_TRY(ckd_old_blur(ctx, d_dest, d_dest, unsigned(ctx->resX), unsigned(ctx->resY), blur));
+	return CKD_OK;
+}
+
+// Spikey_Draw, shadertoy.cpp:661-733
+extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float time, int close, uint32_t *d_dest)
+{
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	const float *lut = ctx->h_cosLUT;
+	const unsigned fxSize = unsigned(ctx->fxX)*unsigned(ctx->fxY);
+	const float aspect = float(ctx->resY)/float(ctx->resX);
+
+	SpikeyFrame f = {};
+	f.roll = MakeRot(ctx, p->roll);
+	f.specPow = p->specular;
+	f.gamma = p->gamma;
+	CopyColor(f.diffColor, ckdh::Desaturate(ckdh::MichielPal(lut, p->hue), p->desaturation), 4);
+
+	if (close)
+	{
+		CKD_REQUIRE(ctx->images[CKD_IMG_SPIKE_BLUR_MAP0].d_pixels && ctx->images[CKD_IMG_SPIKE_BLUR_MAP1].d_pixels, "spike blur maps not uploaded");
+
+		// RenderSpikeyMap_2x2_Close, shadertoy.cpp:432-458
+		const float zOffsFinal = ckdh::easeInOutElasticf(p->close_z)*p->close_z_scale;
+		f.gx = p->speed*time;
+		f.gy = 16.f*p->close_scale;
+		f.gz = (0 == p->close_aspect_mul) ? 22.f*p->close_scale : aspect*22.f*p->close_scale;
+		f.xOffs = p->close_x;
+		f.yOffs = p->close_y;
+		f.zTerm = 1.f + zOffsFinal;
+		f.normalGrain = p->close_normal_grain;
+		SpikeyCloseEffect fx = { f };
+		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+
+		const float mbOpacity = ckdh::saturatef(p->mix_blur_opacity);
+		if (mbOpacity > 0.f)
+		{
+			// shadertoy.cpp:672-707
+			const float mbMap = ckdh::clampf(0, 1.f, p->mix_blur_map);
+			const float mbBlur = ckdh::clampf(0.f, 100.f, p->mix_blur);
+			const float mbMapBlur = ckdh::clampf(0.f, 100.f, p->mix_map_blur);
+			const size_t fxBytes = size_t(fxSize)*4;
+			const void *map0 = ctx->images[CKD_IMG_SPIKE_BLUR_MAP0].d_pixels, *map1 = ctx->images[CKD_IMG_SPIKE_BLUR_MAP1].d_pixels;
+
+			if (0.f == mbMap)
+				CKD_CUDA(cudaMemcpyAsync(ctx->d_spikeBlurMap, map0, fxBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+			else if (1.f == mbMap)
+				CKD_CUDA(cudaMemcpyAsync(ctx->d_spikeBlurMap, map1, fxBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+			else
+			{
+				CKD_CUDA(cudaMemcpyAsync(ctx->d_spikeBlurMap, map0, fxBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+				CKD_TRY(ckd_blend(ctx, CKD_MIX32, ctx->d_spikeBlurMap, static_cast<const uint32_t *>(map1), fxSize, 0.f, ckdh::x86_f2u(mbMap*255.f) & 0xff));
+			}
+
+			CKD_CUDA(cudaMemcpyAsync(ctx->d_fxMap[1], ctx->d_fxMap[0], fxBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+
+			if (mbMapBlur >= 1.f)
+				CKD_TRY(ckd_old_blur(ctx, ctx->d_spikeBlurMap, ctx->d_spikeBlurMap, unsigned(ctx->fxX), unsigned(ctx->fxY), ckdh::BoxBlurScale(mbMapBlur)));
+			if (mbBlur >= 1.f)
+				CKD_TRY(ckd_old_blur(ctx, ctx->d_fxMap[1], ctx->d_fxMap[1], unsigned(ctx->fxX), unsigned(ctx->fxY), ckdh::BoxBlurScale(mbBlur)));
+
+			CKD_TRY(ckd_blend(ctx, CKD_SOFTLIGHT32AA, ctx->d_fxMap[1], ctx->d_spikeBlurMap, fxSize, tanhf(mbBlur+mbOpacity), 0));
+			CKD_TRY(ckd_blend(ctx, CKD_OVERLAY32A, ctx->d_fxMap[0], ctx->d_fxMap[1], fxSize, 0.f, 0));
+		}
+		return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+	}
+
+	const float warmup = p->warmup;
+	if (0.f == warmup)
+	{
+		// RenderSpikeyMap_2x2_Distant, shadertoy.cpp:525-544
+		f.gx = p->speed*time; f.gy = 16.f; f.gz = 16.f;
+		f.xOffs = p->dist_x;
+		f.yOffs = p->dist_y;
+		f.zTerm = -2.614f + p->dist_z;
+		SpikeyDistantEffect fx = { f };
+		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+		return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+	}
+
+	// RenderSpikeyMap_2x2_Distant_SpecularOnly(…, 1.f+warmup), shadertoy.cpp:600-608, 727-729
+	f.gx = p->speed*time; f.gy = 8.f; f.gz = 16.f;
+	f.warmup = 1.f+warmup;
+	SpikeySpecOnlyEffect fx = { f };
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	CKD_TRY(ckd_old_blur_h(ctx, ctx->d_fxMap[0], ctx->d_fxMap[0], unsigned(ctx->fxX), unsigned(ctx->fxY), ckdh::BoxBlurScale(1.f+warmup)));
+	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+}
+
+// Tunnel_Draw, shadertoy.cpp:840-861
+extern "C" int ckd_tunnel_draw(ckd_ctx *ctx, const ckd_tunnel_params *p, float time, uint32_t *d_dest)
+{
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	const ckd_image_slot &tex = ctx->images[CKD_IMG_TUNNEL_TEX], &texFx = ctx->images[CKD_IMG_TUNNEL_TEX_FX];
+	if (!tex.d_pixels || !texFx.d_pixels || tex.width != 1024 || tex.height != 1024 || texFx.width != 1024 || texFx.height != 1024 || tex.bpp != 4 || texFx.bpp != 4)
+	{
+		ckd_set_error("ckd_tunnel_draw: the two 1024x1024 BGRA tunnel textures have not been uploaded (shadertoy.cpp:174-175)");
+		return CKD_ERR_MISSING_INPUT;
+	}
+
+	TunnelFrame f;
+	f.boxy = p->boxy;
+	f.flowerScale = p->flower_scale;
+	f.flowerFreq = p->flower_freq;
+	f.flowerPhase = p->flower_phase*time;
+	f.roll = MakeRot(ctx, p->roll*time);
+	f.pitch = MakeRot(ctx, p->pitch*time);
+	f.radius = p->radius;
+	f.uMul = p->mul_u;
+	f.vMul = p->mul_v;
+	f.fog0 = p->fog1;
+	f.fog1 = p->fog2;
+	time *= p->speed;
+	f.timeSpeed = time*p->speed;
+
+	const FrameGeom geom = MakeGeom(ctx);
+	const int tilesX = ckd_div_up(geom.fxX, kTileX), tilesY = ckd_div_up(geom.fxY, kTileY);
+	const int numTiles = tilesX*tilesY;
+	const int blocks = std::min(numTiles, ctx->numSMs*8);
+	const RsqrtTab rsqrt = { ctx->d_rsqrtTab, ctx->rsqrtLog2Bin };
+	tunnel_kernel<<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(f, ctx->d_fxMap[0], ctx->d_fxMap[1],
+		static_cast<const uint32_t *>(tex.d_pixels), static_cast<const uint32_t *>(texFx.d_pixels), geom, ctx->d_cosLUT2, rsqrt, tilesX, numTiles);
+	CKD_CHECK_LAUNCH(ctx);
+
+	const float litBlur = ckdh::clampf(0.f, 100.f, p->lit_blur);
+	if (0 != p->lit_tiles)
+	{
+		const unsigned fxSize = unsigned(ctx->fxX)*unsigned(ctx->fxY);
+		if (litBlur >= 1.f)
+			CKD_TRY(ckd_old_blur(ctx, ctx->d_fxMap[1], ctx->d_fxMap[1], unsigned(ctx->fxX), unsigned(ctx->fxY), ckdh::BoxBlurScale(litBlur)));
+		CKD_TRY(ckd_blend(ctx, CKD_ADD32, ctx->d_fxMap[0], ctx->d_fxMap[1], fxSize, 0.f, 0));
+	}
+	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+}
+
+// Sinuses_Draw, shadertoy.cpp:984-988
+extern "C" int ckd_sinuses_draw(ckd_ctx *ctx, const ckd_sinuses_params *p, float time, uint32_t *d_dest)
+{
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	const float *lut = ctx->h_cosLUT;
+
+	SinusesEffect fx;
+	fx.f.specPow = 1.f + p->specular;
+	fx.f.roll = MakeRot(ctx, p->roll);
+	fx.f.offsX = p->offs_x;
+	fx.f.gamma = p->gamma;
+	CopyColor(fx.f.diffColor, ckdh::Desaturate(ckdh::MichielPal(lut, p->hue), p->desaturation), 4);
+
+	// fSinPath(time*speed), shadertoy.cpp:870-876
+	const float pathTime = time*p->speed;
+	const float timeMod = pathTime*0.314f;
+	const float sine = ckdh::lutsinf(lut, timeMod);
+	const float cosine = ckdh::lutcosf(lut, timeMod);
+	fx.f.origin[0] = sine*2.f*ckdh::kGoldenRatio - cosine*1.5f;
+	fx.f.origin[1] = cosine*3.14f + sine*ckdh::kGoldenRatio;
+	fx.f.origin[2] = pathTime;
+
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+}
+
+// Laura_Draw, shadertoy.cpp:1105-1109
+extern "C" int ckd_laura_draw(ckd_ctx *ctx, const ckd_laura_params *p, float time, uint32_t *d_dest)
+{
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	const float *lut = ctx->h_cosLUT;
+
+	LauraEffect fx;
+	CopyColor(fx.f.diffColor, ckdh::Desaturate(ckdh::MichielPal(lut, p->hue), p->saturate), 4);
+	fx.f.originZ = p->speed*time;
+	fx.f.yaw = MakeRot(ctx, p->yaw);
+	fx.f.pitch = MakeRot(ctx, p->pitch);
+	fx.f.roll = MakeRot(ctx, p->roll*time);
+
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+}

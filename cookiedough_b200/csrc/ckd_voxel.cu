@@ -1,0 +1,944 @@
+// ckd_voxel.cu -- voxel ray casters: landscape, tunnelscape, ball (beams / no beams), torus twister.
+//
+// The reference walks every ray front to back, one step at a time, keeping the highest (or lowest) projected height
+// drawn so far and emitting a Gouraud span (cspanISSE16) whenever a step pokes out above it.  Here a WARP owns a ray
+// and its 32 lanes own 32 consecutive steps: every lane samples its step (bilinear height + colour gathers out of
+// L2-resident maps), a warp prefix-min/max over the projected heights gives each lane the occlusion horizon it would
+// have seen in the serial loop, the visible lanes emit their spans (short ones per lane, long ones warp-cooperatively),
+// and the carry (horizon, previous height/colour, beam accumulator) moves on to the next 32 steps.  Spans are written
+// into a shared-memory line buffer pre-filled with the clear colour, so the reference's memset32 + scattered span
+// stores become exactly one coalesced write of every output pixel.
+
+#include "ckd_internal.h"
+#include "ckd_math.cuh"
+#include "ckd_hostmath.h"
+
+using namespace ckd;
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Color16 { int c[4]; }; // 16-bit lanes B,G,R,A of an unpacked pixel (c2vISSE16, util.h:125-127)
+
+__device__ __forceinline__ Color16 unpack16(uint32_t px)
+{
+	Color16 r;
+	r.c[0] = int(px & 0xff); r.c[1] = int((px >> 8) & 0xff); r.c[2] = int((px >> 16) & 0xff); r.c[3] = int(px >> 24);
+	return r;
+}
+
+__device__ __forceinline__ Color16 shfl_color(const Color16 &v, int srcLane)
+{
+	Color16 r;
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) r.c[i] = __shfl_sync(kFull, v.c[i], srcLane);
+	return r;
+}
+
+__device__ __forceinline__ Color16 shfl_up_color(const Color16 &v)
+{
+	Color16 r;
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) r.c[i] = __shfl_up_sync(kFull, v.c[i], 1);
+	return r;
+}
+
+// ---- texture sampling (bilinear.h) ----------------------------------------------------------------------------------
+
+struct TexCoords { unsigned i00, i10, i01, i11; uint32_t fu, fv; };
+
+// bsamp_prepUVs, bilinear.h:10-31
+__device__ __forceinline__ TexCoords prep_uvs(int U, int V, unsigned mapAnd, unsigned mapShift)
+{
+	unsigned U0 = unsigned(U >> 8), V0 = unsigned(V >> 8);
+	unsigned U1 = U0 + 1, V1 = V0 + 1;
+	U0 &= mapAnd; V0 = (V0 & mapAnd) << mapShift;
+	U1 &= mapAnd; V1 = (V1 & mapAnd) << mapShift;
+	TexCoords t;
+	t.i00 = U0+V0; t.i10 = U1+V0; t.i01 = U0+V1; t.i11 = U1+V1;
+	t.fu = U & 0xff; t.fv = V & 0xff;
+	return t;
+}
+
+__device__ __forceinline__ unsigned sample_u8(const uint8_t *__restrict__ tex, const TexCoords &t)
+{
+	return bilerp_u8(__ldg(tex + t.i00), __ldg(tex + t.i10), __ldg(tex + t.i01), __ldg(tex + t.i11), int(t.fu), int(t.fv));
+}
+
+__device__ __forceinline__ uint32_t sample_argb(const uint32_t *__restrict__ tex, const TexCoords &t)
+{
+	return bilerp_argb(__ldg(tex + t.i00), __ldg(tex + t.i10), __ldg(tex + t.i01), __ldg(tex + t.i11), t.fu, t.fv);
+}
+
+// ---- cspanISSE16 (cspan.h:47-78) --------------------------------------------------------------------------------------
+// 16.16 fixed-point ramp from colour A to colour B over 'length' pixels of which the last... 'drawLength' are drawn, with
+// the reference's pmaddwd / pmuldq quirks restated literally: the divisor and the deltas are read as
+// pairs of signed 16-bit words, and the pre-step only reaches the B and R lanes.
+
+struct SpanRamp { uint32_t from[4]; int step[4]; };
+
+__device__ __forceinline__ int madd16(int a, int b)
+{
+	// one 32-bit lane of pmaddwd
+	return int(short(a & 0xffff))*int(short(b & 0xffff)) + int(short(a >> 16))*int(short(b >> 16));
+}
+
+__device__ __forceinline__ SpanRamp span_setup(unsigned length, unsigned drawLength, const Color16 &A, const Color16 &B)
+{
+	SpanRamp r;
+	const int divisor = int(65536u/length);
+	const unsigned preSteps = length - drawLength;
+	const long long prod = (long long)divisor*(long long)int(preSteps); // _mm_mul_epi32: lanes 0 and 2, 64-bit results
+	const int prodLo = int(prod & 0xffffffffll), prodHi = int(prod >> 32);
+	#pragma unroll
+	for (int i = 0; i < 4; ++i)
+	{
+		const int delta = B.c[i] - A.c[i];
+		const int preStep = madd16(delta, (i & 1) ? prodHi : prodLo);
+		r.step[i] = madd16(delta, divisor);
+		r.from[i] = (uint32_t(A.c[i]) << 16) + uint32_t(preStep);
+	}
+	return r;
+}
+
+__device__ __forceinline__ uint32_t span_pixel(const SpanRamp &r, unsigned j)
+{
+	uint32_t px = 0;
+	#pragma unroll
+	for (int i = 0; i < 4; ++i)
+	{
+		const uint32_t v = (r.from[i] + j*uint32_t(r.step[i])) >> 16; // psrld 16, then packusdw (no-op on 16 bits), packuswb
+		const uint32_t ch = (v > 32767u) ? 0u : min(v, 255u);
+		px |= ch << (8*i);
+	}
+	return px;
+}
+
+constexpr unsigned kShortSpan = 6; // spans up to this length are drawn by their own lane, longer ones by the whole warp
+
+// Emits the spans of one 32-step chunk into a line buffer.  Lane parameters: visible, pos (index of the span's first
+// pixel in the line), dir (+1/-1 index increment), length/drawLength and the two colours; 'limit' clips writes to the line.
+__device__ __forceinline__ void emit_spans(uint32_t *line, int limit, bool visible, int pos, int dir, unsigned length, unsigned drawLength, const Color16 &A, const Color16 &B)
+{
+	const int lane = threadIdx.x & 31;
+	SpanRamp ramp;
+	if (visible)
+		ramp = span_setup(length, drawLength, A, B);
+
+	if (visible && drawLength <= kShortSpan)
+	{
+		for (unsigned j = 0; j < drawLength; ++j)
+		{
+			const int idx = pos + int(j)*dir;
+			if (idx >= 0 && idx < limit)
+				line[idx] = span_pixel(ramp, j);
+		}
+	}
+
+	unsigned longMask = __ballot_sync(kFull, visible && drawLength > kShortSpan);
+	while (longMask)
+	{
+		const int src = __ffs(longMask) - 1;
+		longMask &= longMask - 1;
+		SpanRamp r;
+		#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			r.from[i] = __shfl_sync(kFull, ramp.from[i], src);
+			r.step[i] = __shfl_sync(kFull, ramp.step[i], src);
+		}
+		const int p = __shfl_sync(kFull, pos, src);
+		const unsigned len = __shfl_sync(kFull, drawLength, src);
+		for (unsigned j = lane; j < len; j += 32)
+		{
+			const int idx = p + int(j)*dir;
+			if (idx >= 0 && idx < limit)
+				line[idx] = span_pixel(r, j);
+		}
+	}
+}
+
+// warp exclusive prefix min / max with carry-in (lane i gets op(carry, v_0..v_{i-1})); returns the inclusive total via 'total'
+__device__ __forceinline__ int warp_excl_min(int v, int carry, int &total)
+{
+	const int lane = threadIdx.x & 31;
+	int incl = v;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const int o = __shfl_up_sync(kFull, incl, d);
+		if (lane >= d) incl = min(incl, o);
+	}
+	int excl = __shfl_up_sync(kFull, incl, 1);
+	excl = (lane == 0) ? carry : min(carry, excl);
+	total = min(carry, __shfl_sync(kFull, incl, 31));
+	return excl;
+}
+
+__device__ __forceinline__ unsigned warp_excl_max(unsigned v, unsigned carry, unsigned &total)
+{
+	const int lane = threadIdx.x & 31;
+	unsigned incl = v;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const unsigned o = __shfl_up_sync(kFull, incl, d);
+		if (lane >= d) incl = max(incl, o);
+	}
+	unsigned excl = __shfl_up_sync(kFull, incl, 1);
+	excl = (lane == 0) ? carry : max(carry, excl);
+	total = max(carry, __shfl_sync(kFull, incl, 31));
+	return excl;
+}
+
+// per-channel psubusw / paddusw on 16-bit lanes
+__device__ __forceinline__ int subs16(int a, int b) { return max(a - b, 0); }
+__device__ __forceinline__ int adds16(int a, int b) { return min(a + b, 65535); }
+
+// -------------------------------------------------------------------------------------------------------------
+// Landscape -- landscape.cpp:56-192
+// -------------------------------------------------------------------------------------------------------------
+
+constexpr int kScapeColsPerBlock = 8;
+constexpr unsigned kScapeRayLength = 512; // landscape.cpp:43
+
+struct LandscapeFrame
+{
+	int resX, resY;
+	int fpX1, fpY1;           // ray origin, 24:8
+	float X1, Y1;
+	float viewCos, viewSin;
+	float rayY;               // kMapSize*kMapViewLenScale
+	int mapTilt;              // s_mapTilt
+	uint32_t clearColor;      // s_pFogGradient[0]
+};
+
+__global__ void __launch_bounds__(kScapeColsPerBlock*32) landscape_kernel(uint32_t *__restrict__ pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
+	const uint32_t *__restrict__ fogGradient, const LandscapeFrame f, int lineStride)
+{
+	extern __shared__ uint32_t s_lines[]; // [kScapeColsPerBlock][lineStride]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned iRay = blockIdx.x*kScapeColsPerBlock + warp;
+	uint32_t *line = s_lines + warp*lineStride;
+
+	for (int y = lane; y < f.resY; y += 32)
+		line[y] = f.clearColor;
+	__syncwarp();
+
+	if (iRay < unsigned(f.resX))
+	{
+		// per-column set-up, landscape.cpp:172-190 and voxel-shared.h:8-24 (IEEE float, identical on both sides)
+		const float rayX = 0.25f*(float(iRay) - float(f.resX)*0.5f);
+		float rotRayX = rayX, rotRayY = f.rayY;
+		{
+			const float rX = f.viewCos*rotRayX - f.viewSin*rotRayY;
+			const float rY = f.viewSin*rotRayX + f.viewCos*rotRayY;
+			rotRayX = rX; rotRayY = rY;
+		}
+		const float X2 = f.X1+rotRayX, Y2 = f.Y1+rotRayY;
+		float dX = X2-f.X1, dY = Y2-f.Y1;
+		if (fabsf(dX+dY) > kEpsilon)
+		{
+			const float length = 1.f/sqrtf(dX*dX + dY*dY);
+			dX *= length;
+			dY *= length;
+		}
+		const float fishMul = f.rayY / sqrtf(rotRayX*rotRayX + rotRayY*rotRayY);
+
+		const int fpDX = ftofp24(dX), fpDY = ftofp24(dY);
+		const int fpFishMul = ftofp24(fabsf(fishMul));
+
+		// vscape_ray, landscape.cpp:56-107
+		int carryLastHeight = f.resY;
+		int carryLastDrawn = f.resY;
+		Color16 carryLastColor;
+		{
+			const unsigned U = unsigned(f.fpX1 >> 8) & 1023u, V = (unsigned(f.fpY1 >> 8) & 1023u) << 10;
+			carryLastColor = unpack16(__ldg(colorMap + (U|V)));
+		}
+
+		for (unsigned base = 0; base < kScapeRayLength; base += 32)
+		{
+			const unsigned iStep = base + lane;
+			const int curX = int(unsigned(f.fpX1) + (iStep+1)*unsigned(fpDX));
+			const int curY = int(unsigned(f.fpY1) + (iStep+1)*unsigned(fpDY));
+
+			const TexCoords t = prep_uvs(curX, curY, 1023u, 10u);
+			const unsigned mapHeight = sample_u8(heightMap, t);
+			Color16 color = unpack16(sample_argb(colorMap, t));
+
+			const Color16 fog = unpack16(__ldg(fogGradient + (iStep >> 1)));
+			#pragma unroll
+			for (int i = 0; i < 4; ++i) color.c[i] = subs16(color.c[i], fog.c[i]);
+
+			int height = 255-int(mapHeight);
+			height <<= 16;
+			height = int(unsigned(height) / (unsigned(fpFishMul)*(iStep+1)));
+			height *= 512; // kMapScale
+			height >>= 8;
+			height += f.mapTilt;
+
+			// what the serial loop would have seen: previous step's height/colour and the lowest height drawn before it
+			int prevHeight = __shfl_up_sync(kFull, height, 1);
+			Color16 prevColor = shfl_up_color(color);
+			if (lane == 0) { prevHeight = carryLastHeight; prevColor = carryLastColor; }
+
+			int newLastDrawn;
+			const int drawnBefore = warp_excl_min(height, carryLastDrawn, newLastDrawn);
+
+			const bool visible = height < drawnBefore;
+			emit_spans(line, f.resY, visible, height, 1, unsigned(prevHeight - height), unsigned(drawnBefore - height), color, prevColor);
+
+			carryLastDrawn = newLastDrawn;
+			carryLastHeight = __shfl_sync(kFull, height, 31);
+			carryLastColor = shfl_color(color, 31);
+		}
+	}
+
+	__syncthreads();
+
+	// write the kScapeColsPerBlock columns out: one 32-byte sector per row
+	const int x0 = blockIdx.x*kScapeColsPerBlock;
+	for (int i = threadIdx.x; i < f.resY*kScapeColsPerBlock; i += blockDim.x)
+	{
+		const int y = i / kScapeColsPerBlock, c = i % kScapeColsPerBlock;
+		if (x0 + c < f.resX)
+			pDest[size_t(y)*f.resX + x0 + c] = s_lines[c*lineStride + y];
+	}
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Tunnelscape -- tunnelscape.cpp:44-134
+// -------------------------------------------------------------------------------------------------------------
+
+constexpr int kRowsPerBlock = 4;
+
+struct TunnelscapeFrame
+{
+	int resX, resY;
+	int dX, dY, fpFromY;
+	float mapStepX;           // 2048.f/(kTargetResY-1)
+	float fromXOffs;          // syncDirX * time*kGoldenRatio
+	float viewLenScale;       // kMapViewLenScale = kAspect*0.5f (tunnelscape.cpp:29)
+	uint32_t clearColor;
+};
+
+__global__ void __launch_bounds__(kRowsPerBlock*32) tunnelscape_kernel(uint32_t *__restrict__ pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
+	const uint32_t *__restrict__ fogGradient, const TunnelscapeFrame f)
+{
+	extern __shared__ uint32_t s_lines[]; // [kRowsPerBlock][resX]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned iRay = blockIdx.x*kRowsPerBlock + warp;
+	if (iRay >= unsigned(f.resY))
+		return;
+	uint32_t *line = s_lines + warp*f.resX;
+
+	for (int x = lane; x < f.resX; x += 32)
+		line[x] = f.clearColor;
+	__syncwarp();
+
+	// tscape, tunnelscape.cpp:121-131
+	const float mapX = float(iRay)*f.mapStepX;
+	const float fromX = mapX + f.fromXOffs;
+	const int fpFromX = ftofp24(fromX);
+
+	// tscape_ray, tunnelscape.cpp:44-99
+	int carryLastHeight = f.resX;
+	int carryLastDrawn = f.resX;
+	Color16 carryLastColor;
+	{
+		const unsigned U = unsigned(fpFromX >> 8) & 2047u, V = (unsigned(f.fpFromY >> 8) & 2047u) << 11;
+		carryLastColor = unpack16(__ldg(colorMap + (U|V)));
+	}
+
+	for (unsigned base = 0; base < 512; base += 32)
+	{
+		const unsigned iStep = base + lane;
+		const int curX = int(unsigned(fpFromX) + (iStep+1)*unsigned(f.dX));
+		const int curY = int(unsigned(f.fpFromY) + (iStep+1)*unsigned(f.dY));
+
+		const TexCoords t = prep_uvs(curX, curY, 2047u, 11u);
+		const unsigned mapHeight = sample_u8(heightMap, t);
+		Color16 color = unpack16(sample_argb(colorMap, t));
+
+		const Color16 fog = unpack16(__ldg(fogGradient + (iStep >> 1)));
+		#pragma unroll
+		for (int i = 0; i < 4; ++i) color.c[i] = subs16(color.c[i], fog.c[i]);
+
+		// tunnelscape.cpp:73-81 (the divide by 'iStep+1' is unsigned, the multiply wraps)
+		int height = 255-int(mapHeight);
+		height -= 96;   // kMapViewHeight
+		height <<= 8;
+		height = cvtt_x86(float(height)/f.viewLenScale);
+		height = int(unsigned(height) / (iStep+1));
+		height = int(unsigned(height)*160u); // kMapScale
+		height >>= 8;
+		height += 120;  // kMapTilt
+
+		int prevHeight = __shfl_up_sync(kFull, height, 1);
+		Color16 prevColor = shfl_up_color(color);
+		if (lane == 0) { prevHeight = carryLastHeight; prevColor = carryLastColor; }
+
+		int newLastDrawn;
+		const int drawnBefore = warp_excl_min(height, carryLastDrawn, newLastDrawn);
+
+		const bool visible = height < drawnBefore;
+		// spans pile up left to right: the span of this step starts where everything drawn before it ended
+		emit_spans(line, f.resX, visible, f.resX - drawnBefore, 1, unsigned(prevHeight - height), unsigned(drawnBefore - height), color, prevColor);
+
+		carryLastDrawn = newLastDrawn;
+		carryLastHeight = __shfl_sync(kFull, height, 31);
+		carryLastColor = shfl_color(color, 31);
+	}
+
+	__syncwarp();
+	uint32_t *row = pDest + size_t(iRay)*f.resX;
+	for (int x = lane*4; x < f.resX; x += 128)
+		*reinterpret_cast<uint4 *>(row + x) = *reinterpret_cast<const uint4 *>(line + x);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Ball -- ball.cpp:80-365
+// -------------------------------------------------------------------------------------------------------------
+
+struct BallFrame
+{
+	int resX, resY;
+	int fromX, fromY;
+	unsigned rayLength;       // s_curRayLength
+	unsigned beamAtten;       // s_beamAtten
+	float beamAlphaMin;       // s_beamAlphaMin
+	unsigned lowLight;
+};
+
+// tables: heightProj[1024], projNorm0[1024], projNorm1[1024], projNorm2[1024] (ball.cpp:61-62)
+template <bool BEAMS>
+__global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
+	const uint32_t *__restrict__ auxMap /* beam mix or env map */, const int *__restrict__ tables, const int *__restrict__ rayDeltas, const BallFrame f)
+{
+	extern __shared__ uint32_t s_lines[]; // [kRowsPerBlock][resX]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned iRay = blockIdx.x*kRowsPerBlock + warp;
+	if (iRay >= unsigned(f.resY))
+		return;
+	uint32_t *line = s_lines + warp*f.resX;
+	uint32_t *row = pDest + size_t(iRay)*f.resX;
+
+	if (BEAMS)
+	{
+		// no clear in this path (ball.cpp:352-363): pixels that are not written keep the render target's previous content
+		for (int x = lane*4; x < f.resX; x += 128)
+			*reinterpret_cast<uint4 *>(line + x) = *reinterpret_cast<const uint4 *>(row + x);
+	}
+	else
+	{
+		for (int x = lane; x < f.resX; x += 32)
+			line[x] = 0; // memset32(pDest, 0, kTargetSize), ball.cpp:342
+	}
+	__syncwarp();
+
+	const int dX = rayDeltas[iRay*2], dY = rayDeltas[iRay*2+1];
+	const int *heightProj = tables, *projNorm0 = tables + 1024, *projNorm1 = tables + 2048, *projNorm2 = tables + 3072;
+
+	unsigned carryLastHeight = 0, carryLastDrawn = 0;
+	Color16 carryLastColor = unpack16(sample_argb(colorMap, prep_uvs(f.fromX, f.fromY, 1023u, 10u)));
+	int beamCarry[4] = { 0, 0, 0, 0 };
+
+	for (unsigned base = 0; base < f.rayLength; base += 32)
+	{
+		const unsigned iStep = base + lane;
+		const bool active = iStep < f.rayLength;
+		const unsigned tabIdx = active ? iStep : 0;
+
+		const int curX = int(unsigned(f.fromX) - (iStep+1)*unsigned(dX));
+		const int curY = int(unsigned(f.fromY) - (iStep+1)*unsigned(dY));
+		const TexCoords t = prep_uvs(curX, curY, 1023u, 10u);
+		const unsigned mapHeight = sample_u8(heightMap, t);
+		Color16 color = unpack16(sample_argb(colorMap, t));
+
+		if (BEAMS)
+		{
+			// vball_ray_beams, ball.cpp:113-140
+			Color16 beam = unpack16(sample_argb(auxMap, t));
+			const unsigned heightNorm = (mapHeight*unsigned(__ldg(projNorm0 + tabIdx))) >> 8;
+			const unsigned heightNorm2 = (mapHeight*unsigned(__ldg(projNorm1 + tabIdx))) >> 8;
+			const unsigned diffuse = heightNorm + ((unsigned(int(heightNorm2-heightNorm))*f.lowLight) >> 8);
+			const int litWhite = int(diffuse & 0xffffu); // _mm_set1_epi16
+
+			int beamIncl[4];
+			#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				const int b = ((beam.c[i]*int(f.beamAtten)) & 0xffff) >> 8;
+				int lit = ((b*litWhite) & 0xffff) >> 8;
+				if (!active) lit = 0;
+				// paddusw prefix: all terms are >= 0, so the saturating running sum is min(65535, exact prefix sum)
+				int incl = lit;
+				#pragma unroll
+				for (int d = 1; d < 32; d <<= 1)
+				{
+					const int o = __shfl_up_sync(kFull, incl, d);
+					if (lane >= d) incl += o;
+				}
+				beamIncl[i] = min(beamCarry[i] + incl, 65535);
+				beamCarry[i] = __shfl_sync(kFull, beamIncl[i], 31);
+				color.c[i] = adds16(adds16(color.c[i], beamIncl[i]), litWhite);
+			}
+		}
+		else
+		{
+			// vball_ray_no_beams, ball.cpp:228-262
+			const int envU = int(unsigned(512 << 8) - (iStep+1)*unsigned(dX << 1));
+			const int envV = int(unsigned(512 << 8) - (iStep+1)*unsigned(dY << 1));
+			const TexCoords te = prep_uvs(envU + int(mapHeight), envV + int(mapHeight), 1023u, 10u);
+			const Color16 envCol = unpack16(sample_argb(auxMap, te));
+			const unsigned diffuse = (mapHeight*unsigned(__ldg(projNorm2 + tabIdx))) >> 8;
+			const int lit = int(diffuse & 0xffffu);
+			const int litFull = int(min(255u, 32u+diffuse)); // kAmbient
+			#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				color.c[i] = adds16(adds16(color.c[i], ((envCol.c[i]*litFull) & 0xffff) >> 8), lit);
+		}
+
+		unsigned height = (mapHeight*unsigned(__ldg(heightProj + tabIdx))) >> 8;
+		if (!active) height = 0; // never visible, leaves the carries alone (they are taken from the last active lane below)
+
+		unsigned prevHeight = __shfl_up_sync(kFull, height, 1);
+		Color16 prevColor = shfl_up_color(color);
+		if (lane == 0) { prevHeight = carryLastHeight; prevColor = carryLastColor; }
+
+		unsigned newLastDrawn;
+		const unsigned drawnBefore = warp_excl_max(height, carryLastDrawn, newLastDrawn);
+
+		const bool visible = active && height > drawnBefore;
+		emit_spans(line, f.resX, visible, int(drawnBefore), 1, height - prevHeight, height - drawnBefore, prevColor, color);
+
+		carryLastDrawn = newLastDrawn;
+		const int lastLane = int(min(f.rayLength - base, 32u)) - 1;
+		carryLastHeight = __shfl_sync(kFull, height, lastLane);
+		carryLastColor = shfl_color(color, lastLane);
+	}
+
+	__syncwarp();
+
+	if (BEAMS)
+	{
+		// beam extrusion, ball.cpp:168-203
+		uint32_t beamCol = 0;
+		#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			const uint32_t v = uint32_t(beamCarry[i]);
+			beamCol |= ((v > 32767u) ? 0u : min(v, 255u)) << (8*i); // v2cISSE16: packuswb
+		}
+		const unsigned lastDrawnHeight = carryLastDrawn;
+		const unsigned remainder = unsigned(f.resX - 1) - lastDrawnHeight;
+		beamCol &= 0xffffffu;
+
+		const unsigned beamR = beamCol >> 16, beamG = (beamCol >> 8) & 0xff, beamB = beamCol & 0xff;
+		const unsigned mulR = 4731u, mulG = 46871u, mulB = 13932u; // unsigned(0.0722f*65536.f) etc.
+		const unsigned luminosity = ((beamR*mulR) >> 16) + ((beamG*mulG) >> 16) + ((beamB*mulB) >> 16);
+		const float fLuminosity = float(luminosity);
+
+		if (remainder <= unsigned(f.resX))
+		{
+			// 'curStep += alphaStep' is a serial float accumulation: lane 0 walks it, all lanes then shade in parallel
+			const float alphaStep = 1.f / float(remainder - 1);
+			if (lane == 0)
+			{
+				float curStep = 0.f;
+				for (unsigned i = 0; i < remainder; ++i)
+				{
+					line[lastDrawnHeight + i] = __float_as_uint(curStep);
+					curStep += alphaStep;
+				}
+			}
+			__syncwarp();
+			for (unsigned i = lane; i < remainder; i += 32)
+			{
+				const float curStep = __uint_as_float(line[lastDrawnHeight + i]);
+				const float fBeamAlpha = smoothstepf(f.beamAlphaMin, fLuminosity, curStep);
+				const unsigned beamAlpha = f2u_x86(fBeamAlpha);
+				line[lastDrawnHeight + i] = beamCol | (beamAlpha << 24);
+			}
+			__syncwarp();
+		}
+	}
+
+	for (int x = lane*4; x < f.resX; x += 128)
+		*reinterpret_cast<uint4 *>(row + x) = *reinterpret_cast<const uint4 *>(line + x);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Twister -- torus-twister.cpp:40-117
+// -------------------------------------------------------------------------------------------------------------
+
+// one warp per ray, two rays (right/left of centre) per row; rayOrigins[iRay*2] = fromX, [iRay*2+1] = fromY (host sinf)
+__global__ void __launch_bounds__(kRowsPerBlock*64) twister_kernel(uint32_t *__restrict__ pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
+	const int *__restrict__ tables, const int *__restrict__ rayOrigins, int resX, int resY)
+{
+	extern __shared__ uint32_t s_lines[]; // [kRowsPerBlock][resX]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int rowInBlock = warp >> 1, side = warp & 1;
+	const unsigned iRay = blockIdx.x*kRowsPerBlock + rowInBlock;
+	uint32_t *line = s_lines + rowInBlock*resX;
+	const bool rowValid = iRay < unsigned(resY);
+
+	// memset32(g_renderTarget[0], 0, kTargetSize), torus-twister.cpp:169: each of the two warps clears its half
+	const int half = resX >> 1;
+	for (int x = side*half + lane; x < (side+1)*half; x += 32)
+		line[x] = 0;
+	__syncthreads();
+
+	if (rowValid)
+	{
+		const int *heightProj = tables, *heightProjNorm = tables + 512;
+		const int kHalfMap = 1024/2;
+		const int fromX0 = rayOrigins[iRay*2], fromY = rayOrigins[iRay*2+1];
+
+		// vtwister_ray(pDest+xOffs, fromX, fromY, 512) and vtwister_ray(pDest+xOffs-1, fromX-512, fromY, -512), torus-twister.cpp:113-115
+		const int startX = (0 == side) ? fromX0 : fromX0 - kHalfMap;
+		const int dX = (0 == side) ? kHalfMap : -kHalfMap;
+		const int direction = (dX < 0) ? -1 : 1;
+		const int startPos = half + ((0 == side) ? 0 : -1);
+
+		unsigned carryLastHeight = 0, carryLastDrawn = 0;
+		Color16 carryLastColor = unpack16(sample_argb(colorMap, prep_uvs(startX, fromY, 1023u, 10u)));
+
+		for (unsigned base = 0; base < 512; base += 32)
+		{
+			const unsigned iStep = base + lane;
+			const int curX = int(unsigned(startX) - (iStep+1)*unsigned(dX));
+			const TexCoords t = prep_uvs(curX, fromY, 1023u, 10u);
+			const unsigned mapHeight = sample_u8(heightMap, t);
+			Color16 color = unpack16(sample_argb(colorMap, t));
+
+			const unsigned heightNorm = (mapHeight*unsigned(__ldg(heightProjNorm + iStep))) >> 8;
+			const int litWhite = int(heightNorm & 0xffffu);
+			#pragma unroll
+			for (int i = 0; i < 4; ++i) color.c[i] = adds16(color.c[i], litWhite);
+
+			const unsigned height = (mapHeight*unsigned(__ldg(heightProj + iStep))) >> 8;
+
+			unsigned prevHeight = __shfl_up_sync(kFull, height, 1);
+			Color16 prevColor = shfl_up_color(color);
+			if (lane == 0) { prevHeight = carryLastHeight; prevColor = carryLastColor; }
+
+			unsigned newLastDrawn;
+			const unsigned drawnBefore = warp_excl_max(height, carryLastDrawn, newLastDrawn);
+
+			const bool visible = height > drawnBefore;
+			emit_spans(line, resX, visible, startPos + int(drawnBefore)*direction, direction, height - prevHeight, height - drawnBefore, prevColor, color);
+
+			carryLastDrawn = newLastDrawn;
+			carryLastHeight = __shfl_sync(kFull, height, 31);
+			carryLastColor = shfl_color(color, 31);
+		}
+	}
+
+	__syncthreads();
+	if (rowValid)
+	{
+		uint32_t *row = pDest + size_t(iRay)*resX;
+		for (int x = (side*32 + lane)*4; x < resX; x += 256)
+			*reinterpret_cast<uint4 *>(row + x) = *reinterpret_cast<const uint4 *>(line + x);
+	}
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// host helpers
+// -------------------------------------------------------------------------------------------------------------
+
+int RequireImage(const ckd_ctx *ctx, ckd_image slot, int w, int h, int bpp, const char *what)
+{
+	const ckd_image_slot &s = ctx->images[slot];
+	if (!s.d_pixels || s.bpp != bpp || (w > 0 && s.width != w) || (h > 0 && s.height != h))
+	{
+		ckd_set_error(std::string("missing or mis-sized input image: ") + what);
+		return CKD_ERR_MISSING_INPUT;
+	}
+	return CKD_OK;
+}
+
+template <class K> int EnsureSmem(K kernel, size_t bytes)
+{
+	if (bytes > 48*1024)
+		CKD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+	return CKD_OK;
+}
+
+} // namespace
+
+// Landscape_Draw, landscape.cpp:228-243
+extern "C" int ckd_landscape_draw(ckd_ctx *ctx, const ckd_landscape_params *p, float time, uint32_t *d_dest)
+{
+	(void)time;
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	CKD_TRY(RequireImage(ctx, CKD_IMG_SCAPE_HEIGHT, 1024, 1024, 1, "landscape height map (assets/scape/D17.png)"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_SCAPE_COLOR, 1024, 1024, 4, "landscape colour map (assets/scape/C17W-edit.png)"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_SCAPE_FOG, 256, 1, 4, "fog gradient (assets/scape/foggradient.jpg)"));
+
+	const float aspect = float(ctx->resY)/float(ctx->resX);
+
+	LandscapeFrame f;
+	f.resX = ctx->resX;
+	f.resY = ctx->resY;
+
+	// vscape, landscape.cpp:109-169 with the gamepad contribution passed in as accumulated state
+	const float tilt = ckdh::clampf(-90.f, 90.f, p->tilt + p->pad_tilt);
+	f.mapTilt = 90 + ckdh::x86_cvtt(tilt);
+	f.viewCos = cosf(p->view_angle);
+	f.viewSin = sinf(p->view_angle);
+	float moveX = -f.viewSin*p->forward;
+	float moveY = f.viewCos*p->forward;
+	moveX += p->pad_move_x;
+	moveY += p->pad_move_y;
+	f.X1 = moveX+p->strafe_x;
+	f.Y1 = moveY+p->strafe_y;
+	f.fpX1 = ckdh::ftofp24(f.X1);
+	f.fpY1 = ckdh::ftofp24(f.Y1);
+	const float kMapViewLenScale = aspect*(ckdh::kPI*0.1f);
+	f.rayY = 1024*kMapViewLenScale;
+
+	f.clearColor = ctx->images[CKD_IMG_SCAPE_FOG].firstPixel; // s_pFogGradient[0], landscape.cpp:238
+
+	const bool warp = 0.f != p->warp_strength;
+	uint32_t *pWrite = warp ? ctx->d_renderTarget[0] : d_dest;
+
+	const int lineStride = ctx->resY | 1;
+	const size_t smem = size_t(kScapeColsPerBlock)*lineStride*4;
+	CKD_TRY(EnsureSmem(landscape_kernel, smem));
+	landscape_kernel<<<ckd_div_up(ctx->resX, kScapeColsPerBlock), kScapeColsPerBlock*32, smem, ctx->stream>>>(pWrite,
+		static_cast<const uint8_t *>(ctx->images[CKD_IMG_SCAPE_HEIGHT].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_SCAPE_COLOR].d_pixels),
+		static_cast<const uint32_t *>(ctx->images[CKD_IMG_SCAPE_FOG].d_pixels), f, lineStride);
+	CKD_CHECK_LAUNCH(ctx);
+
+	if (warp) // note the reference passes (WarpSpeed, WarpStrength) into (strength, speed), landscape.cpp:242
+		CKD_TRY(ckd_tape_warp(ctx, d_dest, pWrite, unsigned(ctx->resX), unsigned(ctx->resY), p->warp_speed, p->warp_strength));
+	return CKD_OK;
+}
+
+// Tunnelscape_Draw, tunnelscape.cpp:168-186
+extern "C" int ckd_tunnelscape_draw(ckd_ctx *ctx, const ckd_tunnelscape_params *p, float time, uint32_t *d_dest)
+{
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	CKD_TRY(RequireImage(ctx, CKD_IMG_TSCAPE_HEIGHT, 2048, 2048, 1, "tunnelscape height map (assets/scape/tscape-D7-edit.png)"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_TSCAPE_COLOR, 2048, 2048, 4, "tunnelscape colour map (assets/scape/tscape-C7W-edit.png)"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_TSCAPE_FOG, 256, 1, 4, "fog gradient (assets/scape/foggradient.jpg)"));
+
+	const float aspect = float(ctx->resY)/float(ctx->resX);
+	const float oneOverAspect = 1.f/aspect;
+
+	// tscape, tunnelscape.cpp:103-119
+	TunnelscapeFrame f;
+	f.resX = ctx->resX;
+	f.resY = ctx->resY;
+	f.mapStepX = 2048.f/float(ctx->resY-1);
+	const float syncDirX = p->step_u, syncDirY = p->step_v;
+	const float speedMul = sqrtf(syncDirX*syncDirX + syncDirY*syncDirY) * p->speed;
+	const float fromY = 1024.f + speedMul*time;
+	f.dX = ckdh::ftofp24(syncDirY);
+	f.dY = ckdh::ftofp24(oneOverAspect*syncDirX);
+	f.fpFromY = ckdh::ftofp24(fromY);
+	f.fromXOffs = syncDirX * time*ckdh::kGoldenRatio;
+	f.viewLenScale = aspect*0.5f;
+
+	f.clearColor = ctx->images[CKD_IMG_TSCAPE_FOG].firstPixel; // s_pFogGradient[0], tunnelscape.cpp:170
+
+	const size_t smem = size_t(kRowsPerBlock)*ctx->resX*4;
+	CKD_TRY(EnsureSmem(tunnelscape_kernel, smem));
+	tunnelscape_kernel<<<ckd_div_up(ctx->resY, kRowsPerBlock), kRowsPerBlock*32, smem, ctx->stream>>>(ctx->d_renderTarget[0],
+		static_cast<const uint8_t *>(ctx->images[CKD_IMG_TSCAPE_HEIGHT].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_TSCAPE_COLOR].d_pixels),
+		static_cast<const uint32_t *>(ctx->images[CKD_IMG_TSCAPE_FOG].d_pixels), f);
+	CKD_CHECK_LAUNCH(ctx);
+
+	CKD_TRY(ckd_polar_blit(ctx, d_dest, ctx->d_renderTarget[0], 1));
+
+	if (0.f != p->blur)
+	{
+		const float scaledBlur = ckdh::BoxBlurScale(p->blur);
+		CKD_TRY(ckd_old_blur(ctx, d_dest, d_dest, unsigned(ctx->resX), unsigned(ctx->resY), scaledBlur));
+		CKD_TRY(ckd_old_blur(ctx, d_dest, d_dest, unsigned(ctx->resX), unsigned(ctx->resY), scaledBlur));
+	}
+	return CKD_OK;
+}
+
+// Ball_Draw, ball.cpp:452-514
+extern "C" int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time, uint32_t *d_dest)
+{
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	for (int i = 0; i < 5; ++i)
+		CKD_TRY(RequireImage(ctx, ckd_image(CKD_IMG_BALL_HEIGHT0 + i), 1024, 1024, 1, "ball height map"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_BALL_COLOR0, 1024, 1024, 4, "ball colour map 0"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_BALL_COLOR1, 1024, 1024, 4, "ball colour map 1"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_BALL_ENV, 1024, 1024, 4, "ball env map"));
+	for (int i = 0; i < 3; ++i)
+		CKD_TRY(RequireImage(ctx, ckd_image(CKD_IMG_BALL_BEAM0 + i), 1024, 1024, 4, "ball beam map"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_BALL_BACKGROUND0, ctx->resX, ctx->resY, 4, "ball background 0 (output sized)"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_BALL_BACKGROUND1, ctx->resX, ctx->resY, 4, "ball background 1 (output sized)"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_BALL_HALO, ctx->resX, ctx->resY, 4, "ball halo (output sized)"));
+
+	constexpr size_t mapNumPixels = 1024*1024;
+	const bool hasBeams = 0 != p->has_beams;
+
+	// height map mix, ball.cpp:458-464
+	const unsigned iBaseMap = unsigned(ckdh::clampi(1, 4, p->base_shape_index));
+	CKD_CUDA(cudaMemcpyAsync(ctx->d_ballHeightMix, ctx->images[CKD_IMG_BALL_HEIGHT0 + iBaseMap].d_pixels, mapNumPixels, cudaMemcpyDeviceToDevice, ctx->stream));
+	const uint8_t spikes = uint8_t(p->spikes);
+	if (0 != spikes)
+		CKD_TRY(ckd_blend(ctx, CKD_MIX32, reinterpret_cast<uint32_t *>(ctx->d_ballHeightMix), static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_HEIGHT0].d_pixels), unsigned(mapNumPixels/4), 0.f, spikes));
+
+	if (hasBeams)
+	{
+		// beam map mix, ball.cpp:466-480
+		const float beamA[3] = { ckdh::saturatef(p->beams1), ckdh::saturatef(p->beams2), ckdh::saturatef(p->beams3) };
+		CKD_TRY(ckd_memset32(ctx, ctx->d_ballBeamMix, 0, mapNumPixels));
+		for (int i = 0; i < 3; ++i)
+			if (beamA[i] > 0.f)
+				CKD_TRY(ckd_blit(ctx, CKD_BLITADD32A, ctx->d_ballBeamMix, static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_BEAM0 + i].d_pixels), 1024, 1024, 1024, beamA[i]));
+	}
+
+	// vball(g_renderTarget[0], time*speed), ball.cpp:312-365
+	const float ballTime = time * p->speed;
+
+	// vball_precalc, ball.cpp:283-308 (host libm, like the reference)
+	static thread_local int tables[4096];
+	static thread_local int rayDeltas[16384*2];
+	CKD_REQUIRE(ctx->resY <= 16384, "resolution too large");
+	const float radius = ckdh::clampf(1.f, 1920.f, p->radius);
+	const unsigned rayLength = unsigned(ckdh::clampi(1, 1024, p->ray_length));
+	const float angStepSin = ckdh::kPI/float(rayLength-1);
+	const float angStepCos = angStepSin * 0.99f;
+	for (unsigned iAngle = 0; iAngle < rayLength; ++iAngle)
+	{
+		tables[iAngle] = int(ckdh::x86_f2u(radius*sinf(angStepSin*float(iAngle))));
+		const float cosine = cosf(angStepCos*float(iAngle));
+		if (cosine >= 0.f)
+		{
+			tables[1024+iAngle] = ckdh::x86_cvtt(255.f*powf(cosine, ckdh::kGoldenRatio));
+			tables[2048+iAngle] = ckdh::x86_cvtt(255.f*powf(cosine, ckdh::kGoldenAngle));
+			tables[3072+iAngle] = ckdh::x86_cvtt(255.f*powf(cosine, ckdh::kPI));
+		}
+		else
+			tables[1024+iAngle] = tables[2048+iAngle] = tables[3072+iAngle] = 0;
+	}
+
+	BallFrame f;
+	f.resX = ctx->resX;
+	f.resY = ctx->resY;
+	f.rayLength = rayLength;
+	f.beamAtten = unsigned(ckdh::clampi(0, 255, p->beam_atten));
+	f.beamAlphaMin = ckdh::clampf(0.f, 255.f, p->beam_alpha_min);
+	f.lowLight = unsigned(ckdh::clampi(0, 255, p->low_beams));
+
+	const float timeScale = float(rayLength)*(0.25f/1024);
+	const float fMapDim = 1024.f, fMapHalf = fMapDim*0.5f;
+	f.fromX = ckdh::ftofp24(fMapDim*sinf(ballTime*timeScale) + fMapHalf + p->rotate_offs_x);
+	f.fromY = ckdh::ftofp24(fMapDim*cosf(ballTime*timeScale) + fMapHalf + p->rotate_offs_y);
+
+	// fan deltas, ball.cpp:334-363 + voxel-shared.h:16-31
+	const float delta = ckdh::k2PI/float(ctx->resY-1);
+	for (int iRay = 0; iRay < ctx->resY; ++iRay)
+	{
+		const float curAngle = float(unsigned(iRay))*delta;
+		float dX = cosf(curAngle), dY = sinf(curAngle);
+		if (fabsf(dX+dY) > ckdh::kEpsilon)
+		{
+			const float length = 1.f/sqrtf(dX*dX + dY*dY);
+			dX *= length;
+			dY *= length;
+		}
+		rayDeltas[iRay*2] = ckdh::ftofp24(dX);
+		rayDeltas[iRay*2+1] = ckdh::ftofp24(dY);
+	}
+
+	int *d_tables = ctx->d_voxelTables;
+	int *d_rayDeltas = reinterpret_cast<int *>(ctx->d_rayParams);
+	CKD_CUDA(cudaMemcpyAsync(d_tables, tables, sizeof(int)*4096, cudaMemcpyHostToDevice, ctx->stream));
+	CKD_CUDA(cudaMemcpyAsync(d_rayDeltas, rayDeltas, sizeof(int)*2*ctx->resY, cudaMemcpyHostToDevice, ctx->stream));
+
+	const size_t smem = size_t(kRowsPerBlock)*ctx->resX*4;
+	const unsigned blocks = ckd_div_up(ctx->resY, kRowsPerBlock);
+	if (hasBeams)
+	{
+		CKD_TRY(EnsureSmem(ball_kernel<true>, smem));
+		ball_kernel<true><<<blocks, kRowsPerBlock*32, smem, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
+			static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_COLOR0].d_pixels), ctx->d_ballBeamMix, d_tables, d_rayDeltas, f);
+	}
+	else
+	{
+		CKD_TRY(EnsureSmem(ball_kernel<false>, smem));
+		ball_kernel<false><<<blocks, kRowsPerBlock*32, smem, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
+			static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_COLOR1].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_ENV].d_pixels), d_tables, d_rayDeltas, f);
+	}
+	CKD_CHECK_LAUNCH(ctx);
+
+	// ball.cpp:486-502
+	const float blur = ckdh::BoxBlurScale(p->blur);
+	if (0.f != blur)
+		CKD_TRY(ckd_old_blur_h(ctx, ctx->d_renderTarget[0], ctx->d_renderTarget[0], unsigned(ctx->resX), unsigned(ctx->resY), blur));
+
+	const void *pBackground = ctx->images[hasBeams ? CKD_IMG_BALL_BACKGROUND0 : CKD_IMG_BALL_BACKGROUND1].d_pixels;
+	CKD_CUDA(cudaMemcpyAsync(d_dest, pBackground, size_t(ctx->resX)*ctx->resY*4, cudaMemcpyDeviceToDevice, ctx->stream));
+	CKD_TRY(ckd_polar_blit_a(ctx, d_dest, ctx->d_renderTarget[0], 0));
+
+	if (hasBeams)
+		CKD_TRY(ckd_blend(ctx, CKD_SOFTLIGHT32A, d_dest, static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_HALO].d_pixels), unsigned(ctx->resX)*unsigned(ctx->resY), 0.f, 0));
+	return CKD_OK;
+}
+
+// Twister_Draw, torus-twister.cpp:166-188
+extern "C" int ckd_twister_draw(ckd_ctx *ctx, const ckd_twister_params *p, float time, uint32_t *d_dest)
+{
+	CKD_REQUIRE(ctx && p && d_dest, "null argument");
+	CKD_TRY(RequireImage(ctx, CKD_IMG_TWISTER_HEIGHT, 1024, 1024, 1, "twister height map"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_TWISTER_COLOR, 1024, 1024, 4, "twister colour map"));
+	CKD_TRY(RequireImage(ctx, CKD_IMG_TWISTER_BACKGROUND, ctx->resX, ctx->resY, 4, "twister background (output sized)"));
+	CKD_REQUIRE(ctx->resY <= 16384, "resolution too large");
+
+	// vtwister_precalc, torus-twister.cpp:119-135
+	static thread_local int tables[1024];
+	static thread_local int rayOrigins[16384*2];
+	for (unsigned iAngle = 0; iAngle < 512; ++iAngle)
+	{
+		const float angle = ckdh::kPI/(512-1) * iAngle;
+		const float scale = 600.f*sinf(angle);
+		tables[iAngle] = int(ckdh::x86_f2u(scale));
+		const float cosine = cosf(angle*0.99f);
+		tables[512+iAngle] = (cosine > 0.f) ? int(ckdh::x86_f2u(255.f*powf(cosine, 2.f))) : 0;
+	}
+
+	// vtwister, torus-twister.cpp:92-117
+	const float fMapSize = 1024.f;
+	const float fMapSizeHH = (fMapSize*0.5f) - 0.5f;
+	const float fMapSizeHHH = (fMapSize*0.25f) - 0.5f;
+	const float mapStepY = fMapSize/float(ctx->resY-1);
+	const float shearStep = ckdh::k2PI/float(ctx->resY-1);
+	for (int iRay = 0; iRay < ctx->resY; ++iRay)
+	{
+		const float shearAngle = float(iRay) * shearStep;
+		const float mapY = float(unsigned(iRay))*mapStepY;
+		rayOrigins[iRay*2] = ckdh::ftofp24(fMapSizeHH + fMapSizeHHH*sinf(time*p->shear_speed + shearAngle));
+		rayOrigins[iRay*2+1] = ckdh::ftofp24(mapY + time*p->speed);
+	}
+
+	int *d_tables = ctx->d_voxelTables;
+	int *d_rayOrigins = reinterpret_cast<int *>(ctx->d_rayParams);
+	CKD_CUDA(cudaMemcpyAsync(d_tables, tables, sizeof(int)*1024, cudaMemcpyHostToDevice, ctx->stream));
+	CKD_CUDA(cudaMemcpyAsync(d_rayOrigins, rayOrigins, sizeof(int)*2*ctx->resY, cudaMemcpyHostToDevice, ctx->stream));
+
+	const size_t smem = size_t(kRowsPerBlock)*ctx->resX*4;
+	CKD_TRY(EnsureSmem(twister_kernel, smem));
+	twister_kernel<<<ckd_div_up(ctx->resY, kRowsPerBlock), kRowsPerBlock*64, smem, ctx->stream>>>(ctx->d_renderTarget[0],
+		static_cast<const uint8_t *>(ctx->images[CKD_IMG_TWISTER_HEIGHT].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_TWISTER_COLOR].d_pixels),
+		d_tables, d_rayOrigins, ctx->resX, ctx->resY);
+	CKD_CHECK_LAUNCH(ctx);
+
+	const float blur = p->blur;
+	if (0.f != blur)
+		CKD_TRY(ckd_old_blur_h(ctx, ctx->d_renderTarget[0], ctx->d_renderTarget[0], unsigned(ctx->resX), unsigned(ctx->resY), ckdh::BoxBlurScale(blur)));
+
+	CKD_CUDA(cudaMemcpyAsync(d_dest, ctx->images[CKD_IMG_TWISTER_BACKGROUND].d_pixels, size_t(ctx->resX)*ctx->resY*4, cudaMemcpyDeviceToDevice, ctx->stream));
+	return ckd_polar_blit_a(ctx, d_dest, ctx->d_renderTarget[0], 0);
+}

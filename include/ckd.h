@@ -1,0 +1,276 @@
+/*
+ * ckd.h -- C ABI of cookiedough_b200: the B200 (sm_100a) implementation of cookiedough's per-pixel effect hot path.
+ *
+ * Every entry point is plain C (opaque context, POD parameter structs, raw device/host pointers and sizes) so the
+ * reference -- or any FFI -- can bind it directly.  Each declaration cites the reference interface it replaces
+ * (paths relative to the reference's code/ directory).  The C++ host layer (include/ckd_host.h) re-creates the
+ * reference's own X_Create / X_Draw(uint32_t *pDest, float time, float delta) / X_Destroy names on top of this ABI.
+ *
+ * Conventions
+ *   - pixels are uint32_t ARGB8888 (0xAARRGGBB little endian = bytes B,G,R,A), row-major, no padding (code/main.h:37-43)
+ *   - "d_" pointers are device addresses on the context's GPU; they may alias where the reference allows in-place use
+ *   - all work is enqueued on the context's stream (ckd_set_stream); nothing synchronises unless documented
+ *   - every function returns CKD_OK (0) or a negative ckd_status; ckd_last_error() describes the last failure
+ *   - there is NO CPU fallback: without a usable CUDA device ckd_create() fails with CKD_ERR_CUDA
+ */
+#ifndef CKD_H_
+#define CKD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ckd_ctx ckd_ctx;
+
+typedef enum ckd_status {
+	CKD_OK = 0,
+	CKD_ERR_CUDA = -1,          /* CUDA runtime/driver error (message in ckd_last_error) */
+	CKD_ERR_INVALID = -2,       /* bad argument */
+	CKD_ERR_MISSING_INPUT = -3, /* an image / table the effect needs has not been uploaded */
+	CKD_ERR_UNIMPLEMENTED = -4
+} ckd_status;
+
+/* ---- context (replaces the module globals allocated by Shared_Create / FxBlitter_Create / Polar_Create /
+ *      BoxBlur_Create: shared-resources.cpp:14-37, fx-blitter.cpp:10-20, polar.cpp:61-72, boxblur.cpp:23-28;
+ *      and CalculateCosLUT / InitializeFastCosine: sincos-lut.cpp:9-16, fast-cosine.cpp:10-17) ------------------- */
+
+/* resX/resY replace the compile-time kResX/kResY (main.h:37-38); both must be multiples of 8. */
+int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device);
+void ckd_destroy(ckd_ctx *ctx);
+const char *ckd_last_error(void);
+const char *ckd_version(void);
+
+int ckd_set_stream(ckd_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = default stream */
+int ckd_sync(ckd_ctx *ctx);
+
+int ckd_res_x(const ckd_ctx *ctx);
+int ckd_res_y(const ckd_ctx *ctx);
+int ckd_fxmap_res_x(const ckd_ctx *ctx); /* kFxMapResX = resX/2+4 (fx-blitter.h:16) */
+int ckd_fxmap_res_y(const ckd_ctx *ctx);
+
+/* device twins of the reference's global buffers */
+uint32_t *ckd_frame(ckd_ctx *ctx);                  /* device copy of pDest (main.cpp:307) */
+uint32_t *ckd_fxmap(ckd_ctx *ctx, int index);       /* g_pFxMap[0..3] (fx-blitter.h:26) */
+uint32_t *ckd_render_target(ckd_ctx *ctx, int index); /* g_renderTarget[0..3] (shared-resources.h:12) */
+
+/* generic device memory + copies (host pointers may be pageable or pinned) */
+int ckd_malloc(ckd_ctx *ctx, void **out_d_ptr, size_t bytes);
+int ckd_free(ckd_ctx *ctx, void *d_ptr);
+int ckd_malloc_host(void **out_h_ptr, size_t bytes); /* pinned */
+int ckd_free_host(void *h_ptr);
+int ckd_upload(ckd_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);   /* async on the stream */
+int ckd_download(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes); /* async on the stream */
+
+/* timing on the context's stream (CUDA events) */
+int ckd_timer_start(ckd_ctx *ctx);
+int ckd_timer_stop_ms(ckd_ctx *ctx, float *out_ms); /* synchronises */
+
+/* ---- tables ---------------------------------------------------------------------------------------------------
+ * ckd_create() fills all of these itself with the host's libm / CPU exactly like the reference does at start-up;
+ * the setters exist so tests can pin tables captured on another machine. */
+int ckd_set_cos_lut(ckd_ctx *ctx, const float *lut2049);                      /* g_cosLUT (sincos-lut.cpp:6) */
+/* _mm_rsqrt_ps emulation (shadertoy-util.h:89,260,265): table[parity][mantissa >> log2_bin] holds the result bits for
+ * x = 2^(parity-1) * 1.mantissa, parity 0: [0.5,1), parity 1: [1,2); entries = 2 << (23 - log2_bin). */
+int ckd_set_rsqrt_table(ckd_ctx *ctx, const uint32_t *table, int log2_bin);
+int ckd_get_rsqrt_table(ckd_ctx *ctx, uint32_t *out_table, size_t max_entries, int *out_log2_bin, size_t *out_entries);
+int ckd_set_polar_maps(ckd_ctx *ctx, const int32_t *map, const int32_t *inv_map); /* s_pMap/s_pInvMap (polar.cpp:13-14), 2 ints/px */
+int ckd_get_polar_maps(ckd_ctx *ctx, int32_t *out_map, int32_t *out_inv_map);
+
+/* ---- images (replace Image_Load32 / Image_Load8 results held in file statics) -------------------------------------- */
+typedef enum ckd_image {
+	CKD_IMG_TUNNEL_TEX = 0,      /* shadertoy.cpp:174  1024x1024 BGRA */
+	CKD_IMG_TUNNEL_TEX_FX,       /* shadertoy.cpp:175  1024x1024 BGRA */
+	CKD_IMG_SPIKE_BLUR_MAP0,     /* shadertoy.cpp:180  FX-map sized BGRA */
+	CKD_IMG_SPIKE_BLUR_MAP1,     /* shadertoy.cpp:181 */
+	CKD_IMG_SCAPE_HEIGHT,        /* landscape.cpp:200  1024x1024 L8 */
+	CKD_IMG_SCAPE_COLOR,         /* landscape.cpp:201  1024x1024 BGRA */
+	CKD_IMG_SCAPE_FOG,           /* landscape.cpp:206  256x1 BGRA */
+	CKD_IMG_TSCAPE_HEIGHT,       /* tunnelscape.cpp:139 2048x2048 L8 */
+	CKD_IMG_TSCAPE_COLOR,        /* tunnelscape.cpp:140 2048x2048 BGRA */
+	CKD_IMG_TSCAPE_FOG,          /* tunnelscape.cpp:145 256x1 BGRA */
+	CKD_IMG_BALL_HEIGHT0,        /* ball.cpp:367-380 (5 maps, 1024x1024 L8) */
+	CKD_IMG_BALL_HEIGHT1,
+	CKD_IMG_BALL_HEIGHT2,
+	CKD_IMG_BALL_HEIGHT3,
+	CKD_IMG_BALL_HEIGHT4,
+	CKD_IMG_BALL_COLOR0,         /* ball.cpp:394-395 */
+	CKD_IMG_BALL_COLOR1,
+	CKD_IMG_BALL_BEAM0,          /* ball.cpp:400-402 */
+	CKD_IMG_BALL_BEAM1,
+	CKD_IMG_BALL_BEAM2,
+	CKD_IMG_BALL_ENV,            /* ball.cpp:407 */
+	CKD_IMG_BALL_BACKGROUND0,    /* ball.cpp:412-413 output sized */
+	CKD_IMG_BALL_BACKGROUND1,
+	CKD_IMG_BALL_HALO,           /* ball.cpp:422 output sized */
+	CKD_IMG_TWISTER_HEIGHT,      /* torus-twister.cpp:143 1024x1024 L8 */
+	CKD_IMG_TWISTER_COLOR,       /* torus-twister.cpp:144 */
+	CKD_IMG_TWISTER_BACKGROUND,  /* torus-twister.cpp:149 output sized */
+	CKD_IMG_COUNT
+} ckd_image;
+
+/* bytes_per_pixel: 1 (L8) or 4 (BGRA).  The pixels are copied to the device. */
+int ckd_set_image(ckd_ctx *ctx, ckd_image slot, const void *h_pixels, int width, int height, int bytes_per_pixel);
+const void *ckd_get_image(ckd_ctx *ctx, ckd_image slot); /* device pointer or NULL */
+
+/* ---- 2D post chain ---------------------------------------------------------------------------------------------- */
+
+/* Fx_Blit_2x2(pDest, pSrc) fx-blitter.cpp:27-75: FX map (fxResX x fxResY) -> output (resX x resY) */
+int ckd_fx_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src);
+
+/* Polar_Blit / Polar_BlitA (polar.cpp:135-154, 180-198) */
+int ckd_polar_blit(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse);
+int ckd_polar_blit_a(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse);
+
+/* 2007 box blur (deprecated/boxblur.cpp:44-231); d_dest may equal d_src (the reference's in-place semantics are kept) */
+int ckd_old_blur_h(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength);
+int ckd_old_blur_v(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength);
+int ckd_old_blur(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength);
+float ckd_box_blur_scale(float strength); /* BoxBlurScale, deprecated/boxblur.h:13-19 */
+
+/* 2026 multi-pass blur (boxblur.cpp:270-318).  Rows are read 2 pixels past their end like the reference does
+ * (boxblur.cpp:171,185): d_src must have >= 2 readable pixels after the last row. */
+int ckd_new_blur_h(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength, float gain, unsigned num_passes);
+int ckd_new_blur_v(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength, float gain, unsigned num_passes);
+int ckd_new_blur(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength, float gain, unsigned num_passes);
+
+/* blend ops on equally sized buffers (util.cpp:83-812, util.h:73-122) */
+typedef enum ckd_blend_op {
+	CKD_MIX32 = 0,        /* Mix32(dest, src, n, alpha)            u_param = alpha (uint8)      util.cpp:83  */
+	CKD_MIXOVER32 = 1,    /* MixOver32                                                          util.cpp:148 */
+	CKD_ADD32 = 2,        /* Add32                                                              util.cpp:132 */
+	CKD_SUB32 = 3,        /* Sub32                                                              util.cpp:179 */
+	CKD_EXCL32 = 4,       /* Excl32                                                             util.cpp:194 */
+	CKD_SOFTLIGHT32 = 5,  /* SoftLight32                                                        util.cpp:242 */
+	CKD_SOFTLIGHT32A = 6, /* SoftLight32A                                                       util.cpp:274 */
+	CKD_SOFTLIGHT32AA = 7,/* SoftLight32AA(dest, src, n, alpha)    f_param = alpha              util.cpp:309 */
+	CKD_OVERLAY32 = 8,    /* Overlay32                                                          util.cpp:434 */
+	CKD_OVERLAY32A = 9,   /* Overlay32A                                                         util.cpp:485 */
+	CKD_DARKEN32_50 = 10, /* Darken32_50                                                        util.cpp:518 */
+	CKD_MULSRC32 = 11,    /* MulSrc32                                                           util.cpp:605 */
+	CKD_MULSRC32A = 12,   /* MulSrc32A                                                          util.cpp:620 */
+	CKD_MIXSRC32 = 13,    /* MixSrc32                                                           util.cpp:661 */
+	CKD_FADE32 = 14       /* Fade32(dest, n, RGB, alpha)  u_param = alpha<<24 | RGB; src unused util.cpp:798 */
+} ckd_blend_op;
+int ckd_blend(ckd_ctx *ctx, ckd_blend_op op, uint32_t *d_dest, const uint32_t *d_src, unsigned num_pixels, float f_param, unsigned u_param);
+
+/* rectangular blits (util.cpp:707-796) */
+typedef enum ckd_blit_op {
+	CKD_BLITSRC32 = 0, CKD_BLITSRC32A = 1, CKD_BLITADD32 = 2, CKD_BLITADD32A = 3
+} ckd_blit_op;
+int ckd_blit(ckd_ctx *ctx, ckd_blit_op op, uint32_t *d_dest, const uint32_t *d_src, unsigned dest_res_x, unsigned src_res_x, unsigned y_res, float alpha);
+/* MixSrc32S (util.cpp:636-659) */
+int ckd_mix_src_s(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned dest_res_x, unsigned dest_res_y, unsigned src_stride);
+
+/* memset32 (util.h:57-67) and TapeWarp32 (util.cpp:552-603; note the reference's sampler row stride is resX, not x_res) */
+int ckd_memset32(ckd_ctx *ctx, uint32_t *d_dest, uint32_t value, size_t num_ints);
+int ckd_tape_warp(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength, float speed);
+
+/* ---- effects: one entry per reference X_Draw; the structs carry every Rocket-derived scalar the reference pulls
+ *      with Rocket::getf/geti inside the call (track names in comments) ------------------------------------------- */
+
+typedef struct ckd_plasma_params {       /* shadertoy.cpp:213-216 */
+	float speed;         /* plasma:Speed */
+	float hue;           /* plasma:Hue */
+	float gamma;         /* plasma:Gamma */
+	float desaturation;  /* plasma:Desaturation */
+} ckd_plasma_params;
+int ckd_plasma_draw(ckd_ctx *ctx, const ckd_plasma_params *p, float time, uint32_t *d_dest); /* Plasma_Draw shadertoy.cpp:276 */
+
+typedef struct ckd_nautilus_params {     /* shadertoy.cpp:304-307,399 */
+	float roll;          /* nautilus:Roll */
+	float hue;           /* nautilus:Hue */
+	float speed;         /* nautilus:Speed */
+	float desaturation;  /* nautilus:Desat */
+	float blur;          /* nautilus:Blur (raw track value, BoxBlurScale is applied inside) */
+} ckd_nautilus_params;
+int ckd_nautilus_draw(ckd_ctx *ctx, const ckd_nautilus_params *p, float time, uint32_t *d_dest); /* Nautilus_Draw shadertoy.cpp:395 */
+
+typedef struct ckd_spikey_params {       /* shadertoy.cpp:436-450, 529-537, 604-606, 669-677, 715 */
+	float speed;             /* spike:Speed */
+	float roll;              /* spike:Roll */
+	float specular;          /* spike:Specular */
+	float desaturation;      /* spike:Desaturation */
+	float hue;               /* spike:Hue */
+	float gamma;             /* spike:Gamma */
+	float warmup;            /* distSpike:Warmup */
+	float dist_x, dist_y, dist_z;    /* distSpike:xOffs/yOffs/zOffs */
+	float close_x, close_y, close_z; /* closeSpike:xOffs/yOffs/zOffs */
+	float close_z_scale;     /* closeSpike:zOffsScale */
+	float close_normal_grain;/* closeSpike:NormalGrain */
+	float close_scale;       /* closeSpike:Scale */
+	int close_rim;           /* geti(closeSpike:Rim) */
+	int close_aspect_mul;    /* geti(closeSpike:AspectMul) */
+	float mix_blur_map;      /* closeSpike:MixBlurMap */
+	float mix_blur;          /* closeSpike:MixBlur */
+	float mix_map_blur;      /* closeSpike:MixMapBlur */
+	float mix_blur_opacity;  /* closeSpike:MixBlurOpacity */
+} ckd_spikey_params;
+int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float time, int close, uint32_t *d_dest); /* Spikey_Draw shadertoy.cpp:661 */
+
+typedef struct ckd_tunnel_params {       /* shadertoy.cpp:752-762, 842-843 */
+	float boxy, flower_scale, flower_freq, flower_phase; /* tunnel:Boxy/FlowerScale/FlowerFreq/FlowerPhase */
+	float speed, roll, pitch, radius;                    /* tunnel:Speed/Roll/Pitch/Radius */
+	float mul_u, mul_v;                                  /* tunnel:MulU/MulV */
+	int lit_tiles;                                       /* geti(tunnel:LitTiles) */
+	float lit_blur;                                      /* tunnel:LitBlur */
+	float fog1, fog2;                                    /* tunnel:Fog1/Fog2 */
+} ckd_tunnel_params;
+int ckd_tunnel_draw(ckd_ctx *ctx, const ckd_tunnel_params *p, float time, uint32_t *d_dest); /* Tunnel_Draw shadertoy.cpp:840 */
+
+typedef struct ckd_sinuses_params {      /* shadertoy.cpp:905-911 */
+	float specular, roll, speed, offs_x, gamma, hue, desaturation; /* sinusesTunnel:* */
+} ckd_sinuses_params;
+int ckd_sinuses_draw(ckd_ctx *ctx, const ckd_sinuses_params *p, float time, uint32_t *d_dest); /* Sinuses_Draw shadertoy.cpp:984 */
+
+typedef struct ckd_laura_params {        /* shadertoy.cpp:1019-1024 */
+	float speed, yaw, pitch, roll, hue, saturate; /* laura:* */
+} ckd_laura_params;
+int ckd_laura_draw(ckd_ctx *ctx, const ckd_laura_params *p, float time, uint32_t *d_dest); /* Laura_Draw shadertoy.cpp:1105 */
+
+typedef struct ckd_landscape_params {    /* landscape.cpp:128,156,230-242 (gamepad state = 0: view angle 0, no strafe) */
+	float forward;        /* voxelScape:Forward */
+	float tilt;           /* voxelScape:Tilt */
+	float warp_speed;     /* voxelScape:WarpSpeed */
+	float warp_strength;  /* voxelScape:WarpStrength */
+	/* accumulated gamepad state (landscape.cpp:116-154 statics); all zero for a headless run */
+	float pad_tilt, view_angle, strafe_x, strafe_y, pad_move_x, pad_move_y;
+} ckd_landscape_params;
+int ckd_landscape_draw(ckd_ctx *ctx, const ckd_landscape_params *p, float time, uint32_t *d_dest); /* Landscape_Draw landscape.cpp:228 */
+
+typedef struct ckd_tunnelscape_params {  /* tunnelscape.cpp:108-111,177 */
+	float step_u, step_v, speed, blur; /* starsTunnel:stepU/stepV/Speed/Blur */
+} ckd_tunnelscape_params;
+int ckd_tunnelscape_draw(ckd_ctx *ctx, const ckd_tunnelscape_params *p, float time, uint32_t *d_dest); /* Tunnelscape_Draw tunnelscape.cpp:168 */
+
+typedef struct ckd_ball_params {         /* ball.cpp:82,285-286,318-319,322,331-332,456-470,483,486 */
+	float blur;             /* ball:Blur */
+	float radius;           /* ball:Radius */
+	int ray_length;         /* geti(ball:RayLength) */
+	int spikes;             /* geti(ball:Spikes) */
+	int has_beams;          /* geti(ball:HasBeams) */
+	int base_shape_index;   /* geti(ball:BaseShapeIndex) */
+	float speed;            /* ball:Speed */
+	int beam_atten;         /* geti(ball:BeamAttenuation) */
+	float beam_alpha_min;   /* ball:BeamAlphaMin */
+	float rotate_offs_x, rotate_offs_y; /* ball:RotateOffsX/Y */
+	float beams1, beams2, beams3;       /* ball:Beams1..3 */
+	int low_beams;          /* geti(ball:BallLowBeams) */
+} ckd_ball_params;
+int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time, uint32_t *d_dest); /* Ball_Draw ball.cpp:452 */
+
+typedef struct ckd_twister_params {      /* torus-twister.cpp:100-101,173 */
+	float speed, shear_speed, blur; /* twister:Speed, twister::ShearSpeed (sic), twister:Blur */
+} ckd_twister_params;
+int ckd_twister_draw(ckd_ctx *ctx, const ckd_twister_params *p, float time, uint32_t *d_dest); /* Twister_Draw torus-twister.cpp:166 */
+
+/* number of CUDA kernels this library launched on this context so far (bench.py's gpu_launches) */
+unsigned long long ckd_launch_count(const ckd_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CKD_H_ */
