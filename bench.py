@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of cookiedough_b200 (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload "effect-suite-4k": one STEP renders one 3840x2160 frame through each of the 12 effect entry points of the
+hot path (BASELINE.json configs 1-3 at their pinned Rocket rows: the 7 raymarch variants, landscape, tunnelscape,
+ball with and without beams, twister), each including its own post chain (Fx_Blit_2x2, polar remap, in-place box blur,
+blends) exactly as the reference's X_Draw does.  Metric: Mpixel/s of finished output pixels (12 x 8.2944 Mpx per step).
+
+  value   device-resident: parameters evaluated, maps resident in HBM, frames stay on the GPU; CUDA-event timed.
+  e2e     the same step through the reference-facing C++ host layer: Rocket evaluation on the host, X_Draw(pDest, time,
+          delta) into a pinned HOST buffer, i.e. every frame is copied device->host inside the timed region.
+  N > 1   frames shard across GPUs (one process per GPU, no data-path collective): weak scaling, every rank renders
+          K steps; value = total pixels / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+RES_X, RES_Y = 3840, 2160
+ROW_RATE = (170.0 / (60.0 * (170.0 / 174.0))) * 16.0
+
+# label, C-ABI effect, host/reference effect, close flag, pinned Rocket row
+SUITE = [
+    ("plasma", "plasma", "plasma", None, 2600),
+    ("nautilus", "nautilus", "nautilus", None, 5700),
+    ("spikey_close", "spikey", "spikey_close", True, 6800),
+    ("spikey_distant", "spikey", "spikey_distant", False, 3600),
+    ("tunnel", "tunnel", "tunnel", None, 4500),
+    ("sinuses", "sinuses", "sinuses", None, 7800),
+    ("laura", "laura", "laura", None, 8900),
+    ("landscape", "landscape", "landscape", None, 500),
+    ("tunnelscape", "tunnelscape", "tunnelscape", None, 4300),
+    ("ball", "ball", "ball", None, 1500),
+    ("ball_beams", "ball", "ball", None, 2060),
+    ("twister", "twister", "twister", None, 2008),
+]
+PIXELS_PER_STEP = len(SUITE) * RES_X * RES_Y
+
+# mean FP32 operations per FX-map pixel at the pinned rows (instrumented-oracle estimate; 1 op = one
+# FP add/mul/cvt/cmp, no FMA contraction) -- denominators for the raymarch kernels' FP32 roofline
+FLOP_PER_FX_PIXEL = {
+    "raymarch_plasma": 1.7e3, "raymarch_nautilus": 2.2e3, "raymarch_spikey_close": 1.7e3, "raymarch_spikey_distant": 1.8e3,
+    "raymarch_spikey_spec": 1.9e3, "raymarch_sinuses": 2.7e3, "raymarch_laura": 1.7e3, "raymarch_tunnel": 0.25e3,
+}
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        return rank, world, local, dist
+    return rank, world, local, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own CPU implementation (oracle/_ref) on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+
+def reference_suite_runner():
+    from cookiedough_b200.assets import Assets
+    from oracle import ref as oref
+    if not oref.available(RES_Y):
+        return None, None
+    R = oref.Reference.get(RES_Y, Assets(RES_X, RES_Y))
+    out = R.frame()
+
+    def step():
+        for _, _, ref_eff, _, row in SUITE:
+            R.set_row(row)
+            R.draw(ref_eff, out)
+    return R, step
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    R, step = reference_suite_runner()
+    base = {"impl": "reference", "metric": "Mpixel/s", "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+            "config": {"workload": "effect-suite-4k", "res": [RES_X, RES_Y], "effects": [s[0] for s in SUITE]}}
+    if step is None:
+        base["unavailable"] = "oracle/_ref (compiled reference) is not present in this checkout"
+        print(json.dumps(base))
+        return 0
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = PIXELS_PER_STEP * args.steps / dt / 1e6
+    sample = f"{args.steps} full steps (12 frames at {RES_X}x{RES_Y} each) after {max(args.warmup, 1)} warm-up steps"
+    base.update({"value": value, "ms_per_step": 1e3 * dt / args.steps, "gpu_launches": 0,
+                 "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cpu_threads(), "kind": "reference", "sample": sample},
+                 "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    rank, world, local, dist = dist_setup(args.gpus)
+    import torch
+    from cookiedough_b200 import capi, hostapi
+    from cookiedough_b200.assets import Assets
+
+    torch.cuda.set_device(local)
+    assets = Assets(RES_X, RES_Y)
+    host = hostapi.Host(RES_X, RES_Y, local, assets)
+    ctx = host.context()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    # parameters of every suite entry, evaluated once by the host layer's Rocket (the device-resident leg feeds them
+    # straight to the C ABI; the e2e leg re-evaluates them per frame like the reference does)
+    cases = []
+    for label, eff, host_eff, close, row in SUITE:
+        host.set_row(row)
+        cases.append((label, eff, host_eff, close, row, capi.params_from_tracks(eff, host.track), float(np.float32(host.time))))
+
+    d_frames = [ctx.malloc(RES_X * RES_Y * 4 + 65536) for _ in range(2)]  # alternate targets so no frame is rewritten back to back
+
+    def step_device(i):
+        for j, (label, eff, host_eff, close, row, params, t) in enumerate(cases):
+            ctx.draw(eff, params, t, d_dest=d_frames[(i + j) & 1], close=close)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_device(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        dist.barrier()
+
+    # ---- end to end through the reference-facing host API (HOST pDest, D2H inside the timed region) -------------
+    frame_bytes = RES_X * RES_Y * 4
+    h_frame = ctx.malloc_host(frame_bytes)
+    e2e_steps = max(1, min(args.steps, 10))
+
+    def step_e2e():
+        for label, eff, host_eff, close, row, params, t in cases:
+            host.set_row(row)
+            host.draw(host_eff, h_frame)
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * PIXELS_PER_STEP * e2e_steps / e2e_s / 1e6
+    # per step: 12 parameter structs + the ball / twister per-frame tables go up, 12 finished frames come down
+    h2d_bytes = 12 * 96 + 2 * (4096 * 4 + RES_Y * 8) + (1024 * 4 + RES_Y * 8)
+    d2h_bytes = len(SUITE) * frame_bytes
+
+    # ---- per-kernel roofline: CUDA events around every launch in an instrumented repeat of the timed steps -------
+    roofline, kernels = None, {}
+    per_effect = {}
+    if rank == 0:
+        hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+        prof_steps = max(1, min(args.steps, 5))
+        ctx.profile_begin()
+        for i in range(prof_steps):
+            step_device(i)
+        stats = ctx.profile_end()
+        total_ms = sum(s["total_ms"] for s in stats.values()) or 1.0
+        fx_pixels = (RES_X // 2 + 4) * (RES_Y // 2 + 4)
+        fp32_peak = 148 * 128 * sm_max_mhz * 1e6 / 1e12  # FADD/FMUL issue rate without FMA contraction, TFLOP/s
+        traffic = {}
+        tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)
+        for name, s in sorted(stats.items(), key=lambda kv: -kv[1]["total_ms"]):
+            avg_ms = s["total_ms"] / s["launches"]
+            entry = {"launches_per_step": s["launches"] / prof_steps, "avg_ms": avg_ms, "share": s["total_ms"] / total_ms}
+            if name in FLOP_PER_FX_PIXEL:
+                tf = FLOP_PER_FX_PIXEL[name] * fx_pixels / (avg_ms * 1e-3) / 1e12
+                entry.update({"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak})
+            else:
+                gbs = s["algo_bytes"] / s["launches"] / (avg_ms * 1e-3) / 1e9
+                entry.update({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak})
+            entry["traffic"] = traffic.get(name)
+            kernels[name] = entry
+        dominant = max(kernels, key=lambda k: kernels[k]["share"])
+        roofline = dict(kernels[dominant], kernel=dominant, peak_source=peak_src,
+                        timing="CUDA events around every launch, instrumented repeat of the timed steps")
+        # the HBM-bound kernel with the largest share, reported next to the dominant one
+        hbm_kernels = [k for k in kernels if kernels[k]["bound"] == "hbm"]
+        if hbm_kernels:
+            top_hbm = max(hbm_kernels, key=lambda k: kernels[k]["share"])
+            roofline["dominant_hbm_kernel"] = dict(kernels[top_hbm], kernel=top_hbm)
+
+        # per-effect device time (one frame each, median of 3)
+        for label, eff, host_eff, close, row, params, t in cases:
+            ts = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ctx.draw(eff, params, t, d_dest=d_frames[0], close=close)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            ms = float(np.median(ts))
+            per_effect[label] = {"ms": ms, "fps": 1e3 / ms, "mpixel_s": RES_X * RES_Y / ms / 1e3}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference itself on the host cores ---------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        R, ref_step = reference_suite_runner()
+        if ref_step is not None:
+            ref_step()
+            passes = 2
+            t0 = time.perf_counter()
+            for _ in range(passes):
+                ref_step()
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": PIXELS_PER_STEP * passes / dt / 1e6, "unit": "Mpixel/s", "cores": cpu_threads(), "kind": "reference",
+                            "sample": f"{passes} full steps of the same suite (12 frames at {RES_X}x{RES_Y}) on oracle/_ref after 1 warm-up step, OpenMP on all host threads"}
+        else:
+            cpu_baseline = {"value": None, "unit": "Mpixel/s", "cores": cpu_threads(), "kind": "reference", "sample": "oracle/_ref not present"}
+
+    if rank == 0:
+        value = world * PIXELS_PER_STEP * args.steps / (elapsed_ms * 1e-3) / 1e6
+        working_set_mb = (12 * 2 * RES_X * RES_Y * 4 + 2 * RES_X * RES_Y * 8 + 60e6) / 1e6
+        line = {
+            "metric": "Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "fps_per_effect_mean": 1e3 * len(SUITE) / (elapsed_ms / args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+            "config": {"workload": "effect-suite-4k", "res": [RES_X, RES_Y], "effects": [s[0] for s in SUITE], "rows": [s[4] for s in SUITE],
+                       "assets": "procedural stand-ins" if assets.synthetic else "reference art (oracle/_ref/assets.npz)",
+                       "l2": f"no explicit flush: one step streams ~{working_set_mb:.0f} MB (frames, render targets, polar maps, textures) through the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "api": "X_Draw(uint32_t *pDest, float time, float delta) of include/ckd_host.h, pinned host pDest"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "per_effect": per_effect,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

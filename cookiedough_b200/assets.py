@@ -63,28 +63,53 @@ def _nearest_resize(arr, new_h, new_w):
     return np.ascontiguousarray(arr[yi][:, xi])
 
 
+def _hash_u32(x):
+    """integer avalanche hash on uint32 arrays (pure integer arithmetic: identical on every platform / numpy version)"""
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7FEB352D)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846CA68B)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def _tri(v, period):
+    """integer triangle wave in [0, 255]"""
+    v = np.mod(v, period).astype(np.int64)
+    half = period // 2
+    return (np.where(v < half, v, period - v) * 255 // max(half, 1)).astype(np.int64)
+
+
 def _synthetic(path, h, w, gray):
-    """deterministic procedural stand-in: smooth ridges + hash noise (keeps voxel spans/occlusion non-trivial)"""
+    """deterministic procedural stand-in: smooth integer ridges + hash noise (keeps voxel spans / occlusion non-trivial)"""
     seed = sum((i + 1) * b for i, b in enumerate(path.encode())) & 0xFFFFFFFF
-    rng = np.random.default_rng(seed)
-    y = np.arange(h, dtype=np.float64)[:, None]
-    x = np.arange(w, dtype=np.float64)[None, :]
-    fx, fy = rng.uniform(2, 9, 2)
-    base = 0.5 + 0.25 * np.sin(x * (2 * np.pi * fx / w)) * np.cos(y * (2 * np.pi * fy / max(h, 2))) \
-        + 0.2 * np.sin((x + y) * (2 * np.pi * 3 / max(w, 2)))
-    noise = rng.random((h, w)) * 0.1
-    lum = np.clip((base + noise) * 200.0, 0, 255).astype(np.uint8)
+    y = np.arange(h, dtype=np.int64)[:, None]
+    x = np.arange(w, dtype=np.int64)[None, :]
+    p1 = 64 + seed % 97
+    p2 = 96 + (seed >> 7) % 131
+    ridges = (_tri(x + (seed & 63), p1) * _tri(y + (seed >> 3 & 63), p2)) // 255
+    diag = _tri(x + 2 * y, 3 * p1 // 2)
+    noise = (_hash_u32((x + y * w + seed).astype(np.uint32)) >> np.uint32(27)).astype(np.int64)  # 0..31
+    lum = np.clip((ridges * 5 + diag * 3) // 8 + noise - 16, 0, 255).astype(np.uint8)
     if "tscape-D7" in path:
         lum = (lum.astype(np.uint16) * 150 // 255).astype(np.uint8)  # keep below the view height (code/tunnelscape.cpp:75)
+    if "ball/hmap" in path:
+        # the reference's ball caster runs off its 1280-pixel rows when height*radius>>8 >= 1280 (SURVEY App. B H2/H3):
+        # with ball:Radius clamped to 1920 the stand-in maps stay below 170
+        lum = (lum.astype(np.uint16) * 160 // 255).astype(np.uint8)
     if gray:
         return lum
     b = lum
     g = np.roll(lum, w // 7, axis=1)
-    r = np.roll(lum, h // 5, axis=0) if h > 1 else lum
+    r = np.roll(lum, h // 5, axis=0) if h > 1 else np.roll(lum, w // 11, axis=1)
     a = np.full_like(lum, 255)
-    if "halo" in path or "background" in path or "blur-map" in path:
+    if "halo" in path or "background" in path or "blur-map" in path or "foggradient" in path:
         a = np.roll(lum, w // 3, axis=1)
-    rgba = np.stack([b, g, r, a], axis=-1)
+    if "foggradient" in path:
+        ramp = (np.arange(w, dtype=np.int64) * 200 // max(w - 1, 1)).astype(np.uint8)[None, :]
+        b, g, r = ramp, (ramp // 2 + 20).astype(np.uint8), (255 - ramp).astype(np.uint8) // 3
+    rgba = np.stack(np.broadcast_arrays(b, g, r, a), axis=-1)
     return np.ascontiguousarray(rgba).view(np.uint32).reshape(h, w)
 
 

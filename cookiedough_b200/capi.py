@@ -111,6 +111,12 @@ BLEND_OPS = {
 }
 BLIT_OPS = {"BlitSrc32": 0, "BlitSrc32A": 1, "BlitAdd32": 2, "BlitAdd32A": 3}
 
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint), ("total_ms", C.c_double), ("algo_bytes", C.c_double)]
+
+
 _lib = None
 
 
@@ -162,6 +168,8 @@ def load():
         "ckd_ball_draw": ([VP, C.POINTER(BallParams), F, VP], _I),
         "ckd_twister_draw": ([VP, C.POINTER(TwisterParams), F, VP], _I),
         "ckd_launch_count": ([VP], C.c_ulonglong),
+        "ckd_profile_begin": ([VP], _I),
+        "ckd_profile_end": ([VP, C.POINTER(KernelStat), _I, C.POINTER(_I)], _I),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)  # raises AttributeError if the ABI symbol is not exported
@@ -338,6 +346,25 @@ class Context:
 
     def tape_warp(self, d_dest, d_src, w, h, strength, speed):
         self._check(self.L.ckd_tape_warp(self.h, C.c_void_p(d_dest), C.c_void_p(d_src), w, h, C.c_float(strength), C.c_float(speed)))
+
+    def profile_begin(self):
+        self._check(self.L.ckd_profile_begin(self.h))
+
+    def profile_end(self):
+        """-> {kernel name: {"launches", "total_ms", "algo_bytes"}} measured with CUDA events around every launch"""
+        stats = (KernelStat * 64)()
+        count = C.c_int()
+        self._check(self.L.ckd_profile_end(self.h, stats, 64, C.byref(count)))
+        return {stats[i].name.decode(): {"launches": int(stats[i].launches), "total_ms": float(stats[i].total_ms), "algo_bytes": float(stats[i].algo_bytes)}
+                for i in range(count.value)}
+
+    def malloc_host(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.L.ckd_malloc_host(C.byref(p), nbytes))
+        return p.value
+
+    def free_host(self, ptr):
+        self._check(self.L.ckd_free_host(C.c_void_p(ptr)))
 
     def timer_start(self):
         self._check(self.L.ckd_timer_start(self.h))

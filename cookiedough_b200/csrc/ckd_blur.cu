@@ -109,6 +109,7 @@ static int OldBlurPass(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, un
 	s.fullDiv = WeightToDiv16(kernelSpan << 4);
 
 	const unsigned threads = numLines*4;
+	ckd_prof_begin(ctx, stepStride == 1 ? "old_blur_h" : "old_blur_v", 8.0*numLines*lineLen);
 	old_blur_kernel<<<ckd_div_up(threads, 128), 128, 0, ctx->stream>>>(reinterpret_cast<uint8_t *>(d_dest), reinterpret_cast<const uint8_t *>(d_src), numLines, lineStride, stepStride, s);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
@@ -271,6 +272,7 @@ static int NewBlurLines(ckd_ctx *ctx, uint32_t *d_dest, uint32_t *d_scratch, con
 	const unsigned threads = numLines*4;
 	for (unsigned iPass = 0; iPass < numPasses; ++iPass)
 	{
+		ckd_prof_begin(ctx, stepStride == 1 ? "new_blur_h" : "new_blur_v", 8.0*numLines*lineLen);
 		new_blur_kernel<<<ckd_div_up(threads, 128), 128, 0, ctx->stream>>>(reinterpret_cast<uint8_t *>(pDest), reinterpret_cast<const uint8_t *>(pRead),
 			numLines, lineLen, lineStride, stepStride, lineStride, stepStride, s);
 		CKD_CHECK_LAUNCH(ctx);

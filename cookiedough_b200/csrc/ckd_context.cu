@@ -309,6 +309,7 @@ extern "C" void ckd_destroy(ckd_ctx *ctx)
 		if (slot.d_pixels) cudaFree(slot.d_pixels);
 	if (ctx->d_rsqrtTab) cudaFree(ctx->d_rsqrtTab);
 	free(ctx->h_rsqrtTab);
+	for (auto &e : ctx->profEntries) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
 	if (ctx->evStart) cudaEventDestroy(ctx->evStart);
 	if (ctx->evStop) cudaEventDestroy(ctx->evStop);
 	if (ctx->d_pool) cudaFree(ctx->d_pool);
@@ -393,6 +394,72 @@ extern "C" int ckd_timer_stop_ms(ckd_ctx *ctx, float *out_ms)
 	CKD_CUDA(cudaEventRecord(ctx->evStop, ctx->stream));
 	CKD_CUDA(cudaEventSynchronize(ctx->evStop));
 	CKD_CUDA(cudaEventElapsedTime(out_ms, ctx->evStart, ctx->evStop));
+	return CKD_OK;
+}
+
+void ckd_prof_begin(ckd_ctx *ctx, const char *name, double algoBytes)
+{
+	if (!ctx->profiling)
+		return;
+	if (ctx->profUsed == ctx->profEntries.size())
+	{
+		ckd_ctx::ProfEntry e = { name, algoBytes, nullptr, nullptr };
+		if (cudaSuccess != cudaEventCreate(&e.start) || cudaSuccess != cudaEventCreate(&e.stop))
+			return;
+		ctx->profEntries.push_back(e);
+	}
+	ckd_ctx::ProfEntry &e = ctx->profEntries[ctx->profUsed];
+	e.name = name;
+	e.algoBytes = algoBytes;
+	cudaEventRecord(e.start, ctx->stream);
+	ctx->profPending = int(ctx->profUsed++);
+}
+
+void ckd_prof_end(ckd_ctx *ctx)
+{
+	if (ctx->profPending < 0)
+		return;
+	cudaEventRecord(ctx->profEntries[ctx->profPending].stop, ctx->stream);
+	ctx->profPending = -1;
+}
+
+extern "C" int ckd_profile_begin(ckd_ctx *ctx)
+{
+	CKD_REQUIRE(ctx, "null context");
+	ctx->profiling = true;
+	ctx->profUsed = 0;
+	ctx->profPending = -1;
+	return CKD_OK;
+}
+
+extern "C" int ckd_profile_end(ckd_ctx *ctx, ckd_kernel_stat *out_stats, int max_stats, int *out_count)
+{
+	CKD_REQUIRE(ctx && out_count, "null argument");
+	ctx->profiling = false;
+	CKD_CUDA(cudaStreamSynchronize(ctx->stream));
+	int count = 0;
+	for (size_t i = 0; i < ctx->profUsed; ++i)
+	{
+		const ckd_ctx::ProfEntry &e = ctx->profEntries[i];
+		float ms = 0.f;
+		CKD_CUDA(cudaEventElapsedTime(&ms, e.start, e.stop));
+		int slot = -1;
+		for (int j = 0; j < count; ++j)
+			if (0 == strncmp(out_stats[j].name, e.name, sizeof(out_stats[j].name)-1)) { slot = j; break; }
+		if (slot < 0)
+		{
+			if (!out_stats || count >= max_stats)
+				continue;
+			slot = count++;
+			memset(&out_stats[slot], 0, sizeof(ckd_kernel_stat));
+			strncpy(out_stats[slot].name, e.name, sizeof(out_stats[slot].name)-1);
+		}
+		out_stats[slot].launches++;
+		out_stats[slot].total_ms += ms;
+		out_stats[slot].algo_bytes += e.algoBytes;
+	}
+	*out_count = count;
+	ctx->profUsed = 0;
 	return CKD_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string>
+#include <vector>
 
 #include "../../include/ckd.h"
 
@@ -49,13 +50,24 @@ struct ckd_ctx {
 	float *d_rayParams = nullptr;     // per-ray host-computed parameters (ball fan deltas, twister origins)
 
 	ckd_image_slot images[CKD_IMG_COUNT];
+
+	// optional per-launch CUDA-event profiler (ckd_profile_begin / ckd_profile_end)
+	bool profiling = false;
+	int profPending = -1;
+	struct ProfEntry { const char *name; double algoBytes; cudaEvent_t start, stop; };
+	std::vector<ProfEntry> profEntries;
+	size_t profUsed = 0;
 };
+
+// brackets the next kernel launch with CUDA events when profiling is on; algoBytes = algorithmic bytes of that launch
+void ckd_prof_begin(ckd_ctx *ctx, const char *name, double algoBytes);
+void ckd_prof_end(ckd_ctx *ctx);
 
 void ckd_set_error(const std::string &message);
 int ckd_cuda_fail(cudaError_t err, const char *what, const char *file, int line);
 
 #define CKD_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return ckd_cuda_fail(_e, #expr, __FILE__, __LINE__); } while (0)
-#define CKD_CHECK_LAUNCH(ctx) do { (ctx)->launches++; cudaError_t _e = cudaPeekAtLastError(); if (_e != cudaSuccess) return ckd_cuda_fail(_e, "kernel launch", __FILE__, __LINE__); } while (0)
+#define CKD_CHECK_LAUNCH(ctx) do { (ctx)->launches++; ckd_prof_end(ctx); cudaError_t _e = cudaPeekAtLastError(); if (_e != cudaSuccess) return ckd_cuda_fail(_e, "kernel launch", __FILE__, __LINE__); } while (0)
 #define CKD_REQUIRE(cond, msg) do { if (!(cond)) { ckd_set_error(std::string(__func__) + ": " + (msg)); return CKD_ERR_INVALID; } } while (0)
 #define CKD_TRY(expr) do { int _r = (expr); if (_r != CKD_OK) return _r; } while (0)
 

@@ -49,6 +49,7 @@ extern "C" int ckd_fx_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d
 	const int halfX = ctx->fxX - 4, halfY = ctx->fxY - 4;
 	const dim3 block(64, 4);
 	const dim3 grid(ckd_div_up(halfX/2, block.x), ckd_div_up(halfY, block.y));
+	ckd_prof_begin(ctx, "fx_blit_2x2", 5.0*ctx->resX*ctx->resY);
 	fx_blit_2x2_kernel<<<grid, block, 0, ctx->stream>>>(d_dest, d_src, ctx->fxX, ctx->resX, halfX, halfY);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
@@ -200,11 +201,13 @@ template <int OP> static int LaunchBlend(ckd_ctx *ctx, uint32_t *d_dest, const u
 	{
 		const unsigned numQuads = numPixels/4;
 		const unsigned blocks = std::max(1u, std::min(maxBlocks, ckd_div_up(std::max(numQuads, 1u), 256)));
+		ckd_prof_begin(ctx, "blend", (OP == CKD_FADE32 ? 8.0 : 12.0)*numPixels);
 		blend_kernel<OP><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, numQuads, numPixels, p);
 	}
 	else
 	{
 		const unsigned blocks = std::max(1u, std::min(maxBlocks, ckd_div_up(numPixels, 256)));
+		ckd_prof_begin(ctx, "blend", (OP == CKD_FADE32 ? 8.0 : 12.0)*numPixels);
 		blend_kernel_scalar<OP><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, numPixels, p);
 	}
 	CKD_CHECK_LAUNCH(ctx);
@@ -300,6 +303,7 @@ template <int OP> static int LaunchRect(ckd_ctx *ctx, uint32_t *d_dest, const ui
 		return CKD_OK;
 	const dim3 block(64, 4);
 	const dim3 grid(ckd_div_up(width, block.x), ckd_div_up(height, block.y));
+	ckd_prof_begin(ctx, "rect_blit", 12.0*width*height);
 	rect_kernel<OP><<<grid, block, 0, ctx->stream>>>(d_dest, d_src, destStride, srcStride, width, height, fa);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
@@ -348,6 +352,7 @@ extern "C" int ckd_memset32(ckd_ctx *ctx, uint32_t *d_dest, uint32_t value, size
 		return CKD_OK;
 	const size_t numQuads = num_ints/4;
 	const unsigned blocks = unsigned(std::max<size_t>(1, std::min<size_t>(size_t(ctx->numSMs)*16, ckd_div_up(std::max<size_t>(numQuads, 1), 256))));
+	ckd_prof_begin(ctx, "memset32", 4.0*num_ints);
 	memset32_kernel<<<blocks, 256, 0, ctx->stream>>>(d_dest, value, numQuads, num_ints);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
@@ -407,6 +412,7 @@ static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, in
 	const unsigned numQuads = unsigned(size_t(ctx->resX)*ctx->resY/4);
 	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap : ctx->d_polarMap);
 	const unsigned blocks = ckd_div_up(numQuads, 256);
+	ckd_prof_begin(ctx, alpha ? "polar_blit_a" : "polar_blit", (alpha ? 20.0 : 16.0)*ctx->resX*ctx->resY);
 	if (alpha)
 		polar_blit_kernel<true><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
 	else
@@ -457,6 +463,7 @@ extern "C" int ckd_tape_warp(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_s
 	CKD_REQUIRE(d_dest != d_src, "TapeWarp32 cannot run in place");
 	const dim3 block(64, 4);
 	const dim3 grid(ckd_div_up(x_res, block.x), ckd_div_up(y_res, block.y));
+	ckd_prof_begin(ctx, "tape_warp", 8.0*x_res*y_res);
 	tape_warp_kernel<<<grid, block, 0, ctx->stream>>>(d_dest, d_src, ctx->d_cosLUT2, x_res, y_res, unsigned(ctx->resX), strength, speed);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;

@@ -634,13 +634,14 @@ Rot MakeRot(const ckd_ctx *ctx, float angle)
 	return { ckdh::lutcosf(ctx->h_cosLUT, angle), ckdh::lutsinf(ctx->h_cosLUT, angle) };
 }
 
-template <class Effect> int LaunchRaymarch(ckd_ctx *ctx, const Effect &effect, uint32_t *d_fxmap)
+template <class Effect> int LaunchRaymarch(ckd_ctx *ctx, const Effect &effect, uint32_t *d_fxmap, const char *name)
 {
 	const FrameGeom geom = MakeGeom(ctx);
 	const int tilesX = ckd_div_up(geom.fxX, kTileX), tilesY = ckd_div_up(geom.fxY, kTileY);
 	const int numTiles = tilesX*tilesY;
 	const int blocks = std::min(numTiles, ctx->numSMs*8);
 	const RsqrtTab rsqrt = { ctx->d_rsqrtTab, ctx->rsqrtLog2Bin };
+	ckd_prof_begin(ctx, name, 4.0*geom.fxX*geom.fxY);
 	raymarch_kernel<Effect><<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(effect, d_fxmap, geom, ctx->d_cosLUT2, rsqrt, tilesX, numTiles);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
@@ -672,7 +673,7 @@ extern "C" int ckd_plasma_draw(ckd_ctx *ctx, const ckd_plasma_params *p, float t
 	fx.f.dirSin = ckdh::lutsinf(lut, angle);
 	fx.f.gamma = p->gamma;
 
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_plasma"));
 	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
 }
 
@@ -694,7 +695,7 @@ extern "C" int ckd_nautilus_draw(ckd_ctx *ctx, const ckd_nautilus_params *p, flo
 	fx.f.funkCos = ckdh::lutcosf(lut, time*ckdh::kGoldenRatio*0.1f);
 	fx.f.roll = MakeRot(ctx, p->roll*time);
 
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_nautilus"));
 	CKD_TRY(ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]));
 	const float blur = ckdh::BoxBlurScale(p->blur);
 	if (0.f != blur)
@@ -730,7 +731,7 @@ extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float t
 		f.zTerm = 1.f + zOffsFinal;
 		f.normalGrain = p->close_normal_grain;
 		SpikeyCloseEffect fx = { f };
-		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_close"));
 
 		const float mbOpacity = ckdh::saturatef(p->mix_blur_opacity);
 		if (mbOpacity > 0.f)
@@ -774,7 +775,7 @@ extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float t
 		f.yOffs = p->dist_y;
 		f.zTerm = -2.614f + p->dist_z;
 		SpikeyDistantEffect fx = { f };
-		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_distant"));
 		return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
 	}
 
@@ -782,7 +783,7 @@ extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float t
 	f.gx = p->speed*time; f.gy = 8.f; f.gz = 16.f;
 	f.warmup = 1.f+warmup;
 	SpikeySpecOnlyEffect fx = { f };
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_spec"));
 	CKD_TRY(ckd_old_blur_h(ctx, ctx->d_fxMap[0], ctx->d_fxMap[0], unsigned(ctx->fxX), unsigned(ctx->fxY), ckdh::BoxBlurScale(1.f+warmup)));
 	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
 }
@@ -818,6 +819,7 @@ extern "C" int ckd_tunnel_draw(ckd_ctx *ctx, const ckd_tunnel_params *p, float t
 	const int numTiles = tilesX*tilesY;
 	const int blocks = std::min(numTiles, ctx->numSMs*8);
 	const RsqrtTab rsqrt = { ctx->d_rsqrtTab, ctx->rsqrtLog2Bin };
+	ckd_prof_begin(ctx, "raymarch_tunnel", 8.0*geom.fxX*geom.fxY);
 	tunnel_kernel<<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(f, ctx->d_fxMap[0], ctx->d_fxMap[1],
 		static_cast<const uint32_t *>(tex.d_pixels), static_cast<const uint32_t *>(texFx.d_pixels), geom, ctx->d_cosLUT2, rsqrt, tilesX, numTiles);
 	CKD_CHECK_LAUNCH(ctx);
@@ -855,7 +857,7 @@ extern "C" int ckd_sinuses_draw(ckd_ctx *ctx, const ckd_sinuses_params *p, float
 	fx.f.origin[1] = cosine*3.14f + sine*ckdh::kGoldenRatio;
 	fx.f.origin[2] = pathTime;
 
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_sinuses"));
 	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
 }
 
@@ -872,6 +874,6 @@ extern "C" int ckd_laura_draw(ckd_ctx *ctx, const ckd_laura_params *p, float tim
 	fx.f.pitch = MakeRot(ctx, p->pitch);
 	fx.f.roll = MakeRot(ctx, p->roll*time);
 
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0]));
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_laura"));
 	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
 }

@@ -709,6 +709,7 @@ extern "C" int ckd_landscape_draw(ckd_ctx *ctx, const ckd_landscape_params *p, f
 	const int lineStride = ctx->resY | 1;
 	const size_t smem = size_t(kScapeColsPerBlock)*lineStride*4;
 	CKD_TRY(EnsureSmem(landscape_kernel, smem));
+	ckd_prof_begin(ctx, "voxel_landscape", 4.0*ctx->resX*ctx->resY);
 	landscape_kernel<<<ckd_div_up(ctx->resX, kScapeColsPerBlock), kScapeColsPerBlock*32, smem, ctx->stream>>>(pWrite,
 		static_cast<const uint8_t *>(ctx->images[CKD_IMG_SCAPE_HEIGHT].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_SCAPE_COLOR].d_pixels),
 		static_cast<const uint32_t *>(ctx->images[CKD_IMG_SCAPE_FOG].d_pixels), f, lineStride);
@@ -748,6 +749,7 @@ extern "C" int ckd_tunnelscape_draw(ckd_ctx *ctx, const ckd_tunnelscape_params *
 
 	const size_t smem = size_t(kRowsPerBlock)*ctx->resX*4;
 	CKD_TRY(EnsureSmem(tunnelscape_kernel, smem));
+	ckd_prof_begin(ctx, "voxel_tunnelscape", 4.0*ctx->resX*ctx->resY);
 	tunnelscape_kernel<<<ckd_div_up(ctx->resY, kRowsPerBlock), kRowsPerBlock*32, smem, ctx->stream>>>(ctx->d_renderTarget[0],
 		static_cast<const uint8_t *>(ctx->images[CKD_IMG_TSCAPE_HEIGHT].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_TSCAPE_COLOR].d_pixels),
 		static_cast<const uint32_t *>(ctx->images[CKD_IMG_TSCAPE_FOG].d_pixels), f);
@@ -863,12 +865,14 @@ extern "C" int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time,
 	if (hasBeams)
 	{
 		CKD_TRY(EnsureSmem(ball_kernel<true>, smem));
+		ckd_prof_begin(ctx, "voxel_ball_beams", 8.0*ctx->resX*ctx->resY);
 		ball_kernel<true><<<blocks, kRowsPerBlock*32, smem, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
 			static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_COLOR0].d_pixels), ctx->d_ballBeamMix, d_tables, d_rayDeltas, f);
 	}
 	else
 	{
 		CKD_TRY(EnsureSmem(ball_kernel<false>, smem));
+		ckd_prof_begin(ctx, "voxel_ball", 4.0*ctx->resX*ctx->resY);
 		ball_kernel<false><<<blocks, kRowsPerBlock*32, smem, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
 			static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_COLOR1].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_ENV].d_pixels), d_tables, d_rayDeltas, f);
 	}
@@ -930,6 +934,7 @@ extern "C" int ckd_twister_draw(ckd_ctx *ctx, const ckd_twister_params *p, float
 
 	const size_t smem = size_t(kRowsPerBlock)*ctx->resX*4;
 	CKD_TRY(EnsureSmem(twister_kernel, smem));
+	ckd_prof_begin(ctx, "voxel_twister", 4.0*ctx->resX*ctx->resY);
 	twister_kernel<<<ckd_div_up(ctx->resY, kRowsPerBlock), kRowsPerBlock*64, smem, ctx->stream>>>(ctx->d_renderTarget[0],
 		static_cast<const uint8_t *>(ctx->images[CKD_IMG_TWISTER_HEIGHT].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_TWISTER_COLOR].d_pixels),
 		d_tables, d_rayOrigins, ctx->resX, ctx->resY);

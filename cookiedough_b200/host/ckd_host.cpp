@@ -1,0 +1,925 @@
+// ckd_host.cpp -- C++ host layer: the reference's entry points (include/ckd_host.h) on top of the C ABI (include/ckd.h).
+//
+// Contains: the GNU Rocket reader (XML project or binary .track files) with sync_get_val's interpolation
+// (3rdparty/rocket-stripped/lib/track.c:9-60, device.c:41-78,309-332), the Rocket:: wrapper (rocket.cpp:26-92),
+// the per-effect Create/Draw/Destroy shims that read the same tracks the reference reads, and host-buffer wrappers of
+// the 2D post ops.
+
+#include "../../include/ckd_host.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ctype.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------------------------
+// error + context
+// ---------------------------------------------------------------------------------------------------------------
+
+static std::string s_lastError;
+void SetLastError(const std::string &description) { s_lastError = description; }
+const std::string &CkdHost_GetLastError() { return s_lastError; }
+
+static ckd_ctx *s_ctx = nullptr;
+static double s_timeSec = 0.0;
+static std::string s_rocketSource;
+
+struct HostImage { std::vector<uint8_t> pixels; int width, height, bpp; };
+static std::map<std::string, HostImage> s_images;
+
+static const double kRowRate = (170.0 / (60.0*(170.0/174.0)))*16.0; // audio.cpp:18
+
+static bool Check(int rc, const char *what)
+{
+	if (CKD_OK == rc)
+		return true;
+	SetLastError(std::string(what) + ": " + ckd_last_error());
+	return false;
+}
+
+bool CkdHost_Create(int resX, int resY, int device)
+{
+	if (nullptr != s_ctx)
+		CkdHost_Destroy();
+	return Check(ckd_create(&s_ctx, resX, resY, device), "CkdHost_Create");
+}
+
+void CkdHost_Destroy()
+{
+	ckd_destroy(s_ctx);
+	s_ctx = nullptr;
+}
+
+ckd_ctx *CkdHost_Context() { return s_ctx; }
+void CkdHost_SetRocketSource(const char *path) { s_rocketSource = path ? path : ""; }
+void CkdHost_SetTime(double seconds) { s_timeSec = seconds; }
+
+void CkdHost_RegisterImage(const char *path, const void *pixels, int width, int height, int bytesPerPixel)
+{
+	HostImage &img = s_images[path];
+	img.width = width; img.height = height; img.bpp = bytesPerPixel;
+	const size_t bytes = size_t(width)*height*bytesPerPixel;
+	img.pixels.assign(static_cast<const uint8_t *>(pixels), static_cast<const uint8_t *>(pixels) + bytes);
+}
+
+// Image_Load32 / Image_Load8 equivalent: registered pixels -> device image slot
+static bool LoadImage(const char *path, ckd_image slot, int bpp)
+{
+	if (nullptr == s_ctx)
+	{
+		SetLastError("CkdHost_Create() has not been called");
+		return false;
+	}
+	auto it = s_images.find(path);
+	if (it == s_images.end() || it->second.bpp != bpp)
+	{
+		SetLastError(std::string("Can not load image: ") + path); // image.cpp:40
+		return false;
+	}
+	return Check(ckd_set_image(s_ctx, slot, it->second.pixels.data(), it->second.width, it->second.height, bpp), path);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GNU Rocket
+// ---------------------------------------------------------------------------------------------------------------
+
+struct TrackKey { int row; float value; int type; }; // track.h:16-20
+struct ckd_sync_track { std::string name; std::vector<TrackKey> keys; };
+
+static std::map<std::string, std::unique_ptr<ckd_sync_track>> s_tracks;     // tracks handed out by AddTrack
+static std::map<std::string, std::vector<TrackKey>> s_xmlTracks;           // parsed XML project
+static bool s_launched = false;
+static double s_rocketRow = 0.0;
+static SyncTrack s_stopTrack = nullptr;
+
+// path_encode + sync_track_path, device.c:41-78
+static std::string TrackPath(const std::string &base, const std::string &name)
+{
+	std::string out = base + "_";
+	for (unsigned char ch : name)
+	{
+		if (ch == '.' || ch == '_' || ch == '/' || isalnum(ch))
+			out += char(ch);
+		else
+		{
+			out += '-';
+			out += "0123456789ABCDEF"[(ch >> 4) & 0xF];
+			out += "0123456789ABCDEF"[ch & 0xF];
+		}
+	}
+	return out + ".track";
+}
+
+// read_track_data, device.c:309-332
+static bool ReadTrackFile(const std::string &path, std::vector<TrackKey> &keys)
+{
+	FILE *fp = fopen(path.c_str(), "rb");
+	if (!fp)
+		return false;
+	int numKeys = 0;
+	if (1 != fread(&numKeys, sizeof(int), 1, fp) || numKeys < 0) { fclose(fp); return false; }
+	keys.resize(size_t(numKeys));
+	for (auto &key : keys)
+	{
+		char type = 0;
+		if (1 != fread(&key.row, sizeof(int), 1, fp) || 1 != fread(&key.value, sizeof(float), 1, fp) || 1 != fread(&type, sizeof(char), 1, fp))
+		{ fclose(fp); return false; }
+		key.type = type;
+	}
+	fclose(fp);
+	return true;
+}
+
+static bool Attr(const std::string &tag, const char *name, std::string &value)
+{
+	const std::string needle = std::string(name) + "=\"";
+	const size_t at = tag.find(needle);
+	if (at == std::string::npos)
+		return false;
+	const size_t from = at + needle.size();
+	const size_t to = tag.find('"', from);
+	if (to == std::string::npos)
+		return false;
+	value = tag.substr(from, to - from);
+	return true;
+}
+
+// <sync rows=".."><tracks><track name=".."><key interpolation=".." row=".." value=".."/>...
+static bool ParseRocketXml(const std::string &path)
+{
+	FILE *fp = fopen(path.c_str(), "rb");
+	if (!fp)
+		return false;
+	std::string text;
+	char buf[65536];
+	size_t n;
+	while ((n = fread(buf, 1, sizeof(buf), fp)) > 0)
+		text.append(buf, n);
+	fclose(fp);
+
+	s_xmlTracks.clear();
+	std::vector<TrackKey> *current = nullptr;
+	size_t pos = 0;
+	while ((pos = text.find('<', pos)) != std::string::npos)
+	{
+		const size_t end = text.find('>', pos);
+		if (end == std::string::npos)
+			break;
+		const std::string tag = text.substr(pos + 1, end - pos - 1);
+		pos = end + 1;
+		if (0 == tag.compare(0, 6, "track "))
+		{
+			std::string name;
+			if (!Attr(tag, "name", name))
+				return false;
+			current = &s_xmlTracks[name];
+		}
+		else if (0 == tag.compare(0, 4, "key ") && current)
+		{
+			std::string row, value, interp;
+			if (!Attr(tag, "row", row) || !Attr(tag, "value", value) || !Attr(tag, "interpolation", interp))
+				return false;
+			TrackKey key;
+			key.row = atoi(row.c_str());
+			key.value = strtof(value.c_str(), nullptr);
+			key.type = atoi(interp.c_str());
+			current->push_back(key);
+		}
+		else if (0 == tag.compare(0, 6, "/track"))
+			current = nullptr;
+	}
+	return !s_xmlTracks.empty();
+}
+
+static bool IsXmlSource() { return s_rocketSource.size() > 7 && 0 == s_rocketSource.compare(s_rocketSource.size() - 7, 7, ".rocket"); }
+
+// sync_find_key + key_idx_floor, track.c:62-85, track.h:29-35
+static int KeyIdxFloor(const std::vector<TrackKey> &keys, int row)
+{
+	int lo = 0, hi = int(keys.size());
+	while (lo < hi)
+	{
+		const int mi = (lo + hi)/2;
+		if (keys[mi].row < row) lo = mi + 1;
+		else if (keys[mi].row > row) hi = mi;
+		else return mi;
+	}
+	return lo - 1; // -(lo) - 1 negated and biased, then idx = -idx - 2
+}
+
+// sync_get_val, track.c:32-60 (double arithmetic, no -ffast-math)
+static double SyncGetVal(const ckd_sync_track *t, double row)
+{
+	const std::vector<TrackKey> &k = t->keys;
+	if (k.empty())
+		return 0.0;
+	const int irow = int(floor(row));
+	const int idx = KeyIdxFloor(k, irow);
+	if (idx < 0)
+		return k[0].value;
+	if (idx > int(k.size()) - 2)
+		return k[k.size() - 1].value;
+
+	const TrackKey &k0 = k[idx], &k1 = k[idx+1];
+	double u = (row - k0.row) / (k1.row - k0.row);
+	switch (k0.type)
+	{
+	case 0: return k0.value;                              // KEY_STEP
+	case 1: break;                                        // KEY_LINEAR
+	case 2: u = u*u*(3 - 2*u); break;                     // KEY_SMOOTH
+	case 3: u = pow(u, 2.0); break;                       // KEY_RAMP
+	default: return 0.0;
+	}
+	return k0.value + (k1.value - k0.value)*u;
+}
+
+namespace Rocket
+{
+	bool Launch()
+	{
+		s_tracks.clear();
+		if (s_rocketSource.empty())
+			s_rocketSource = "sync/"; // rocket.cpp:30
+		if (IsXmlSource() && !ParseRocketXml(s_rocketSource))
+		{
+			SetLastError("Can not read GNU Rocket project: " + s_rocketSource);
+			return false;
+		}
+		s_launched = true;
+		s_stopTrack = AddTrack("demo:quit"); // rocket.cpp:41
+		return true;
+	}
+
+	void Land()
+	{
+		s_tracks.clear();
+		s_xmlTracks.clear();
+		s_launched = false;
+	}
+
+	bool Boost()
+	{
+		s_rocketRow = s_timeSec*kRowRate; // Audio_Rocket_Sync, audio.cpp:175-178
+		if (nullptr != s_stopTrack && 0.0 != get(s_stopTrack))
+			return false;
+		return true;
+	}
+
+	// sync_get_track, device.c:589-611: a track that has no data yet is created empty (value 0)
+	SyncTrack AddTrack(const char *name)
+	{
+		auto it = s_tracks.find(name);
+		if (it != s_tracks.end())
+			return it->second.get();
+		std::unique_ptr<ckd_sync_track> track(new ckd_sync_track);
+		track->name = name;
+		if (IsXmlSource())
+		{
+			auto found = s_xmlTracks.find(name);
+			if (found != s_xmlTracks.end())
+				track->keys = found->second;
+		}
+		else
+		{
+			std::string base = s_rocketSource;
+			if (!base.empty() && base.back() != '/')
+				base += '/';
+			ReadTrackFile(TrackPath(base, name), track->keys);
+		}
+		SyncTrack result = track.get();
+		s_tracks[name] = std::move(track);
+		return result;
+	}
+
+	double get(SyncTrack track) { return SyncGetVal(track, s_rocketRow); }
+	int geti(SyncTrack track) { return int(roundf(getf(track))); } // rocket.h:27-29
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// frame helpers
+// ---------------------------------------------------------------------------------------------------------------
+
+static void Finish(int rc, uint32_t *pDest, const char *what)
+{
+	if (!Check(rc, what))
+		return;
+	const size_t bytes = size_t(ckd_res_x(s_ctx))*ckd_res_y(s_ctx)*sizeof(uint32_t);
+	if (Check(ckd_download(s_ctx, pDest, ckd_frame(s_ctx), bytes), what))
+		Check(ckd_sync(s_ctx), what);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shadertoy.cpp
+// ---------------------------------------------------------------------------------------------------------------
+
+static SyncTrack trackLauraSpeed, trackLauraYaw, trackLauraPitch, trackLauraRoll, trackLauraHue, trackLauraSaturate;
+static SyncTrack trackNautilusRoll, trackNautilusBlur, trackNautilusHue, trackNautilusSpeed, trackNautilusDesaturation;
+static SyncTrack trackSpikeSpeed, trackSpikeRoll, trackSpikeSpecular, trackSpikeDesaturation, trackDistSpikeWarmup, trackSpikeHue, trackSpikeGamma;
+static SyncTrack trackDistSpikeX, trackDistSpikeY, trackDistSpikeZ, trackCloseSpikeX, trackCloseSpikeY, trackCloseSpikeZ, trackCloseSpikeZScale;
+static SyncTrack trackCloseSpikeNormalGrain, trackCloseSpikeScale, trackCloseSpikeRim, trackCloseSpikeAspectMul;
+static SyncTrack trackCloseMixBlurMap, trackCloseMixBlur, trackCloseMixBlurOpacity, trackCloseMixMapBlur;
+static SyncTrack trackSinusesSpecular, trackSinusesRoll, trackSinusesSpeed, trackSinusesOffsX, trackSinusesGamma, trackSinusesHue, trackSinusesDesat;
+static SyncTrack trackPlasmaSpeed, trackPlasmaHue, trackPlasmaGamma, trackPlasmaDesat;
+static SyncTrack trackTunnelBoxy, trackTunnelFlowerScale, trackTunnelFlowerFreq, trackTunnelFlowerPhase, trackTunnelSpeed, trackTunnelRoll, trackTunnelPitch;
+static SyncTrack trackTunnelRadius, trackTunnelMulU, trackTunnelMulV, trackTunnelLitTiles, trackTunnelLitBlur, trackTunnelFog1, trackTunnelFog2;
+
+// shadertoy.cpp:101-188
+bool Shadertoy_Create()
+{
+	trackLauraSpeed = Rocket::AddTrack("laura:Speed");
+	trackLauraYaw = Rocket::AddTrack("laura:Yaw");
+	trackLauraPitch = Rocket::AddTrack("laura:Pitch");
+	trackLauraRoll = Rocket::AddTrack("laura:Roll");
+	trackLauraHue = Rocket::AddTrack("laura:Hue");
+	trackLauraSaturate = Rocket::AddTrack("laura:Saturate");
+
+	trackNautilusRoll = Rocket::AddTrack("nautilus:Roll");
+	trackNautilusBlur = Rocket::AddTrack("nautilus:Blur");
+	trackNautilusHue = Rocket::AddTrack("nautilus:Hue");
+	trackNautilusSpeed = Rocket::AddTrack("nautilus:Speed");
+	trackNautilusDesaturation = Rocket::AddTrack("nautilus:Desat");
+
+	trackSpikeSpeed = Rocket::AddTrack("spike:Speed");
+	trackSpikeRoll = Rocket::AddTrack("spike:Roll");
+	trackSpikeSpecular = Rocket::AddTrack("spike:Specular");
+	trackSpikeDesaturation = Rocket::AddTrack("spike:Desaturation");
+	trackDistSpikeWarmup = Rocket::AddTrack("distSpike:Warmup");
+	trackSpikeHue = Rocket::AddTrack("spike:Hue");
+	trackSpikeGamma = Rocket::AddTrack("spike:Gamma");
+	trackDistSpikeX = Rocket::AddTrack("distSpike:xOffs");
+	trackDistSpikeY = Rocket::AddTrack("distSpike:yOffs");
+	trackDistSpikeZ = Rocket::AddTrack("distSpike:zOffs");
+	trackCloseSpikeX = Rocket::AddTrack("closeSpike:xOffs");
+	trackCloseSpikeY = Rocket::AddTrack("closeSpike:yOffs");
+	trackCloseSpikeZ = Rocket::AddTrack("closeSpike:zOffs");
+	trackCloseSpikeZScale = Rocket::AddTrack("closeSpike:zOffsScale");
+	trackCloseSpikeNormalGrain = Rocket::AddTrack("closeSpike:NormalGrain");
+	trackCloseSpikeScale = Rocket::AddTrack("closeSpike:Scale");
+	trackCloseSpikeRim = Rocket::AddTrack("closeSpike:Rim");
+	trackCloseSpikeAspectMul = Rocket::AddTrack("closeSpike:AspectMul");
+	trackCloseMixBlurMap = Rocket::AddTrack("closeSpike:MixBlurMap");
+	trackCloseMixBlur = Rocket::AddTrack("closeSpike:MixBlur");
+	trackCloseMixMapBlur = Rocket::AddTrack("closeSpike:MixMapBlur");
+	trackCloseMixBlurOpacity = Rocket::AddTrack("closeSpike:MixBlurOpacity");
+
+	trackSinusesSpecular = Rocket::AddTrack("sinusesTunnel:Specular");
+	trackSinusesRoll = Rocket::AddTrack("sinusesTunnel:Roll");
+	trackSinusesSpeed = Rocket::AddTrack("sinusesTunnel:Speed");
+	trackSinusesOffsX = Rocket::AddTrack("sinusesTunnel:OffsX");
+	trackSinusesGamma = Rocket::AddTrack("sinusesTunnel:Gamma");
+	trackSinusesHue = Rocket::AddTrack("sinusesTunnel:Hue");
+	trackSinusesDesat = Rocket::AddTrack("sinusesTunnel:Desaturation");
+
+	trackPlasmaSpeed = Rocket::AddTrack("plasma:Speed");
+	trackPlasmaHue = Rocket::AddTrack("plasma:Hue");
+	trackPlasmaGamma = Rocket::AddTrack("plasma:Gamma");
+	trackPlasmaDesat = Rocket::AddTrack("plasma:Desaturation");
+
+	trackTunnelBoxy = Rocket::AddTrack("tunnel:Boxy");
+	trackTunnelFlowerScale = Rocket::AddTrack("tunnel:FlowerScale");
+	trackTunnelFlowerFreq = Rocket::AddTrack("tunnel:FlowerFreq");
+	trackTunnelFlowerPhase = Rocket::AddTrack("tunnel:FlowerPhase");
+	trackTunnelSpeed = Rocket::AddTrack("tunnel:Speed");
+	trackTunnelRoll = Rocket::AddTrack("tunnel:Roll");
+	trackTunnelPitch = Rocket::AddTrack("tunnel:Pitch");
+	trackTunnelRadius = Rocket::AddTrack("tunnel:Radius");
+	trackTunnelMulU = Rocket::AddTrack("tunnel:MulU");
+	trackTunnelMulV = Rocket::AddTrack("tunnel:MulV");
+	trackTunnelLitTiles = Rocket::AddTrack("tunnel:LitTiles");
+	trackTunnelLitBlur = Rocket::AddTrack("tunnel:LitBlur");
+	trackTunnelFog1 = Rocket::AddTrack("tunnel:Fog1");
+	trackTunnelFog2 = Rocket::AddTrack("tunnel:Fog2");
+
+	if (!LoadImage("assets/shadertoy/nytrik-hextexture.png", CKD_IMG_TUNNEL_TEX, 4)
+		|| !LoadImage("assets/shadertoy/nytrik-hextexture-fx.png", CKD_IMG_TUNNEL_TEX_FX, 4))
+		return false;
+
+	// these *must* be FX map sized (shadertoy.cpp:179-183)
+	if (!LoadImage("assets/shadertoy/close-up-blur-map-1.png", CKD_IMG_SPIKE_BLUR_MAP0, 4)
+		|| !LoadImage("assets/shadertoy/close-up-blur-map-2.png", CKD_IMG_SPIKE_BLUR_MAP1, 4))
+		return false;
+	for (const char *path : { "assets/shadertoy/close-up-blur-map-1.png", "assets/shadertoy/close-up-blur-map-2.png" })
+	{
+		const HostImage &img = s_images[path];
+		if (img.width != ckd_fxmap_res_x(s_ctx) || img.height != ckd_fxmap_res_y(s_ctx))
+		{
+			SetLastError(std::string(path) + " must be FX-map sized");
+			return false;
+		}
+	}
+	return true;
+}
+
+void Shadertoy_Destroy() {}
+
+// shadertoy.cpp:276-280
+void Plasma_Draw(uint32_t *pDest, float time, float delta)
+{
+	(void)delta;
+	ckd_plasma_params p;
+	p.speed = Rocket::getf(trackPlasmaSpeed);
+	p.hue = Rocket::getf(trackPlasmaHue);
+	p.gamma = Rocket::getf(trackPlasmaGamma);
+	p.desaturation = Rocket::getf(trackPlasmaDesat);
+	Finish(ckd_plasma_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Plasma_Draw");
+}
+
+// shadertoy.cpp:395-407
+void Nautilus_Draw(uint32_t *pDest, float time, float delta)
+{
+	(void)delta;
+	ckd_nautilus_params p;
+	p.roll = Rocket::getf(trackNautilusRoll);
+	p.hue = Rocket::getf(trackNautilusHue);
+	p.speed = Rocket::getf(trackNautilusSpeed);
+	p.desaturation = Rocket::getf(trackNautilusDesaturation);
+	p.blur = Rocket::getf(trackNautilusBlur);
+	Finish(ckd_nautilus_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Nautilus_Draw");
+}
+
+// shadertoy.cpp:661-733
+void Spikey_Draw(uint32_t *pDest, float time, float delta, bool close /* = true */)
+{
+	(void)delta;
+	ckd_spikey_params p;
+	p.speed = Rocket::getf(trackSpikeSpeed);
+	p.roll = Rocket::getf(trackSpikeRoll);
+	p.specular = Rocket::getf(trackSpikeSpecular);
+	p.desaturation = Rocket::getf(trackSpikeDesaturation);
+	p.hue = Rocket::getf(trackSpikeHue);
+	p.gamma = Rocket::getf(trackSpikeGamma);
+	p.warmup = Rocket::getf(trackDistSpikeWarmup);
+	p.dist_x = Rocket::getf(trackDistSpikeX);
+	p.dist_y = Rocket::getf(trackDistSpikeY);
+	p.dist_z = Rocket::getf(trackDistSpikeZ);
+	p.close_x = Rocket::getf(trackCloseSpikeX);
+	p.close_y = Rocket::getf(trackCloseSpikeY);
+	p.close_z = Rocket::getf(trackCloseSpikeZ);
+	p.close_z_scale = Rocket::getf(trackCloseSpikeZScale);
+	p.close_normal_grain = Rocket::getf(trackCloseSpikeNormalGrain);
+	p.close_scale = Rocket::getf(trackCloseSpikeScale);
+	p.close_rim = Rocket::geti(trackCloseSpikeRim);
+	p.close_aspect_mul = Rocket::geti(trackCloseSpikeAspectMul);
+	p.mix_blur_map = Rocket::getf(trackCloseMixBlurMap);
+	p.mix_blur = Rocket::getf(trackCloseMixBlur);
+	p.mix_map_blur = Rocket::getf(trackCloseMixMapBlur);
+	p.mix_blur_opacity = Rocket::getf(trackCloseMixBlurOpacity);
+	Finish(ckd_spikey_draw(s_ctx, &p, time, close ? 1 : 0, ckd_frame(s_ctx)), pDest, "Spikey_Draw");
+}
+
+// shadertoy.cpp:840-861
+void Tunnel_Draw(uint32_t *pDest, float time, float delta)
+{
+	(void)delta;
+	ckd_tunnel_params p;
+	p.boxy = Rocket::getf(trackTunnelBoxy);
+	p.flower_scale = Rocket::getf(trackTunnelFlowerScale);
+	p.flower_freq = Rocket::getf(trackTunnelFlowerFreq);
+	p.flower_phase = Rocket::getf(trackTunnelFlowerPhase);
+	p.speed = Rocket::getf(trackTunnelSpeed);
+	p.roll = Rocket::getf(trackTunnelRoll);
+	p.pitch = Rocket::getf(trackTunnelPitch);
+	p.radius = Rocket::getf(trackTunnelRadius);
+	p.mul_u = Rocket::getf(trackTunnelMulU);
+	p.mul_v = Rocket::getf(trackTunnelMulV);
+	p.lit_tiles = Rocket::geti(trackTunnelLitTiles);
+	p.lit_blur = Rocket::getf(trackTunnelLitBlur);
+	p.fog1 = Rocket::getf(trackTunnelFog1);
+	p.fog2 = Rocket::getf(trackTunnelFog2);
+	Finish(ckd_tunnel_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Tunnel_Draw");
+}
+
+// shadertoy.cpp:984-988
+void Sinuses_Draw(uint32_t *pDest, float time, float delta)
+{
+	(void)delta;
+	ckd_sinuses_params p;
+	p.specular = Rocket::getf(trackSinusesSpecular);
+	p.roll = Rocket::getf(trackSinusesRoll);
+	p.speed = Rocket::getf(trackSinusesSpeed);
+	p.offs_x = Rocket::getf(trackSinusesOffsX);
+	p.gamma = Rocket::getf(trackSinusesGamma);
+	p.hue = Rocket::getf(trackSinusesHue);
+	p.desaturation = Rocket::getf(trackSinusesDesat);
+	Finish(ckd_sinuses_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Sinuses_Draw");
+}
+
+// shadertoy.cpp:1105-1109
+void Laura_Draw(uint32_t *pDest, float time, float delta)
+{
+	(void)delta;
+	ckd_laura_params p;
+	p.speed = Rocket::getf(trackLauraSpeed);
+	p.yaw = Rocket::getf(trackLauraYaw);
+	p.pitch = Rocket::getf(trackLauraPitch);
+	p.roll = Rocket::getf(trackLauraRoll);
+	p.hue = Rocket::getf(trackLauraHue);
+	p.saturate = Rocket::getf(trackLauraSaturate);
+	Finish(ckd_laura_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Laura_Draw");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// landscape.cpp
+// ---------------------------------------------------------------------------------------------------------------
+
+static SyncTrack trackVoxelScapeForward, trackVoxelScapeTilt, trackWarpSpeed, trackWarpStrength;
+
+// landscape.cpp:194-222
+bool Landscape_Create()
+{
+	if (!LoadImage("assets/scape/D17.png", CKD_IMG_SCAPE_HEIGHT, 1) || !LoadImage("assets/scape/C17W-edit.png", CKD_IMG_SCAPE_COLOR, 4))
+		return false;
+	if (!LoadImage("assets/scape/foggradient.jpg", CKD_IMG_SCAPE_FOG, 4))
+		return false;
+	trackVoxelScapeForward = Rocket::AddTrack("voxelScape:Forward");
+	trackVoxelScapeTilt = Rocket::AddTrack("voxelScape:Tilt");
+	trackWarpSpeed = Rocket::AddTrack("voxelScape:WarpSpeed");
+	trackWarpStrength = Rocket::AddTrack("voxelScape:WarpStrength");
+	return true;
+}
+
+void Landscape_Destroy() {}
+
+// landscape.cpp:228-243; the gamepad (landscape.cpp:112-154) is absent in a headless run: its accumulated state stays zero
+void Landscape_Draw(uint32_t *pDest, float time, float delta)
+{
+	(void)delta;
+	ckd_landscape_params p;
+	memset(&p, 0, sizeof(p));
+	p.forward = Rocket::getf(trackVoxelScapeForward);
+	p.tilt = Rocket::getf(trackVoxelScapeTilt);
+	p.warp_speed = Rocket::getf(trackWarpSpeed);
+	p.warp_strength = Rocket::getf(trackWarpStrength);
+	Finish(ckd_landscape_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Landscape_Draw");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tunnelscape.cpp
+// ---------------------------------------------------------------------------------------------------------------
+
+static SyncTrack trackStarsStepU, trackStarsStepV, trackStarsSpeed, trackStarsBlur;
+
+// tunnelscape.cpp:136-162
+bool Tunnelscape_Create()
+{
+	if (!LoadImage("assets/scape/tscape-D7-edit.png", CKD_IMG_TSCAPE_HEIGHT, 1) || !LoadImage("assets/scape/tscape-C7W-edit.png", CKD_IMG_TSCAPE_COLOR, 4))
+		return false;
+	if (!LoadImage("assets/scape/foggradient.jpg", CKD_IMG_TSCAPE_FOG, 4))
+		return false;
+	trackStarsStepU = Rocket::AddTrack("starsTunnel:stepU");
+	trackStarsStepV = Rocket::AddTrack("starsTunnel:stepV");
+	trackStarsSpeed = Rocket::AddTrack("starsTunnel:Speed");
+	trackStarsBlur = Rocket::AddTrack("starsTunnel:Blur");
+	return true;
+}
+
+void Tunnelscape_Destroy() {}
+
+// tunnelscape.cpp:168-186
+void Tunnelscape_Draw(uint32_t *pDest, float time, float delta)
+{
+	(void)delta;
+	ckd_tunnelscape_params p;
+	p.step_u = Rocket::getf(trackStarsStepU);
+	p.step_v = Rocket::getf(trackStarsStepV);
+	p.speed = Rocket::getf(trackStarsSpeed);
+	p.blur = Rocket::getf(trackStarsBlur);
+	Finish(ckd_tunnelscape_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Tunnelscape_Draw");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ball.cpp
+// ---------------------------------------------------------------------------------------------------------------
+
+static SyncTrack trackBallBlur, trackBallRadius, trackBallRayLength, trackBallSpikes, trackBallHasBeams, trackBallBaseShapeIndex, trackBallSpeed;
+static SyncTrack trackBallBeamAtten, trackBallBeamAlphaMin, trackBallRotateOffsX, trackBallRotateOffsY, trackBallBeams1, trackBallBeams2, trackBallBeams3, trackBallLowBeams;
+
+// ball.cpp:367-450
+bool Ball_Create()
+{
+	static const char *kHeightMapPaths[5] = { "assets/ball/hmap_1_1k.jpg", "assets/ball/hmap_4_1k.jpg", "assets/ball/hmap_2_1k.jpg", "assets/ball/hmap_3_1k.jpg", "assets/ball/hmap_5_1k.jpg" };
+	for (int iMap = 0; iMap < 5; ++iMap)
+		if (!LoadImage(kHeightMapPaths[iMap], ckd_image(CKD_IMG_BALL_HEIGHT0 + iMap), 1))
+			return false;
+	if (!LoadImage("assets/ball/colormap_1k.jpg", CKD_IMG_BALL_COLOR0, 4) || !LoadImage("assets/ball/colormap_2_1k.jpg", CKD_IMG_BALL_COLOR1, 4))
+		return false;
+	if (!LoadImage("assets/ball/beammap_1k_1.jpg", CKD_IMG_BALL_BEAM0, 4) || !LoadImage("assets/ball/beammap_1k_2.jpg", CKD_IMG_BALL_BEAM1, 4)
+		|| !LoadImage("assets/ball/beammap_1k_3-2.jpg", CKD_IMG_BALL_BEAM2, 4))
+		return false;
+	if (!LoadImage("assets/ball/envmap3_1k.jpg", CKD_IMG_BALL_ENV, 4))
+		return false;
+	if (!LoadImage("assets/ball/nytrik-background_1280x720.png", CKD_IMG_BALL_BACKGROUND0, 4)
+		|| !LoadImage("assets/ball/nytrik-background-2-1280x720.png", CKD_IMG_BALL_BACKGROUND1, 4))
+		return false;
+	if (!LoadImage("assets/ball/halo.png", CKD_IMG_BALL_HALO, 4))
+		return false;
+
+	trackBallBlur = Rocket::AddTrack("ball:Blur");
+	trackBallRadius = Rocket::AddTrack("ball:Radius");
+	trackBallRayLength = Rocket::AddTrack("ball:RayLength");
+	trackBallSpikes = Rocket::AddTrack("ball:Spikes");
+	trackBallHasBeams = Rocket::AddTrack("ball:HasBeams");
+	trackBallBaseShapeIndex = Rocket::AddTrack("ball:BaseShapeIndex");
+	trackBallSpeed = Rocket::AddTrack("ball:Speed");
+	trackBallBeamAtten = Rocket::AddTrack("ball:BeamAttenuation");
+	trackBallBeamAlphaMin = Rocket::AddTrack("ball:BeamAlphaMin");
+	trackBallRotateOffsX = Rocket::AddTrack("ball:RotateOffsX");
+	trackBallRotateOffsY = Rocket::AddTrack("ball:RotateOffsY");
+	trackBallBeams1 = Rocket::AddTrack("ball:Beams1");
+	trackBallBeams2 = Rocket::AddTrack("ball:Beams2");
+	trackBallBeams3 = Rocket::AddTrack("ball:Beams3");
+	trackBallLowBeams = Rocket::AddTrack("ball:BallLowBeams");
+	return true;
+}
+
+void Ball_Destroy() {}
+
+// ball.cpp:452-514
+void Ball_Draw(uint32_t *pDest, float time, float delta)
+{
+	(void)delta;
+	ckd_ball_params p;
+	p.blur = Rocket::getf(trackBallBlur);
+	p.radius = Rocket::getf(trackBallRadius);
+	p.ray_length = Rocket::geti(trackBallRayLength);
+	p.spikes = Rocket::geti(trackBallSpikes);
+	p.has_beams = Rocket::geti(trackBallHasBeams);
+	p.base_shape_index = Rocket::geti(trackBallBaseShapeIndex);
+	p.speed = Rocket::getf(trackBallSpeed);
+	p.beam_atten = Rocket::geti(trackBallBeamAtten);
+	p.beam_alpha_min = Rocket::getf(trackBallBeamAlphaMin);
+	p.rotate_offs_x = Rocket::getf(trackBallRotateOffsX);
+	p.rotate_offs_y = Rocket::getf(trackBallRotateOffsY);
+	p.beams1 = Rocket::getf(trackBallBeams1);
+	p.beams2 = Rocket::getf(trackBallBeams2);
+	p.beams3 = Rocket::getf(trackBallBeams3);
+	p.low_beams = Rocket::geti(trackBallLowBeams);
+	Finish(ckd_ball_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Ball_Draw");
+}
+
+bool Ball_HasBeams() { return Rocket::geti(trackBallHasBeams) != 0; } // ball.cpp:521-524
+
+// ---------------------------------------------------------------------------------------------------------------
+// torus-twister.cpp
+// ---------------------------------------------------------------------------------------------------------------
+
+static SyncTrack trackTwisterSpeed, trackTwisterShearSpeed, trackTwisterBlur;
+
+// torus-twister.cpp:139-160
+bool Twister_Create()
+{
+	if (!LoadImage("assets/twister/hmap_2_1k.jpg", CKD_IMG_TWISTER_HEIGHT, 1) || !LoadImage("assets/twister/colormap_1k.jpg", CKD_IMG_TWISTER_COLOR, 4))
+		return false;
+	if (!LoadImage("assets/twister/nytrik-background_1280x720.png", CKD_IMG_TWISTER_BACKGROUND, 4))
+		return false;
+	trackTwisterSpeed = Rocket::AddTrack("twister:Speed");
+	trackTwisterShearSpeed = Rocket::AddTrack("twister::ShearSpeed"); // sic (torus-twister.cpp:156)
+	trackTwisterBlur = Rocket::AddTrack("twister:Blur");
+	return true;
+}
+
+void Twister_Destroy() {}
+
+// torus-twister.cpp:166-188
+void Twister_Draw(uint32_t *pDest, float time, float delta)
+{
+	(void)delta;
+	ckd_twister_params p;
+	p.speed = Rocket::getf(trackTwisterSpeed);
+	p.shear_speed = Rocket::getf(trackTwisterShearSpeed);
+	p.blur = Rocket::getf(trackTwisterBlur);
+	Finish(ckd_twister_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Twister_Draw");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2D post ops on host buffers: upload -> kernel -> download.  Staging uses the context's render targets 2 and 3,
+// which no effect touches.
+// ---------------------------------------------------------------------------------------------------------------
+
+namespace {
+
+struct Staged
+{
+	uint32_t *d_dest = nullptr;
+	const uint32_t *d_src = nullptr;
+	uint32_t *pDest;
+	size_t destBytes;
+	bool ok = false;
+
+	Staged(uint32_t *pDest_, size_t destPixels, const uint32_t *pSrc, size_t srcPixels, bool destIsInput)
+		: pDest(pDest_), destBytes(destPixels*4)
+	{
+		if (nullptr == s_ctx) { SetLastError("CkdHost_Create() has not been called"); return; }
+		const size_t cap = size_t(ckd_res_x(s_ctx))*ckd_res_y(s_ctx);
+		if (destPixels > cap || srcPixels > cap) { SetLastError("buffer larger than the output resolution"); return; }
+		d_dest = ckd_render_target(s_ctx, 2);
+		if (destIsInput && !Check(ckd_upload(s_ctx, d_dest, pDest, destBytes), "upload")) return;
+		if (pSrc == pDest || nullptr == pSrc)
+			d_src = d_dest;
+		else
+		{
+			uint32_t *d = ckd_render_target(s_ctx, 3);
+			if (!Check(ckd_upload(s_ctx, d, pSrc, srcPixels*4), "upload")) return;
+			d_src = d;
+		}
+		ok = true;
+	}
+
+	void Finish(int rc, const char *what)
+	{
+		if (ok && Check(rc, what) && Check(ckd_download(s_ctx, pDest, d_dest, destBytes), what))
+			Check(ckd_sync(s_ctx), what);
+	}
+};
+
+void Blend(ckd_blend_op op, uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels, float f, unsigned u, const char *what)
+{
+	Staged s(pDest, numPixels, pSrc, numPixels, true);
+	if (s.ok) s.Finish(ckd_blend(s_ctx, op, s.d_dest, s.d_src, numPixels, f, u), what);
+}
+
+size_t OutPixels() { return s_ctx ? size_t(ckd_res_x(s_ctx))*ckd_res_y(s_ctx) : 0; }
+size_t FxPixels() { return s_ctx ? size_t(ckd_fxmap_res_x(s_ctx))*ckd_fxmap_res_y(s_ctx) : 0; }
+
+} // namespace
+
+void Polar_Blit(uint32_t *pDest, const uint32_t *pSrc, bool inverse)
+{
+	Staged s(pDest, OutPixels(), pSrc, OutPixels(), false);
+	if (s.ok) s.Finish(ckd_polar_blit(s_ctx, s.d_dest, s.d_src, inverse), "Polar_Blit");
+}
+
+void Polar_BlitA(uint32_t *pDest, const uint32_t *pSrc, bool inverse)
+{
+	Staged s(pDest, OutPixels(), pSrc, OutPixels(), true);
+	if (s.ok) s.Finish(ckd_polar_blit_a(s_ctx, s.d_dest, s.d_src, inverse), "Polar_BlitA");
+}
+
+void Fx_Blit_2x2(uint32_t *pDest, const uint32_t *pSrc)
+{
+	Staged s(pDest, OutPixels(), pSrc, FxPixels(), false);
+	if (s.ok) s.Finish(ckd_fx_blit_2x2(s_ctx, s.d_dest, s.d_src), "Fx_Blit_2x2");
+}
+
+void HorizontalBoxBlur32(uint32_t *pDest, const uint32_t *pSrc, unsigned int xRes, unsigned int yRes, float strength)
+{
+	Staged s(pDest, size_t(xRes)*yRes, pSrc, size_t(xRes)*yRes, pDest == pSrc);
+	if (s.ok) s.Finish(ckd_old_blur_h(s_ctx, s.d_dest, s.d_src, xRes, yRes, strength), "HorizontalBoxBlur32");
+}
+
+void VerticalBoxBlur32(uint32_t *pDest, const uint32_t *pSrc, unsigned int xRes, unsigned int yRes, float strength)
+{
+	Staged s(pDest, size_t(xRes)*yRes, pSrc, size_t(xRes)*yRes, pDest == pSrc);
+	if (s.ok) s.Finish(ckd_old_blur_v(s_ctx, s.d_dest, s.d_src, xRes, yRes, strength), "VerticalBoxBlur32");
+}
+
+void BoxBlur32(uint32_t *pDest, const uint32_t *pSrc, unsigned int xRes, unsigned int yRes, float strength)
+{
+	Staged s(pDest, size_t(xRes)*yRes, pSrc, size_t(xRes)*yRes, pDest == pSrc);
+	if (s.ok) s.Finish(ckd_old_blur(s_ctx, s.d_dest, s.d_src, xRes, yRes, strength), "BoxBlur32");
+}
+
+float BoxBlurScale(float strength) { return ckd_box_blur_scale(strength); }
+
+void BoxBlur_Horz32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float gain, unsigned numPasses)
+{
+	Staged s(pDest, size_t(xRes)*yRes, pSrc, size_t(xRes)*yRes, pDest == pSrc);
+	if (s.ok) s.Finish(ckd_new_blur_h(s_ctx, s.d_dest, s.d_src, xRes, yRes, strength, gain, numPasses), "BoxBlur_Horz32");
+}
+
+void BoxBlur_Vert32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float gain, unsigned numPasses)
+{
+	Staged s(pDest, size_t(xRes)*yRes, pSrc, size_t(xRes)*yRes, pDest == pSrc);
+	if (s.ok) s.Finish(ckd_new_blur_v(s_ctx, s.d_dest, s.d_src, xRes, yRes, strength, gain, numPasses), "BoxBlur_Vert32");
+}
+
+void BoxBlur_32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float gain, unsigned numPasses)
+{
+	Staged s(pDest, size_t(xRes)*yRes, pSrc, size_t(xRes)*yRes, pDest == pSrc);
+	if (s.ok) s.Finish(ckd_new_blur(s_ctx, s.d_dest, s.d_src, xRes, yRes, strength, gain, numPasses), "BoxBlur_32");
+}
+
+void Mix32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels, uint8_t alpha) { Blend(CKD_MIX32, pDest, pSrc, numPixels, 0.f, alpha, "Mix32"); }
+void MixOver32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels) { Blend(CKD_MIXOVER32, pDest, pSrc, numPixels, 0.f, 0, "MixOver32"); }
+void Add32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels) { Blend(CKD_ADD32, pDest, pSrc, numPixels, 0.f, 0, "Add32"); }
+void Sub32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels) { Blend(CKD_SUB32, pDest, pSrc, numPixels, 0.f, 0, "Sub32"); }
+void Excl32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels) { Blend(CKD_EXCL32, pDest, pSrc, numPixels, 0.f, 0, "Excl32"); }
+void SoftLight32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels) { Blend(CKD_SOFTLIGHT32, pDest, pSrc, numPixels, 0.f, 0, "SoftLight32"); }
+void SoftLight32A(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels) { Blend(CKD_SOFTLIGHT32A, pDest, pSrc, numPixels, 0.f, 0, "SoftLight32A"); }
+void SoftLight32AA(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels, float alpha) { Blend(CKD_SOFTLIGHT32AA, pDest, pSrc, numPixels, alpha, 0, "SoftLight32AA"); }
+void Overlay32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels) { Blend(CKD_OVERLAY32, pDest, pSrc, numPixels, 0.f, 0, "Overlay32"); }
+void Overlay32A(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels) { Blend(CKD_OVERLAY32A, pDest, pSrc, numPixels, 0.f, 0, "Overlay32A"); }
+void Darken32_50(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels) { Blend(CKD_DARKEN32_50, pDest, pSrc, numPixels, 0.f, 0, "Darken32_50"); }
+void MulSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels) { Blend(CKD_MULSRC32, pDest, pSrc, numPixels, 0.f, 0, "MulSrc32"); }
+void MulSrc32A(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels) { Blend(CKD_MULSRC32A, pDest, pSrc, numPixels, 0.f, 0, "MulSrc32A"); }
+void MixSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels) { Blend(CKD_MIXSRC32, pDest, pSrc, numPixels, 0.f, 0, "MixSrc32"); }
+void Fade32(uint32_t *pDest, unsigned int numPixels, uint32_t RGB, uint8_t alpha) { Blend(CKD_FADE32, pDest, nullptr, numPixels, 0.f, (unsigned(alpha) << 24) | (RGB & 0xffffff), "Fade32"); }
+
+void TapeWarp32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float speed)
+{
+	Staged s(pDest, size_t(xRes)*yRes, pSrc, size_t(xRes)*yRes, false);
+	if (s.ok) s.Finish(ckd_tape_warp(s_ctx, s.d_dest, s.d_src, xRes, yRes, strength, speed), "TapeWarp32");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// extern "C" hooks so ctypes-based tests and bench.py can drive the C++ entry points above
+// ---------------------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int ckdhost_create(int resX, int resY, int device, const char *rocketSource)
+{
+	if (!CkdHost_Create(resX, resY, device))
+		return -1;
+	CkdHost_SetRocketSource(rocketSource);
+	return 0;
+}
+
+// Rocket::Launch + the five X_Create, demo.cpp:140-148
+int ckdhost_launch()
+{
+	if (!Rocket::Launch()) return -2;
+	if (!Twister_Create()) return -3;
+	if (!Landscape_Create()) return -4;
+	if (!Ball_Create()) return -5;
+	if (!Tunnelscape_Create()) return -6;
+	if (!Shadertoy_Create()) return -7;
+	return 0;
+}
+
+void ckdhost_destroy()
+{
+	Twister_Destroy(); Landscape_Destroy(); Ball_Destroy(); Tunnelscape_Destroy(); Shadertoy_Destroy();
+	Rocket::Land();
+	CkdHost_Destroy();
+}
+
+void ckdhost_register_image(const char *path, const void *pixels, int width, int height, int bpp) { CkdHost_RegisterImage(path, pixels, width, height, bpp); }
+const char *ckdhost_last_error() { return s_lastError.c_str(); }
+void *ckdhost_context() { return s_ctx; }
+
+int ckdhost_set_time(double seconds)
+{
+	CkdHost_SetTime(seconds);
+	return Rocket::Boost() ? 1 : 0;
+}
+
+// Rocket only (no GPU needed): used by the CPU-side tests of the track reader
+int ckdhost_rocket_open(const char *rocketSource)
+{
+	CkdHost_SetRocketSource(rocketSource);
+	return Rocket::Launch() ? 0 : -1;
+}
+
+double ckdhost_track(const char *name) { return Rocket::get(Rocket::AddTrack(name)); }
+int ckdhost_track_i(const char *name) { return Rocket::geti(Rocket::AddTrack(name)); }
+
+// same effect ids as oracle/ref_shim.cpp
+int ckdhost_draw(int effect, uint32_t *pDest, float time, float delta)
+{
+	s_lastError.clear();
+	switch (effect)
+	{
+	case 0: Plasma_Draw(pDest, time, delta); break;
+	case 1: Nautilus_Draw(pDest, time, delta); break;
+	case 2: Spikey_Draw(pDest, time, delta, true); break;
+	case 3: Spikey_Draw(pDest, time, delta, false); break;
+	case 4: Tunnel_Draw(pDest, time, delta); break;
+	case 5: Sinuses_Draw(pDest, time, delta); break;
+	case 6: Laura_Draw(pDest, time, delta); break;
+	case 7: Landscape_Draw(pDest, time, delta); break;
+	case 8: Tunnelscape_Draw(pDest, time, delta); break;
+	case 9: Ball_Draw(pDest, time, delta); break;
+	case 10: Twister_Draw(pDest, time, delta); break;
+	default: return -1;
+	}
+	return s_lastError.empty() ? 0 : -2;
+}
+
+int ckdhost_post(int op, uint32_t *pDest, const uint32_t *pSrc, unsigned a, unsigned b, float f0, float f1, unsigned u)
+{
+	s_lastError.clear();
+	switch (op)
+	{
+	case 0: Fx_Blit_2x2(pDest, pSrc); break;
+	case 1: Polar_Blit(pDest, pSrc, 0 != u); break;
+	case 2: Polar_BlitA(pDest, pSrc, 0 != u); break;
+	case 3: HorizontalBoxBlur32(pDest, pSrc, a, b, f0); break;
+	case 4: VerticalBoxBlur32(pDest, pSrc, a, b, f0); break;
+	case 5: BoxBlur32(pDest, pSrc, a, b, f0); break;
+	case 6: BoxBlur_32(pDest, pSrc, a, b, f0, f1, u); break;
+	case 7: MixSrc32(pDest, pSrc, a); break;
+	case 8: SoftLight32(pDest, pSrc, a); break;
+	case 9: TapeWarp32(pDest, pSrc, a, b, f0, f1); break;
+	default: return -1;
+	}
+	return s_lastError.empty() ? 0 : -2;
+}
+
+} // extern "C"

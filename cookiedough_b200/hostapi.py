@@ -1,0 +1,120 @@
+"""ctypes driver of the C++ host layer (include/ckd_host.h): the reference's own X_Create / X_Draw(uint32_t *pDest, float
+time, float delta) entry points with HOST buffers.  bench.py's end-to-end leg and the drop-in tests go through this."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+ROW_RATE = (170.0 / (60.0 * (170.0 / 174.0))) * 16.0  # code/audio.cpp:18
+
+EFFECT_IDS = {"plasma": 0, "nautilus": 1, "spikey_close": 2, "spikey_distant": 3, "tunnel": 4, "sinuses": 5, "laura": 6,
+              "landscape": 7, "tunnelscape": 8, "ball": 9, "twister": 10}
+POST_IDS = {"Fx_Blit_2x2": 0, "Polar_Blit": 1, "Polar_BlitA": 2, "HorizontalBoxBlur32": 3, "VerticalBoxBlur32": 4, "BoxBlur32": 5,
+            "BoxBlur_32": 6, "MixSrc32": 7, "SoftLight32": 8, "TapeWarp32": 9}
+
+_U32P = C.POINTER(C.c_uint32)
+
+
+def _lib():
+    L = capi.load()
+    if getattr(L, "_host_bound", False):
+        return L
+    L.ckdhost_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p]
+    L.ckdhost_launch.argtypes = []
+    L.ckdhost_register_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.ckdhost_last_error.restype = C.c_char_p
+    L.ckdhost_context.restype = C.c_void_p
+    L.ckdhost_set_time.argtypes = [C.c_double]
+    L.ckdhost_rocket_open.argtypes = [C.c_char_p]
+    L.ckdhost_track.argtypes = [C.c_char_p]
+    L.ckdhost_track.restype = C.c_double
+    L.ckdhost_track_i.argtypes = [C.c_char_p]
+    L.ckdhost_draw.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_float]
+    L.ckdhost_post.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_uint]
+    L._host_bound = True
+    return L
+
+
+def default_rocket_source():
+    """the demo's Rocket project: the XML shipped with the reference when oracle/_ref/data holds a copy"""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return os.environ.get("CKD_ROCKET", os.path.join(here, "oracle", "_ref", "data", "directors-cut.rocket"))
+
+
+class RocketOnly:
+    """the host layer's GNU Rocket reader without a GPU context (CPU-side tests)"""
+
+    def __init__(self, source):
+        self.L = _lib()
+        if self.L.ckdhost_rocket_open(str(source).encode()) != 0:
+            raise capi.CkdError(self.L.ckdhost_last_error().decode())
+
+    def set_time(self, seconds):
+        return self.L.ckdhost_set_time(float(seconds))
+
+    def set_row(self, row):
+        return self.set_time(row / ROW_RATE)
+
+    def track(self, name):
+        return self.L.ckdhost_track(name.encode())
+
+    def track_i(self, name):
+        return self.L.ckdhost_track_i(name.encode())
+
+
+class Host:
+    """CkdHost_Create + Rocket::Launch + the five X_Create (code/main.cpp:263-279, code/demo.cpp:140-148)"""
+
+    def __init__(self, res_x, res_y, device, assets, rocket_source=None):
+        self.L = _lib()
+        self.res_x, self.res_y = res_x, res_y
+        source = rocket_source or default_rocket_source()
+        if self.L.ckdhost_create(res_x, res_y, device, str(source).encode()) != 0:
+            raise capi.CkdError(self.L.ckdhost_last_error().decode())
+        for path in capi.IMAGE_SLOTS:
+            arr = assets[path]
+            self.L.ckdhost_register_image(path.encode(), arr.ctypes.data, arr.shape[1], arr.shape[0], 1 if arr.dtype == np.uint8 else 4)
+        rc = self.L.ckdhost_launch()
+        if rc != 0:
+            raise capi.CkdError(f"host launch failed ({rc}): {self.L.ckdhost_last_error().decode()}")
+        self.ctx_handle = self.L.ckdhost_context()
+        self.time = 0.0
+
+    def context(self):
+        """a capi.Context view of the host layer's ckd_ctx (not owning)"""
+        ctx = capi.Context.__new__(capi.Context)
+        ctx.L = self.L
+        ctx.h = C.c_void_p(self.ctx_handle)
+        ctx.res_x, ctx.res_y = self.res_x, self.res_y
+        ctx.fx_x, ctx.fx_y = self.res_x // 2 + 4, self.res_y // 2 + 4
+        ctx._user = []
+        ctx.close = lambda: None
+        return ctx
+
+    def set_time(self, seconds):
+        self.time = float(seconds)
+        return self.L.ckdhost_set_time(self.time)
+
+    def set_row(self, row):
+        return self.set_time(row / ROW_RATE)
+
+    def track(self, name):
+        return self.L.ckdhost_track(name.encode())
+
+    def draw(self, effect, out, delta=1.6667):
+        """X_Draw(pDest, time, delta) into the caller's host buffer (numpy uint32, or a raw address)"""
+        ptr = out if isinstance(out, int) else out.ctypes.data
+        rc = self.L.ckdhost_draw(EFFECT_IDS[effect], C.c_void_p(ptr), C.c_float(self.time), C.c_float(delta))
+        if rc != 0:
+            raise capi.CkdError(f"{effect}: {self.L.ckdhost_last_error().decode()}")
+        return out
+
+    def post(self, op, dst, src, a=0, b=0, f0=0.0, f1=0.0, u=0):
+        rc = self.L.ckdhost_post(POST_IDS[op], dst.ctypes.data, src.ctypes.data if src is not None else None, a, b, C.c_float(f0), C.c_float(f1), u)
+        if rc != 0:
+            raise capi.CkdError(f"{op}: {self.L.ckdhost_last_error().decode()}")
+
+    def close(self):
+        self.L.ckdhost_destroy()

@@ -269,6 +269,18 @@ int ckd_twister_draw(ckd_ctx *ctx, const ckd_twister_params *p, float time, uint
 /* number of CUDA kernels this library launched on this context so far (bench.py's gpu_launches) */
 unsigned long long ckd_launch_count(const ckd_ctx *ctx);
 
+/* per-kernel timing with CUDA events on the context's stream (measurement only; replaces nothing in the reference,
+ * whose only meter is the average-FPS counter of main.cpp:352-356).  ckd_profile_begin() starts recording a pair of
+ * events around every kernel launch; ckd_profile_end() synchronises and returns one aggregate per kernel name. */
+typedef struct ckd_kernel_stat {
+	char name[48];
+	unsigned launches;
+	double total_ms;       /* sum of the per-launch event durations */
+	double algo_bytes;     /* sum of the algorithmic bytes of those launches (SURVEY.md 8d / DESIGN.md) */
+} ckd_kernel_stat;
+int ckd_profile_begin(ckd_ctx *ctx);
+int ckd_profile_end(ckd_ctx *ctx, ckd_kernel_stat *out_stats, int max_stats, int *out_count);
+
 #ifdef __cplusplus
 }
 #endif

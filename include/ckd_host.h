@@ -1,0 +1,118 @@
+// ckd_host.h -- C++ host layer of cookiedough_b200: the reference's own entry points, backed by the CUDA kernels.
+//
+// Every function below keeps the name, signature, argument meaning and error behaviour of the reference declaration it
+// replaces (cited per block, paths relative to the reference's code/ directory), so demo.cpp-style callers compile
+// unchanged: X_Create() returns bool and reports through SetLastError(), X_Draw(uint32_t *pDest, float time, float delta)
+// fully overwrites the caller-owned HOST buffer pDest (resX*resY ARGB8888), parameters are pulled from the global
+// Rocket row exactly where the reference pulls them.  Internally each call fills a POD struct, calls the C ABI
+// (include/ckd.h) on device-resident buffers and copies the finished frame back.
+//
+// The services the reference takes from SDL/BASS/DevIL are replaced by the small CkdHost_* block: resolution and device
+// selection (compile-time kResX/kResY in the reference), the time source (BASS stream position), and pre-decoded images.
+#pragma once
+
+#include <stdint.h>
+#include <string>
+
+#include "ckd.h"
+
+// ---- headless services (replace main.cpp:213-311 start-up, audio.cpp:159-186, image.cpp:31-73) ----------------------
+
+// LUTs, render targets, FX maps, polar maps, blur scratch (main.cpp:263-279) on GPU 'device'; false + SetLastError on failure
+bool CkdHost_Create(int resX, int resY, int device);
+void CkdHost_Destroy();
+ckd_ctx *CkdHost_Context();
+
+// Rocket data source: a GNU Rocket XML project (target/directors-cut.rocket) or a directory with binary "sync/_*.track"
+// files (what sync_create_device("sync/") reads, rocket.cpp:30).  Must be set before Rocket::Launch().
+void CkdHost_SetRocketSource(const char *path);
+
+// time source of Rocket::Boost(): row = seconds * kRowRate (audio.cpp:18,175-178)
+void CkdHost_SetTime(double seconds);
+
+// pre-decoded image for a path the reference would hand to Image_Load32 / Image_Load8 (image.h:10-11);
+// bytesPerPixel 4 = BGRA, 1 = luminance.  The pixels are copied.
+void CkdHost_RegisterImage(const char *path, const void *pixels, int width, int height, int bytesPerPixel);
+
+// main.h:49 / main.cpp:175-180
+void SetLastError(const std::string &description);
+const std::string &CkdHost_GetLastError();
+
+// ---- rocket.h:13-29 ----------------------------------------------------------------------------------------------------
+
+struct ckd_sync_track;
+typedef const ckd_sync_track *SyncTrack;
+
+namespace Rocket
+{
+	bool Launch();
+	void Land();
+	bool Boost();
+	SyncTrack AddTrack(const char *name);
+	double get(SyncTrack track);
+	inline float getf(SyncTrack track) { return (float) get(track); }
+	int geti(SyncTrack track);
+}
+
+// ---- shadertoy.h:6-15 -------------------------------------------------------------------------------------------------
+
+bool Shadertoy_Create();
+void Shadertoy_Destroy();
+void Nautilus_Draw(uint32_t *pDest, float time, float delta);
+void Spikey_Draw(uint32_t *pDest, float time, float delta, bool close = true);
+void Sinuses_Draw(uint32_t *pDest, float time, float delta);
+void Laura_Draw(uint32_t *pDest, float time, float delta);
+void Plasma_Draw(uint32_t *pDest, float time, float delta);
+void Tunnel_Draw(uint32_t *pDest, float time, float delta);
+
+// ---- landscape.h:7-9, tunnelscape.h:7-9, ball.h:7-13, torus-twister.h:7-9 ---------------------------------------------
+
+bool Landscape_Create();
+void Landscape_Destroy();
+void Landscape_Draw(uint32_t *pDest, float time, float delta);
+
+bool Tunnelscape_Create();
+void Tunnelscape_Destroy();
+void Tunnelscape_Draw(uint32_t *pDest, float time, float delta);
+
+bool Ball_Create();
+void Ball_Destroy();
+void Ball_Draw(uint32_t *pDest, float time, float delta);
+bool Ball_HasBeams();
+
+bool Twister_Create();
+void Twister_Destroy();
+void Twister_Draw(uint32_t *pDest, float time, float delta);
+
+// ---- 2D post chain on HOST buffers (polar.h:7-17, deprecated/boxblur.h:21-41, boxblur.h:7-20, fx-blitter.h:26-33,
+//      util.h:57-122).  pDest/pSrc may alias where the reference allows it. ---------------------------------------------
+
+void Polar_Blit(uint32_t *pDest, const uint32_t *pSrc, bool inverse = false);
+void Polar_BlitA(uint32_t *pDest, const uint32_t *pSrc, bool inverse = false);
+void Fx_Blit_2x2(uint32_t *pDest, const uint32_t *pSrc);
+
+void HorizontalBoxBlur32(uint32_t *pDest, const uint32_t *pSrc, unsigned int xRes, unsigned int yRes, float strength);
+void VerticalBoxBlur32(uint32_t *pDest, const uint32_t *pSrc, unsigned int xRes, unsigned int yRes, float strength);
+void BoxBlur32(uint32_t *pDest, const uint32_t *pSrc, unsigned int xRes, unsigned int yRes, float strength);
+float BoxBlurScale(float strength);
+
+void BoxBlur_Horz32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float gain, unsigned numPasses);
+void BoxBlur_Vert32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float gain, unsigned numPasses);
+void BoxBlur_32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float gain, unsigned numPasses);
+
+void Mix32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels, uint8_t alpha);
+void MixOver32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
+void Add32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
+void Sub32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
+void Excl32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
+void SoftLight32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
+void SoftLight32A(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
+void SoftLight32AA(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels, float alpha);
+void Overlay32(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
+void Overlay32A(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
+void Darken32_50(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
+void MulSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels);
+void MulSrc32A(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels);
+void MixSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels);
+void Fade32(uint32_t *pDest, unsigned int numPixels, uint32_t RGB, uint8_t alpha);
+void TapeWarp32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float speed);

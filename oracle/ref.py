@@ -182,13 +182,19 @@ class Reference:
         fn = {"h": self.lib.ref_new_blur_h, "v": self.lib.ref_new_blur_v, "hv": self.lib.ref_new_blur}[kind]
         fn(_p32(dst), _p32(src), w, h, C.c_float(strength), C.c_float(gain), passes)
 
-    def blend(self, op, dst, src, fparam=0.0, uparam=0):
-        rc = self.lib.ref_blend(BLEND_OPS[op], _p32(dst), _p32(src), dst.size, C.c_float(fparam), C.c_uint(uparam))
+    def blend(self, op, dst, src, fparam=0.0, uparam=0, n=None):
+        rc = self.lib.ref_blend(BLEND_OPS[op], _p32(dst), _p32(src), dst.size if n is None else n, C.c_float(fparam), C.c_uint(uparam))
         assert rc == 0
 
     def blit(self, op, dst, src, dest_res_x, src_res_x, y_res, alpha=1.0):
         rc = self.lib.ref_blit(BLIT_OPS[op], _p32(dst), _p32(src), dest_res_x, src_res_x, y_res, C.c_float(alpha))
         assert rc == 0
+
+    def mix_src_s(self, dst, src, dest_res_x, dest_res_y, src_stride):
+        self.lib.ref_mix_src_s(_p32(dst), _p32(src), dest_res_x, dest_res_y, src_stride)
+
+    def memset32(self, dst, value, n):
+        self.lib.ref_memset32(_p32(dst), C.c_int(int(np.uint32(value).astype(np.int32))), n)
 
     def tape_warp(self, dst, src, w, h, strength, speed):
         self.lib.ref_tape_warp(_p32(dst), _p32(src), w, h, C.c_float(strength), C.c_float(speed))

@@ -1,0 +1,75 @@
+"""CPU-side checks of the drop-in boundary: the C ABI library loads, exports every symbol include/ckd.h declares,
+the header is valid C with the same struct layouts the Python binding uses, and the product fails loudly without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+from conftest import HAVE_GPU, REPO
+
+HEADER = os.path.join(REPO, "include", "ckd.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ckd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cookiedough_b200 import capi
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    names = declared_functions()
+    assert len(names) > 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"include/ckd.h declares symbols the library does not export: {missing}"
+
+
+def test_header_is_plain_c_and_struct_layouts_match_binding():
+    from cookiedough_b200 import capi
+    structs = {
+        "ckd_plasma_params": capi.PlasmaParams, "ckd_nautilus_params": capi.NautilusParams, "ckd_spikey_params": capi.SpikeyParams,
+        "ckd_tunnel_params": capi.TunnelParams, "ckd_sinuses_params": capi.SinusesParams, "ckd_laura_params": capi.LauraParams,
+        "ckd_landscape_params": capi.LandscapeParams, "ckd_tunnelscape_params": capi.TunnelscapeParams,
+        "ckd_ball_params": capi.BallParams, "ckd_twister_params": capi.TwisterParams,
+    }
+    body = "".join(f'printf("{n} %zu\\n", sizeof({n}));\n' for n in structs)
+    src = f'#include <stdio.h>\n#include "ckd.h"\nint main(void) {{ {body} printf("images %d\\n", (int)CKD_IMG_COUNT); return 0; }}\n'
+    with tempfile.TemporaryDirectory() as tmp:
+        c = os.path.join(tmp, "t.c")
+        exe = os.path.join(tmp, "t")
+        open(c, "w").write(src)
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), c, "-o", exe])
+        out = subprocess.check_output([exe], text=True)
+    sizes = dict(line.split() for line in out.strip().splitlines())
+    for name, cls in structs.items():
+        assert int(sizes[name]) == ctypes.sizeof(cls), name
+    assert int(sizes["images"]) == 27
+    slots = []
+    for v in capi.IMAGE_SLOTS.values():
+        slots += list(v) if isinstance(v, tuple) else [v]
+    assert sorted(slots) == list(range(27))
+
+
+def test_struct_fields_map_to_rocket_tracks():
+    from cookiedough_b200 import capi
+    for effect, (cls, names) in capi.TRACKS.items():
+        fields = {n for n, _ in cls._fields_}
+        assert set(names) <= fields, effect
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="this check is for GPU-less hosts")
+def test_no_cpu_fallback_without_gpu():
+    from cookiedough_b200 import capi
+    with pytest.raises(capi.CkdError) as err:
+        capi.Context(1280, 720)
+    assert "no CPU fallback" in str(err.value) or "CUDA" in str(err.value)
+
+
+def test_geti_matches_roundf():
+    from cookiedough_b200.capi import geti
+    assert [geti(v) for v in (0.4, 0.5, 1.5, 2.5, -0.5, -1.5, 511.7)] == [0, 1, 2, 3, -1, -2, 512]

@@ -1,0 +1,120 @@
+"""GPU parity of the integer 2D post chain: bit-exact against the committed goldens and the live compiled reference."""
+import numpy as np
+import pytest
+
+import post_cases as pc
+from util import assert_bit_exact, sha256_u32
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", pc.CASES, ids=[c["label"] for c in pc.CASES])
+def test_post_case_matches_golden(case, ctx_synth, golden_post):
+    out = pc.run_cuda(ctx_synth, case)
+    assert sha256_u32(out) == golden_post[case["label"]], case["label"]
+
+
+def test_post_cases_match_live_reference(live720):
+    R, ctx = live720
+    for case in pc.CASES:
+        assert_bit_exact(pc.run_cuda(ctx, case), pc.run_reference(R, case), case["label"])
+
+
+def test_polar_maps_match_reference_behaviour(live720):
+    """the UV maps are built on the host like the reference does: a remap of an index image pins every entry"""
+    R, ctx = live720
+    n = R.res_x * R.res_y
+    src = np.arange(n, dtype=np.uint32).reshape(R.res_y, R.res_x) * np.uint32(0x01000193)
+    for inverse in (False, True):
+        ref_dst = R.frame()
+        R.polar_blit(ref_dst, np.ascontiguousarray(src), inverse)
+        d_src = ctx.to_device(src, pad_elems=4 * R.res_x)
+        ctx.polar_blit(ctx.frame(), d_src, inverse)
+        assert_bit_exact(ctx.read_frame(), ref_dst, f"polar inverse={inverse}")
+        ctx.free(d_src)
+
+
+# ---- 4K: size-independent properties + live reference -------------------------------------------------------------
+
+def test_post_chain_4k_against_reference(live2160):
+    """Polar_Blit(inverse) -> BoxBlur32 in place -> Fx_Blit_2x2 -> blends at 3840x2160"""
+    R, ctx = live2160
+    w, h = R.res_x, R.res_y
+    n = w * h
+    src = pc.seeded(n, "mul").reshape(h, w)
+    dst = pc.seeded(n, "mix").reshape(h, w)
+    fx = pc.seeded(R.fx_x * R.fx_y, "noise").reshape(R.fx_y, R.fx_x)
+
+    from oracle.ref import aligned_u32
+    r_src = aligned_u32(n, pad=4 * w).reshape(h, w); r_src[:] = src
+    r_dst = aligned_u32(n, pad=4 * w).reshape(h, w); r_dst[:] = dst
+    r_fx = aligned_u32(fx.size, pad=4 * w).reshape(fx.shape); r_fx[:] = fx
+    r_tmp = aligned_u32(n, pad=4 * w).reshape(h, w)
+
+    d_src = ctx.to_device(src, pad_elems=4 * w)
+    d_dst = ctx.to_device(dst, pad_elems=4 * w)
+    d_fx = ctx.to_device(fx, pad_elems=4 * w)
+    d_tmp = ctx.to_device(np.zeros(n, dtype=np.uint32), pad_elems=4 * w)
+
+    R.polar_blit(r_dst, r_src, True)
+    ctx.polar_blit(d_dst, d_src, True)
+    assert_bit_exact(ctx.download(d_dst, (h, w)), r_dst, "4K Polar_Blit(inverse)")
+
+    for strength in (0.11, 0.01, 0.33, 1.0):
+        R.old_blur("hv", r_dst, r_dst, w, h, strength)
+        ctx.old_blur("hv", d_dst, d_dst, w, h, strength)
+        assert_bit_exact(ctx.download(d_dst, (h, w)), r_dst, f"4K BoxBlur32 in place s={strength}")
+
+    R.fx_blit_2x2(r_tmp, r_fx)
+    ctx.fx_blit_2x2(d_tmp, d_fx)
+    assert_bit_exact(ctx.download(d_tmp, (h, w)), r_tmp, "4K Fx_Blit_2x2")
+
+    for op in ("MixSrc32", "SoftLight32", "Overlay32"):
+        R.blend(op, r_dst, r_tmp)
+        ctx.blend(op, d_dst, d_tmp, n)
+        assert_bit_exact(ctx.download(d_dst, (h, w)), r_dst, f"4K {op}")
+
+    R.new_blur("hv", r_tmp, r_dst, w, h, 6.28, 0.1, 3)
+    ctx.new_blur("hv", d_tmp, d_dst, w, h, 6.28, 0.1, 3)
+    assert_bit_exact(ctx.download(d_tmp, (h, w)), r_tmp, "4K BoxBlur_32 kGauss")
+
+    R.polar_blit(r_dst, r_tmp, False, alpha=True)
+    ctx.polar_blit(d_dst, d_tmp, False, alpha=True)
+    assert_bit_exact(ctx.download(d_dst, (h, w)), r_dst, "4K Polar_BlitA")
+
+    for d in (d_src, d_dst, d_fx, d_tmp):
+        ctx.free(d)
+
+
+def test_post_properties_4k(live2160):
+    """identities that hold at any size (no oracle needed)"""
+    _, ctx = live2160
+    w, h = ctx.res_x, ctx.res_y
+    n = w * h
+    a = pc.seeded(n, "noise")
+    const = np.full(n, 0x80402010, dtype=np.uint32)
+    d_a = ctx.to_device(a, pad_elems=4 * w)
+    d_b = ctx.to_device(a, pad_elems=4 * w)
+    d_c = ctx.to_device(const, pad_elems=4 * w)
+    d_z = ctx.to_device(np.zeros(n, dtype=np.uint32), pad_elems=4 * w)
+
+    ctx.blend("Mix32", d_a, d_c, n, uparam=0)            # alpha 0 keeps dest
+    assert np.array_equal(ctx.download(d_a, (n,)), a)
+    ctx.blend("Add32", d_a, d_z, n)                       # + 0
+    assert np.array_equal(ctx.download(d_a, (n,)), a)
+    ctx.blend("Sub32", d_a, d_b, n)                       # x - x
+    assert not ctx.download(d_a, (n,)).any()
+    ctx.polar_blit(d_a, d_c, False)                       # remap of a constant image is constant
+    assert np.array_equal(ctx.download(d_a, (n,)), const)
+    fx = np.full(ctx.fx_x * ctx.fx_y, 0x11223344, dtype=np.uint32)
+    d_fx = ctx.to_device(fx, pad_elems=4 * w)
+    ctx.fx_blit_2x2(d_a, d_fx)                            # upsample of a constant map is constant
+    assert np.array_equal(ctx.download(d_a, (n,)), np.full(n, 0x11223344, dtype=np.uint32))
+    ctx.memset32(d_a, 0xdeadbeef, n)
+    assert np.array_equal(ctx.download(d_a, (n,)), np.full(n, 0xdeadbeef, dtype=np.uint32))
+    # blurring twice from the same input is deterministic
+    ctx.upload(d_a, a); ctx.old_blur("hv", d_a, d_a, w, h, 0.2); first = ctx.download(d_a, (n,))
+    ctx.upload(d_a, a); ctx.old_blur("hv", d_a, d_a, w, h, 0.2)
+    assert np.array_equal(ctx.download(d_a, (n,)), first)
+    for d in (d_a, d_b, d_c, d_z, d_fx):
+        ctx.free(d)
