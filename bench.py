@@ -215,9 +215,19 @@ def run_ours(args):
         step_device(i)
     barrier()
 
+    # clocks: nvidia-smi needs ~1 s to come up, the timed region may be shorter: start it now, keep the identical load
+    # running until it has produced samples, then time the K steps with the sampler still attached
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_load = time.perf_counter()
+        i = 0
+        while time.perf_counter() - t_load < 2.5 and len(sampler.lines) < 8:
+            step_device(i)
+            i += 1
+            if i % 8 == 0:
+                torch.cuda.synchronize()
+    barrier()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -227,6 +237,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - launches0
+    if rank == 0:
+        # keep the same load up briefly so the 100 ms sampler certainly sees the region's clocks
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.4:
+            step_device(0)
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)

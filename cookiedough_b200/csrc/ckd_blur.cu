@@ -91,6 +91,226 @@ __global__ void __launch_bounds__(128) old_blur_kernel(uint8_t *pDest, const uin
 	}
 }
 
+// ---- staged version: the production path -----------------------------------------------------------------------------
+// One WARP owns 8 neighbouring lines (lanes = 8 lines x 4 channels).  The lines' pixels stream through a shared-memory
+// ring that is filled ahead of time with 16-byte cp.async copies (kPrefetch stages of 64 steps in flight), so the serial
+// walk never waits for HBM; results go to a second ring from which (a) the in-place trailing edge re-reads the pixels
+// "it already wrote" and (b) finished 64-step chunks are flushed with coalesced 16-byte stores.  Every global byte is
+// read once and written once; what remains is the dependent add/clamp chain of the recurrence itself.
+
+constexpr unsigned kRing = 512;                 // ring length in steps: >= 255 (widest kernel) + (kPrefetch+1)*kStage
+constexpr unsigned kStage = 64;                 // steps per cp.async group / per flush
+constexpr int kPrefetch = 3;                    // groups in flight ahead of the one being consumed
+constexpr unsigned kPitchH = kRing*4 + 16;      // bytes per line in the horizontal layout (+16: lines land in different banks)
+constexpr unsigned kRingBytes = 8*kPitchH;      // >= kRing*32 (vertical layout)
+
+__device__ __forceinline__ void cp_async16(void *smemDst, const void *gmemSrc, bool valid)
+{
+	const unsigned dst = unsigned(__cvta_generic_to_shared(smemDst));
+	const int bytes = valid ? 16 : 0; // 0 -> zero fill
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(gmemSrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+constexpr int kBlurWarps = 4;                   // warps per CTA: one per SM sub-partition (a 1-warp CTA always lands on sub-partition 0)
+
+template <bool VERT, bool INPLACE>
+__global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t *pDest, const uint8_t *pSrc, unsigned numLines, unsigned len, unsigned pitch, OldBlurSetup s)
+{
+	extern __shared__ __align__(16) uint8_t s_rings[]; // per warp: input ring, output ring
+	const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint8_t *s_in = s_rings + warp*(2*kRingBytes);
+	uint8_t *s_out = s_in + kRingBytes;
+
+	const unsigned r = lane >> 2, chan = lane & 3;
+	const unsigned line0 = (blockIdx.x*kBlurWarps + warp)*8;
+	if (line0 >= numLines)
+		return;
+
+	constexpr unsigned kStep = VERT ? 32 : 4;       // ring bytes between consecutive steps of one line
+	const unsigned laneBase = VERT ? (r*4 + chan) : (r*kPitchH + chan);
+	auto ringAt = [&](unsigned pos) -> unsigned { return laneBase + (pos & (kRing-1))*kStep; };
+
+	// global <-> ring transfers of the 64 steps starting at p0, 16 bytes per lane and instruction
+	auto loadStage = [&](unsigned p0)
+	{
+		#pragma unroll
+		for (unsigned k = 0; k < 4; ++k)
+		{
+			if (VERT)
+			{
+				const unsigned pos = p0 + k*16 + (lane >> 1), col = line0 + (lane & 1)*4;
+				const bool valid = pos < len && col + 3 < numLines;
+				cp_async16(s_in + (pos & (kRing-1))*32 + (lane & 1)*16, valid ? pSrc + (size_t(pos)*pitch + col)*4 : pSrc, valid);
+			}
+			else
+			{
+				const unsigned pos = p0 + (k*4 + (lane & 3))*4, line = line0 + (lane >> 2);
+				const bool valid = pos < len && line < numLines;
+				cp_async16(s_in + (lane >> 2)*kPitchH + (pos & (kRing-1))*4, valid ? pSrc + (size_t(line)*pitch + pos)*4 : pSrc, valid);
+			}
+		}
+	};
+	auto flushStage = [&](unsigned p0)
+	{
+		#pragma unroll
+		for (unsigned k = 0; k < 4; ++k)
+		{
+			if (VERT)
+			{
+				const unsigned pos = p0 + k*16 + (lane >> 1), col = line0 + (lane & 1)*4;
+				if (pos < len && col + 3 < numLines)
+					*reinterpret_cast<uint4 *>(pDest + (size_t(pos)*pitch + col)*4) = *reinterpret_cast<const uint4 *>(s_out + (pos & (kRing-1))*32 + (lane & 1)*16);
+			}
+			else
+			{
+				const unsigned pos = p0 + (k*4 + (lane & 3))*4, line = line0 + (lane >> 2);
+				if (pos < len && line < numLines)
+					*reinterpret_cast<uint4 *>(pDest + (size_t(line)*pitch + pos)*4) = *reinterpret_cast<const uint4 *>(s_out + (lane >> 2)*kPitchH + (pos & (kRing-1))*4);
+			}
+		}
+	};
+
+	const int sh = int(s.remainderShift);
+	const unsigned edgeSpan = s.edgeSpan, kM = s.kernelMedian, span = edgeSpan + kM;
+	const unsigned total = len + edgeSpan;           // step t adds pixel t (while t < len) and emits output t - edgeSpan
+	const unsigned numStages = (total + kStage - 1)/kStage;
+	const unsigned mainEnd = len - edgeSpan;         // outputs [kM, mainEnd) are the full-weight main pass
+	const unsigned fullDiv = s.fullDiv;
+
+	#pragma unroll
+	for (int p = 0; p < kPrefetch; ++p)
+	{
+		loadStage(p*kStage);
+		cp_async_commit();
+	}
+
+	int acc = 0, addRem = 0, subRem = 0;
+	unsigned flushed = 0;
+	unsigned long long hist = 0;                    // the last 8 outputs of this lane, newest in the low byte (short in-place kernels)
+	const unsigned histShift = (kM - 1)*8;
+	const bool shortInPlace = INPLACE && kM < 8;
+
+	// value the trailing edge subtracts at output o: pixel o - kM of the *source as the reference sees it*: already blurred
+	// when running in place, the original otherwise
+	auto subAt = [&](unsigned pos) -> int { return INPLACE ? int(s_out[ringAt(pos)]) : int(s_in[ringAt(pos)]); };
+
+	// one steady-state step: Add + Sub + Div (deprecated/boxblur.cpp:104-110) with the four saturating 16-bit operations folded:
+	// max(min(acc + a, 65535) - b, 0) == max(min(acc + (a - b), 65535 - b), 0), a single DPX add-min-relu
+	auto steady = [&](int px, int spx) -> unsigned
+	{
+		const int a = addRem + (px - (px >> sh));
+		addRem = px >> sh;
+		const int b = subRem + (spx - (spx >> sh));
+		subRem = spx >> sh;
+		acc = __viaddmin_s32_relu(acc, a - b, 65535 - b);
+		return old_div(unsigned(acc), fullDiv);
+	};
+
+	for (unsigned stage = 0; stage < numStages; ++stage)
+	{
+		loadStage((stage + kPrefetch)*kStage);
+		cp_async_commit();
+		cp_async_wait<kPrefetch>();
+		__syncwarp();
+
+		const unsigned t0 = stage*kStage;
+		const unsigned t1 = min(t0 + kStage, total);
+
+		if (t0 >= span && t1 <= len && t1 - t0 == kStage)
+		{
+			for (unsigned tb = t0; tb < t1; tb += 8)
+			{
+				const uint8_t *inp = s_in + laneBase + (tb & (kRing-1))*kStep; // tb is a multiple of 8: no wrap inside the batch
+				const unsigned subPos = (tb - span) & (kRing-1), outPos = (tb - edgeSpan) & (kRing-1);
+				int px[8];
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) px[j] = int(inp[j*kStep]);
+
+				if (shortInPlace)
+				{
+					// the subtracted pixel was produced fewer than 8 steps ago: take it from the register history
+					#pragma unroll
+					for (int j = 0; j < 8; ++j)
+					{
+						const int spx = int((hist >> histShift) & 0xff);
+						const unsigned o = steady(px[j], spx);
+						hist = (hist << 8) | o;
+						s_out[laneBase + ((outPos + j) & (kRing-1))*kStep] = uint8_t(o);
+					}
+				}
+				else
+				{
+					const uint8_t *subBase = (INPLACE ? s_out : s_in) + laneBase;
+					int spx[8];
+					if (subPos <= kRing-8 && outPos <= kRing-8)
+					{
+						#pragma unroll
+						for (int j = 0; j < 8; ++j) spx[j] = int(subBase[(subPos + j)*kStep]);
+						uint8_t *outp = s_out + laneBase + outPos*kStep;
+						#pragma unroll
+						for (int j = 0; j < 8; ++j) outp[j*kStep] = uint8_t(steady(px[j], spx[j]));
+					}
+					else
+					{
+						#pragma unroll
+						for (int j = 0; j < 8; ++j) spx[j] = int(subBase[((subPos + j) & (kRing-1))*kStep]);
+						#pragma unroll
+						for (int j = 0; j < 8; ++j) s_out[laneBase + ((outPos + j) & (kRing-1))*kStep] = uint8_t(steady(px[j], spx[j]));
+					}
+				}
+			}
+		}
+		else
+		{
+			for (unsigned t = t0; t < t1; ++t)
+			{
+				if (t < len)
+				{
+					const int px = int(s_in[ringAt(t)]);
+					acc = min(acc + addRem + (px - (px >> sh)), 65535);
+					addRem = px >> sh;
+				}
+				else if (t == len && s.subEdges)
+					acc = min(acc + addRem, 65535); // deprecated/boxblur.cpp:113-115
+				if (t >= edgeSpan)
+				{
+					const unsigned o = t - edgeSpan;
+					unsigned div;
+					if (o < kM)
+						div = WeightToDiv16(s.startWeight + 16*o);
+					else
+					{
+						const int spx = subAt(o - kM);
+						acc = max(acc - (subRem + (spx - (spx >> sh))), 0);
+						subRem = spx >> sh;
+						div = (o < mainEnd) ? fullDiv : WeightToDiv16(s.startWeight + 16*(len - 1 - o));
+					}
+					const unsigned outv = old_div(unsigned(acc), div);
+					hist = (hist << 8) | outv;
+					s_out[ringAt(o)] = uint8_t(outv);
+				}
+			}
+		}
+		__syncwarp();
+
+		const unsigned done = (t1 > edgeSpan) ? t1 - edgeSpan : 0;
+		while (flushed + kStage <= done)
+		{
+			flushStage(flushed);
+			flushed += kStage;
+		}
+	}
+
+	cp_async_wait<0>();
+	while (flushed < len)
+	{
+		flushStage(flushed);
+		flushed += kStage;
+	}
+}
+
 static int OldBlurPass(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned numLines, unsigned lineLen, size_t lineStride, size_t stepStride, float strength)
 {
 	// deprecated/boxblur.cpp:53-76
@@ -108,9 +328,46 @@ static int OldBlurPass(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, un
 	s.fullPassLen = lineLen - (s.kernelMedian + s.edgeSpan);
 	s.fullDiv = WeightToDiv16(kernelSpan << 4);
 
-	const unsigned threads = numLines*4;
-	ckd_prof_begin(ctx, stepStride == 1 ? "old_blur_h" : "old_blur_v", 8.0*numLines*lineLen);
-	old_blur_kernel<<<ckd_div_up(threads, 128), 128, 0, ctx->stream>>>(reinterpret_cast<uint8_t *>(d_dest), reinterpret_cast<const uint8_t *>(d_src), numLines, lineStride, stepStride, s);
+	const bool vert = (stepStride != 1);
+	const unsigned pitch = unsigned(vert ? stepStride : lineStride); // pixels per image row
+	uint8_t *pDest = reinterpret_cast<uint8_t *>(d_dest);
+	const uint8_t *pSrc = reinterpret_cast<const uint8_t *>(d_src);
+	const bool inPlace = (pDest == pSrc);
+	const bool overlap = !inPlace && pDest < pSrc + size_t(numLines)*lineLen*4 && pSrc < pDest + size_t(numLines)*lineLen*4;
+	const bool aligned = 0 == (pitch & 3) && 0 == ((reinterpret_cast<uintptr_t>(pDest) | reinterpret_cast<uintptr_t>(pSrc)) & 15);
+
+	ckd_prof_begin(ctx, vert ? "old_blur_v" : "old_blur_h", 8.0*numLines*lineLen);
+	if (aligned && !overlap)
+	{
+		const unsigned blocks = ckd_div_up(numLines, 8*kBlurWarps);
+		const size_t smem = size_t(kBlurWarps)*2*kRingBytes;
+		static bool attrSet = false;
+		if (!attrSet)
+		{
+			CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			attrSet = true;
+		}
+		const unsigned threads = kBlurWarps*32;
+		if (vert)
+		{
+			if (inPlace) old_blur_staged_kernel<true, true><<<blocks, threads, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s);
+			else         old_blur_staged_kernel<true, false><<<blocks, threads, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s);
+		}
+		else
+		{
+			if (inPlace) old_blur_staged_kernel<false, true><<<blocks, threads, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s);
+			else         old_blur_staged_kernel<false, false><<<blocks, threads, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s);
+		}
+	}
+	else
+	{
+		// unaligned sub-rectangles or partially overlapping buffers: plain byte-wise walk with the reference's exact read/write order
+		const unsigned threads = numLines*4;
+		old_blur_kernel<<<ckd_div_up(threads, 128), 128, 0, ctx->stream>>>(pDest, pSrc, numLines, lineStride, stepStride, s);
+	}
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
 }
