@@ -149,6 +149,12 @@ def run_reference(R, case):
             dst[:] = src0
         R.old_blur(case["kind"], dst, s, case["w"], case["h"], case["strength"])
     elif op == "new_blur":
+        # HorzBlur32 reads 2 pixels past the end of every line (boxblur.cpp:171,185).  Past the last line of its internal
+        # ping-pong buffers that is whatever an earlier call left there: scrub them with a blur of a zero image so the
+        # "virtual pixels after the end" are 0, which is also what the CUDA path defines (include/ckd.h).
+        zeros = aligned_u32(RES_X * (RES_Y + 8), pad=pad)
+        R.new_blur("hv", zeros, zeros, RES_X, RES_Y + 8, 1.0, 0.0, 2)
+        R.new_blur("hv", zeros, zeros, RES_X, RES_Y + 8, 1.0, 0.0, 3)
         R.new_blur(case["kind"], dst, src, case["w"], case["h"], case["strength"], case["gain"], case["passes"])
     elif op == "tape_warp":
         R.tape_warp(dst, src, RES_X, RES_Y, case["strength"], case["speed"])
