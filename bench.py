@@ -272,6 +272,26 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * PIXELS_PER_STEP * e2e_steps / e2e_s / 1e6
+
+    # same calls with the host layer's two-deep frame pipeline (CkdHost_SetPipelined): frame i's copy overlaps frame i+1's render
+    h_frame2 = ctx.malloc_host(frame_bytes)
+    host.set_pipelined(True)
+    barrier()
+    t0 = time.perf_counter()
+    k = 0
+    for _ in range(e2e_steps):
+        for label, eff, host_eff, close, row, params, t in cases:
+            host.set_row(row)
+            host.draw(host_eff, h_frame if (k & 1) == 0 else h_frame2)
+            k += 1
+    host.flush()
+    e2e_pipe_s = time.perf_counter() - t0
+    host.set_pipelined(False)
+    if dist is not None:
+        tp = torch.tensor([e2e_pipe_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        e2e_pipe_s = float(tp.item())
+    e2e_pipelined = world * PIXELS_PER_STEP * e2e_steps / e2e_pipe_s / 1e6
     # per step: 12 parameter structs + the ball / twister per-frame tables go up, 12 finished frames come down
     h2d_bytes = 12 * 96 + 2 * (4096 * 4 + RES_Y * 8) + (1024 * 4 + RES_Y * 8)
     d2h_bytes = len(SUITE) * frame_bytes
@@ -354,11 +374,106 @@ def run_ours(args):
                        "assets": "procedural stand-ins" if assets.synthetic else "reference art (oracle/_ref/assets.npz)",
                        "l2": f"no explicit flush: one step streams ~{working_set_mb:.0f} MB (frames, render targets, polar maps, textures) through the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                    "api": "X_Draw(uint32_t *pDest, float time, float delta) of include/ckd_host.h, pinned host pDest"},
+                    "api": "X_Draw(uint32_t *pDest, float time, float delta) of include/ckd_host.h, pinned host pDest, synchronous (drop-in semantics)",
+                    "pipelined_value": e2e_pipelined,
+                    "pipelined_note": "same calls with CkdHost_SetPipelined(true): two device frame buffers, copy stream; pDest valid after CkdHost_Flush()"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "per_effect": per_effect,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_timeline(args):
+    """BASELINE config 5 without the compositor's art overlays (SURVEY f1 is a 'next' row): for every frame the effect
+    entry point of the part that is active at that time (demo:Effect, code/demo.cpp:507-1003) renders a 4K frame.
+    Frames shard by index (frame i -> rank i mod N); total work is fixed, so this line reports strong scaling."""
+    rank, world, local, dist = dist_setup(args.gpus)
+    import torch
+    from cookiedough_b200 import capi, hostapi, sharding
+    from cookiedough_b200.assets import Assets
+
+    torch.cuda.set_device(local)
+    assets = Assets(RES_X, RES_Y)
+    host = hostapi.Host(RES_X, RES_Y, local, assets)
+    ctx = host.context()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    times = sharding.timeline_times(args.frames)
+    mine = sharding.frames_for_rank(args.frames, rank, world)
+    abi_effect = {"spikey_close": ("spikey", True), "spikey_distant": ("spikey", False)}
+    h_frame = ctx.malloc_host(RES_X * RES_Y * 4)
+
+    def plan(i):
+        host.set_time(times[i])
+        part = capi.geti(host.track("demo:Effect"))
+        if part == 12 and capi.geti(host.track("demo:FullWarpTPB")) == 0:
+            return None
+        return sharding.EFFECT_OF_PART.get(part)
+
+    def pass_device():
+        n = 0
+        for i in mine:
+            eff = plan(i)
+            if eff is None:
+                continue
+            name, close = abi_effect.get(eff, (eff, None))
+            ctx.draw(name, capi.params_from_tracks(name, host.track), float(np.float32(host.time)), close=close)
+            n += 1
+        return n
+
+    def pass_e2e():
+        n = 0
+        for i in mine:
+            eff = plan(i)
+            if eff is None:
+                continue
+            host.draw(eff, h_frame)
+            n += 1
+        return n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        pass_device()
+    barrier()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    rendered = 0
+    for _ in range(args.steps):
+        rendered = pass_device()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = sharding.reduce_max(dist, ev0.elapsed_time(ev1), device="cuda")
+    launches = ctx.launch_count() - launches0
+    barrier()
+    t0 = time.perf_counter()
+    pass_e2e()
+    torch.cuda.synchronize()
+    e2e_s = sharding.reduce_max(dist, time.perf_counter() - t0, device="cuda")
+    if dist is not None:
+        total_rendered = torch.tensor([rendered], device="cuda", dtype=torch.int64)
+        dist.all_reduce(total_rendered)
+        rendered_all = int(total_rendered.item())
+    else:
+        rendered_all = rendered
+    if rank == 0:
+        px = rendered_all * RES_X * RES_Y
+        print(json.dumps({
+            "metric": "Mpixel/s", "value": px * args.steps / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "fps": rendered_all * args.steps / (ms * 1e-3), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+            "config": {"workload": "timeline-4k", "frames": args.frames, "frames_with_effect_layer": rendered_all, "res": [RES_X, RES_Y],
+                       "sharding": "frame i -> rank i mod N, no data-path collective", "compositor_overlays": "not rendered (SURVEY f1, next)"},
+            "e2e": {"value": px / e2e_s / 1e6, "unit": "Mpixel/s", "fps": rendered_all / e2e_s, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": rendered_all * RES_X * RES_Y * 4},
+            "gpu_launches": int(launches)}))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -372,9 +487,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="effect-suite-4k", choices=["effect-suite-4k", "timeline-4k"],
+                    help="timeline-4k: the 600-frame directors-cut timeline (effect layer of each part, BASELINE config 5), frame i -> rank i mod N (strong scaling)")
+    ap.add_argument("--frames", type=int, default=600)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "timeline-4k":
+        return run_timeline(args)
     return run_ours(args)
 
 

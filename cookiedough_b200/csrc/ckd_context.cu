@@ -142,7 +142,7 @@ extern "C" int ckd_set_cos_lut(ckd_ctx *ctx, const float *lut2049)
 	memcpy(ctx->h_cosLUT, lut2049, sizeof(ctx->h_cosLUT));
 	std::vector<float2> pairs(kCkdCosTabSize);
 	for (int i = 0; i < kCkdCosTabSize; ++i)
-		pairs[i] = make_float2(lut2049[i], lut2049[i+1]);
+		pairs[i] = make_float2(lut2049[i], lut2049[i+1] - lut2049[i]); // b-a of lerpf (Math.h:52-56), same float subtraction
 	CKD_CUDA(cudaMemcpy(ctx->d_cosLUT2, pairs.data(), pairs.size()*sizeof(float2), cudaMemcpyHostToDevice));
 	return CKD_OK;
 }
@@ -310,6 +310,12 @@ extern "C" void ckd_destroy(ckd_ctx *ctx)
 	if (ctx->d_rsqrtTab) cudaFree(ctx->d_rsqrtTab);
 	free(ctx->h_rsqrtTab);
 	for (auto &e : ctx->profEntries) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+	for (int i = 0; i < 2; ++i)
+	{
+		if (ctx->evRendered[i]) cudaEventDestroy(ctx->evRendered[i]);
+		if (ctx->evCopied[i]) cudaEventDestroy(ctx->evCopied[i]);
+	}
+	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 	if (ctx->evStart) cudaEventDestroy(ctx->evStart);
 	if (ctx->evStop) cudaEventDestroy(ctx->evStop);
 	if (ctx->d_pool) cudaFree(ctx->d_pool);
@@ -378,6 +384,46 @@ extern "C" int ckd_download(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t
 {
 	CKD_REQUIRE(ctx && h_dst && d_src, "null argument");
 	CKD_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	return CKD_OK;
+}
+
+extern "C" uint32_t *ckd_frame_slot(ckd_ctx *ctx, int slot)
+{
+	if (!ctx || slot < 0 || slot > 1) return nullptr;
+	return slot ? ctx->d_scratch[1] : ctx->d_frame; // the second blur scratch image is only used by ckd_new_blur
+}
+
+extern "C" int ckd_download_overlapped(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, int slot)
+{
+	CKD_REQUIRE(ctx && h_dst && d_src, "null argument");
+	CKD_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+	if (!ctx->copyStream)
+	{
+		CKD_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; ++i)
+		{
+			CKD_CUDA(cudaEventCreateWithFlags(&ctx->evRendered[i], cudaEventDisableTiming));
+			CKD_CUDA(cudaEventCreateWithFlags(&ctx->evCopied[i], cudaEventDisableTiming));
+		}
+	}
+	CKD_CUDA(cudaEventRecord(ctx->evRendered[slot], ctx->stream));
+	CKD_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evRendered[slot], 0));
+	CKD_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
+	CKD_CUDA(cudaEventRecord(ctx->evCopied[slot], ctx->copyStream));
+	// the next kernels that overwrite d_src must not start before the copy has read it
+	ctx->copyPending[slot] = true;
+	return CKD_OK;
+}
+
+extern "C" int ckd_wait_download(ckd_ctx *ctx, int slot)
+{
+	CKD_REQUIRE(ctx, "null context");
+	CKD_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+	if (ctx->copyPending[slot])
+	{
+		CKD_CUDA(cudaEventSynchronize(ctx->evCopied[slot]));
+		ctx->copyPending[slot] = false;
+	}
 	return CKD_OK;
 }
 

@@ -26,6 +26,9 @@ struct ckd_ctx {
 	int numSMs = 148;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t evStart = nullptr, evStop = nullptr;
+	cudaStream_t copyStream = nullptr;             // read-back overlapped with rendering (ckd_download_overlapped)
+	cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
+	bool copyPending[2] = { false, false };
 	unsigned long long launches = 0;
 
 	// device twins of the reference's global buffers (all carved out of one allocation, with guard rows)
@@ -40,7 +43,7 @@ struct ckd_ctx {
 
 	// tables
 	float h_cosLUT[kCkdCosTabSize+1];
-	float2 *d_cosLUT2 = nullptr;      // [i] = (LUT[i], LUT[i+1]) so one 8-byte load feeds the lerp
+	float2 *d_cosLUT2 = nullptr;      // [i] = (LUT[i], LUT[i+1]-LUT[i]) so one 8-byte load feeds the lerp
 	uint32_t *d_rsqrtTab = nullptr;   // host RSQRTPS table
 	uint32_t *h_rsqrtTab = nullptr;
 	int rsqrtLog2Bin = 13;

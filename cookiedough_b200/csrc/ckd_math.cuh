@@ -59,15 +59,19 @@ __device__ __forceinline__ float smoothstepf(float a, float b, float t)         
 }
 
 // ---- interpolated cosine LUT (sincos-lut.h:13-26) -----------------------------------------------------------------
-// The 2049-entry table is staged in shared memory as 2048 (LUT[i], LUT[i+1]) pairs: one 8-byte LDS per call.
+// The 2049-entry table is staged in shared memory as 2048 (LUT[i], LUT[i+1]-LUT[i]) pairs: one 8-byte LDS per call and the
+// difference (the same IEEE subtraction the reference performs per call) is paid once at start-up.
 
 __device__ __forceinline__ float lutcosf(const float2 *__restrict__ lut2, float angle)
 {
 	angle = fabsf(angle);
 	angle *= (1.f/k2PI)*2048; // constant folds in float exactly like the reference's (1.f/k2PI)*kCosTabSize
-	const int index = cvtt_x86(angle) & 2047;
-	const float2 pair = lut2[index];
-	return lerpf(pair.x, pair.y, fracf(angle));
+	// int(angle) & 2047 with cvttss2si semantics: angle is >= 0 or NaN here, so only the upper bound can overflow
+	// (-> 0x80000000, index 0); NaN converts to 0 on both machines.  (An F2I-free variant built on the 2^23 rounding
+	// trick was measured slower: these kernels are issue bound, not XU bound -- profiles/r01_notes.md.)
+	const int index = (angle < 2147483648.f) ? (__float2int_rz(angle) & 2047) : 0;
+	const float2 pair = lut2[index];           // (LUT[i], LUT[i+1] - LUT[i])
+	return pair.x + pair.y*(angle - truncf(angle)); // lerpf(a, b, t) = a + (b-a)*t, Math.h:52-56
 }
 
 // ARRESTED_DEV_LEGACY (main.h:9): lutsinf(a) = lutcosf(a + pi/2)

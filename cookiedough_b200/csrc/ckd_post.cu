@@ -8,6 +8,8 @@
 #include "ckd_math.cuh"
 #include "ckd_hostmath.h"
 
+#include <stdlib.h>
+
 using namespace ckd;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -404,6 +406,20 @@ template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel(u
 	reinterpret_cast<uint4 *>(pDest)[q] = out;
 }
 
+// one destination pixel per thread: neighbouring lanes fetch neighbouring texels (the polar map is smooth), so a warp's
+// gather touches a handful of sectors instead of 32
+template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel_1px(uint32_t *pDest, const uint32_t *__restrict__ pSrc, const int2 *__restrict__ pMap, unsigned numPixels, unsigned resX)
+{
+	const unsigned i = blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= numPixels)
+		return;
+	const int2 m = __ldg(pMap + i);
+	uint32_t out = polar_fetch(pSrc, m.x, m.y, resX);
+	if (ALPHA)
+		out = polar_blend(pDest[i], out);
+	pDest[i] = out;
+}
+
 static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse, bool alpha)
 {
 	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
@@ -413,7 +429,17 @@ static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, in
 	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap : ctx->d_polarMap);
 	const unsigned blocks = ckd_div_up(numQuads, 256);
 	ckd_prof_begin(ctx, alpha ? "polar_blit_a" : "polar_blit", (alpha ? 20.0 : 16.0)*ctx->resX*ctx->resY);
-	if (alpha)
+	static const int variant = getenv("CKD_POLAR_VARIANT") ? atoi(getenv("CKD_POLAR_VARIANT")) : 0;
+	if (variant == 1)
+	{
+		const unsigned numPixels = numQuads*4;
+		const int2 *pMap2 = reinterpret_cast<const int2 *>(pMap);
+		if (alpha)
+			polar_blit_kernel_1px<true><<<ckd_div_up(numPixels, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap2, numPixels, unsigned(ctx->resX));
+		else
+			polar_blit_kernel_1px<false><<<ckd_div_up(numPixels, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap2, numPixels, unsigned(ctx->resX));
+	}
+	else if (alpha)
 		polar_blit_kernel<true><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
 	else
 		polar_blit_kernel<false><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));

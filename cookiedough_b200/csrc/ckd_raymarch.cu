@@ -101,7 +101,8 @@ struct PlasmaEffect
 		const float r = (f.colMulA[2]*march + f.colMulB[2]*second)*mul;
 
 		// the 4th lane of a Vector3 colour is 0: log_ps(0) = NaN -> exp_ps -> huge -> converts to 0
-		return to_pixel(gamma_adj1(b, f.gamma), gamma_adj1(g, f.gamma), gamma_adj1(r, f.gamma), gamma_adj1(0.f, f.gamma));
+		// (a lane holding 0 -> log_ps = NaN -> exp_ps = e^88 -> x255 = inf -> cvtps2dq = 0x80000000 -> max(0, .) = 0: alpha is 0)
+		return to_pixel(gamma_adj1(b, f.gamma), gamma_adj1(g, f.gamma), gamma_adj1(r, f.gamma), 0.f);
 	}
 };
 
@@ -177,7 +178,7 @@ struct NautilusEffect
 		const float g = (diffuse + f.diffColor[1]*s) + add;
 		const float r = (diffuse + f.diffColor[2]*s) + add;
 
-		return to_pixel(gamma_adj1(b, 1.44f), gamma_adj1(g, 1.44f), gamma_adj1(r, 1.44f), gamma_adj1(0.f, 1.44f));
+		return to_pixel(gamma_adj1(b, 1.44f), gamma_adj1(g, 1.44f), gamma_adj1(r, 1.44f), 0.f); // Vector3 colour: 4th lane 0 -> alpha 0
 	}
 };
 
@@ -517,11 +518,16 @@ __global__ void __launch_bounds__(kTileX*kTileY) raymarch_kernel(const Effect ef
 
 	Env env = { s_lut2, rsqrt, geom };
 
+	// a warp covers an 8x4 pixel block (not a 32x1 strip): neighbouring rays leave the early-exit march loops after
+	// similar step counts, and each of its 4 rows is still one full 32-byte sector of the FX map
+	const unsigned warp = threadIdx.y, lane = threadIdx.x;
+	const unsigned inX = (warp & 3)*8 + (lane & 7), inY = (warp >> 2)*4 + (lane >> 3);
+
 	for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x)
 	{
 		const int tY = tile / tilesX, tX = tile - tY*tilesX;
-		const unsigned iX = tX*kTileX + threadIdx.x;
-		const unsigned iY = tY*kTileY + threadIdx.y;
+		const unsigned iX = tX*kTileX + inX;
+		const unsigned iY = tY*kTileY + inY;
 		if (iX < unsigned(geom.fxX) && iY < unsigned(geom.fxY))
 			pDest[size_t(iY)*geom.fxX + iX] = effect.shade(env, iX, iY);
 	}
@@ -557,11 +563,14 @@ __global__ void __launch_bounds__(kTileX*kTileY) tunnel_kernel(const TunnelFrame
 	stage_cos_lut(s_lut2, g_lut2);
 	__syncthreads();
 
+	const unsigned warp = threadIdx.y, lane = threadIdx.x;
+	const unsigned inX = (warp & 3)*8 + (lane & 7), inY = (warp >> 2)*4 + (lane >> 3);
+
 	for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x)
 	{
 		const int tY = tile / tilesX, tX = tile - tY*tilesX;
-		const unsigned iX = tX*kTileX + threadIdx.x;
-		const unsigned iY = tY*kTileY + threadIdx.y;
+		const unsigned iX = tX*kTileX + inX;
+		const unsigned iY = tY*kTileY + inY;
 		if (iX >= unsigned(geom.fxX) || iY >= unsigned(geom.fxY))
 			continue;
 

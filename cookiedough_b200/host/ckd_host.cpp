@@ -305,11 +305,43 @@ namespace Rocket
 // frame helpers
 // ---------------------------------------------------------------------------------------------------------------
 
+static bool s_pipelined = false;
+static int s_slot = 0;
+
+void CkdHost_Flush()
+{
+	if (nullptr == s_ctx) return;
+	Check(ckd_wait_download(s_ctx, 0), "CkdHost_Flush");
+	Check(ckd_wait_download(s_ctx, 1), "CkdHost_Flush");
+}
+
+void CkdHost_SetPipelined(bool enabled)
+{
+	if (s_pipelined && !enabled)
+		CkdHost_Flush();
+	s_pipelined = enabled;
+}
+
+// device buffer the next X_Draw renders into: the single frame twin, or the free slot of the two-deep pipeline
+static uint32_t *Target()
+{
+	if (!s_pipelined)
+		return ckd_frame(s_ctx);
+	Check(ckd_wait_download(s_ctx, s_slot), "X_Draw"); // the copy that last read this buffer must have finished
+	return ckd_frame_slot(s_ctx, s_slot);
+}
+
 static void Finish(int rc, uint32_t *pDest, const char *what)
 {
 	if (!Check(rc, what))
 		return;
 	const size_t bytes = size_t(ckd_res_x(s_ctx))*ckd_res_y(s_ctx)*sizeof(uint32_t);
+	if (s_pipelined)
+	{
+		Check(ckd_download_overlapped(s_ctx, pDest, ckd_frame_slot(s_ctx, s_slot), bytes, s_slot), what);
+		s_slot ^= 1;
+		return;
+	}
 	if (Check(ckd_download(s_ctx, pDest, ckd_frame(s_ctx), bytes), what))
 		Check(ckd_sync(s_ctx), what);
 }
@@ -427,7 +459,7 @@ void Plasma_Draw(uint32_t *pDest, float time, float delta)
 	p.hue = Rocket::getf(trackPlasmaHue);
 	p.gamma = Rocket::getf(trackPlasmaGamma);
 	p.desaturation = Rocket::getf(trackPlasmaDesat);
-	Finish(ckd_plasma_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Plasma_Draw");
+	Finish(ckd_plasma_draw(s_ctx, &p, time, Target()), pDest, "Plasma_Draw");
 }
 
 // shadertoy.cpp:395-407
@@ -440,7 +472,7 @@ void Nautilus_Draw(uint32_t *pDest, float time, float delta)
 	p.speed = Rocket::getf(trackNautilusSpeed);
 	p.desaturation = Rocket::getf(trackNautilusDesaturation);
 	p.blur = Rocket::getf(trackNautilusBlur);
-	Finish(ckd_nautilus_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Nautilus_Draw");
+	Finish(ckd_nautilus_draw(s_ctx, &p, time, Target()), pDest, "Nautilus_Draw");
 }
 
 // shadertoy.cpp:661-733
@@ -470,7 +502,7 @@ void Spikey_Draw(uint32_t *pDest, float time, float delta, bool close /* = true 
 	p.mix_blur = Rocket::getf(trackCloseMixBlur);
 	p.mix_map_blur = Rocket::getf(trackCloseMixMapBlur);
 	p.mix_blur_opacity = Rocket::getf(trackCloseMixBlurOpacity);
-	Finish(ckd_spikey_draw(s_ctx, &p, time, close ? 1 : 0, ckd_frame(s_ctx)), pDest, "Spikey_Draw");
+	Finish(ckd_spikey_draw(s_ctx, &p, time, close ? 1 : 0, Target()), pDest, "Spikey_Draw");
 }
 
 // shadertoy.cpp:840-861
@@ -492,7 +524,7 @@ void Tunnel_Draw(uint32_t *pDest, float time, float delta)
 	p.lit_blur = Rocket::getf(trackTunnelLitBlur);
 	p.fog1 = Rocket::getf(trackTunnelFog1);
 	p.fog2 = Rocket::getf(trackTunnelFog2);
-	Finish(ckd_tunnel_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Tunnel_Draw");
+	Finish(ckd_tunnel_draw(s_ctx, &p, time, Target()), pDest, "Tunnel_Draw");
 }
 
 // shadertoy.cpp:984-988
@@ -507,7 +539,7 @@ void Sinuses_Draw(uint32_t *pDest, float time, float delta)
 	p.gamma = Rocket::getf(trackSinusesGamma);
 	p.hue = Rocket::getf(trackSinusesHue);
 	p.desaturation = Rocket::getf(trackSinusesDesat);
-	Finish(ckd_sinuses_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Sinuses_Draw");
+	Finish(ckd_sinuses_draw(s_ctx, &p, time, Target()), pDest, "Sinuses_Draw");
 }
 
 // shadertoy.cpp:1105-1109
@@ -521,7 +553,7 @@ void Laura_Draw(uint32_t *pDest, float time, float delta)
 	p.roll = Rocket::getf(trackLauraRoll);
 	p.hue = Rocket::getf(trackLauraHue);
 	p.saturate = Rocket::getf(trackLauraSaturate);
-	Finish(ckd_laura_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Laura_Draw");
+	Finish(ckd_laura_draw(s_ctx, &p, time, Target()), pDest, "Laura_Draw");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -556,7 +588,7 @@ void Landscape_Draw(uint32_t *pDest, float time, float delta)
 	p.tilt = Rocket::getf(trackVoxelScapeTilt);
 	p.warp_speed = Rocket::getf(trackWarpSpeed);
 	p.warp_strength = Rocket::getf(trackWarpStrength);
-	Finish(ckd_landscape_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Landscape_Draw");
+	Finish(ckd_landscape_draw(s_ctx, &p, time, Target()), pDest, "Landscape_Draw");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -590,7 +622,7 @@ void Tunnelscape_Draw(uint32_t *pDest, float time, float delta)
 	p.step_v = Rocket::getf(trackStarsStepV);
 	p.speed = Rocket::getf(trackStarsSpeed);
 	p.blur = Rocket::getf(trackStarsBlur);
-	Finish(ckd_tunnelscape_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Tunnelscape_Draw");
+	Finish(ckd_tunnelscape_draw(s_ctx, &p, time, Target()), pDest, "Tunnelscape_Draw");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -660,7 +692,7 @@ void Ball_Draw(uint32_t *pDest, float time, float delta)
 	p.beams2 = Rocket::getf(trackBallBeams2);
 	p.beams3 = Rocket::getf(trackBallBeams3);
 	p.low_beams = Rocket::geti(trackBallLowBeams);
-	Finish(ckd_ball_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Ball_Draw");
+	Finish(ckd_ball_draw(s_ctx, &p, time, Target()), pDest, "Ball_Draw");
 }
 
 bool Ball_HasBeams() { return Rocket::geti(trackBallHasBeams) != 0; } // ball.cpp:521-524
@@ -694,7 +726,7 @@ void Twister_Draw(uint32_t *pDest, float time, float delta)
 	p.speed = Rocket::getf(trackTwisterSpeed);
 	p.shear_speed = Rocket::getf(trackTwisterShearSpeed);
 	p.blur = Rocket::getf(trackTwisterBlur);
-	Finish(ckd_twister_draw(s_ctx, &p, time, ckd_frame(s_ctx)), pDest, "Twister_Draw");
+	Finish(ckd_twister_draw(s_ctx, &p, time, Target()), pDest, "Twister_Draw");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -860,6 +892,8 @@ void ckdhost_destroy()
 	CkdHost_Destroy();
 }
 
+void ckdhost_set_pipelined(int enabled) { CkdHost_SetPipelined(0 != enabled); }
+void ckdhost_flush() { CkdHost_Flush(); }
 void ckdhost_register_image(const char *path, const void *pixels, int width, int height, int bpp) { CkdHost_RegisterImage(path, pixels, width, height, bpp); }
 const char *ckdhost_last_error() { return s_lastError.c_str(); }
 void *ckdhost_context() { return s_ctx; }

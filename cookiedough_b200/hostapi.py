@@ -116,5 +116,12 @@ class Host:
         if rc != 0:
             raise capi.CkdError(f"{op}: {self.L.ckdhost_last_error().decode()}")
 
+    def set_pipelined(self, enabled):
+        """frame pipelining (CkdHost_SetPipelined): X_Draw returns once enqueued; call flush() before reading the buffers"""
+        self.L.ckdhost_set_pipelined(int(bool(enabled)))
+
+    def flush(self):
+        self.L.ckdhost_flush()
+
     def close(self):
         self.L.ckdhost_destroy()

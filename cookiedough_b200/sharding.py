@@ -1,0 +1,54 @@
+"""Frame-parallel sharding of a timeline across the GPUs of one box.
+
+Every X_Draw is a pure function of (time, Rocket row, assets), so a timeline shards by frame index with no data-path
+collective: frame i goes to rank i mod N.  The only communication is bookkeeping (barrier, max-over-ranks time, gathering
+per-frame checksums to rank 0) and runs over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+import zlib
+
+import numpy as np
+
+ROW_RATE = (170.0 / (60.0 * (170.0 / 174.0))) * 16.0   # code/audio.cpp:18
+TIMELINE_ROWS = 10296                                   # demo:quit fires here
+
+# demo:Effect value -> effect entry point (code/demo.cpp:508-1003); 12 draws Plasma only when demo:FullWarpTPB is set,
+# 13 (sprites) has no effect layer
+EFFECT_OF_PART = {1: "twister", 2: "landscape", 3: "ball", 4: "tunnelscape", 5: "plasma", 6: "nautilus", 7: "spikey_close",
+                  8: "spikey_distant", 9: "tunnel", 10: "sinuses", 11: "laura", 12: "plasma", 13: None}
+
+
+def timeline_times(num_frames=600):
+    """t_i = i * (10296 / 46.4) / num_frames  """
+    total = TIMELINE_ROWS / ROW_RATE
+    return [i * total / num_frames for i in range(num_frames)]
+
+
+def frames_for_rank(num_frames, rank, world_size):
+    """frame i -> rank i mod N"""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    return list(range(rank, num_frames, world_size))
+
+
+def frame_checksum(frame):
+    return zlib.crc32(np.ascontiguousarray(frame).view(np.uint8)) & 0xFFFFFFFF
+
+
+def reduce_max(dist, value, device="cpu"):
+    """max over ranks of a python float (the timing contract: max-over-ranks, on whatever backend dist uses)"""
+    if dist is None:
+        return float(value)
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_checksums(dist, local, num_frames, device="cpu"):
+    """local: {frame index: crc32}; returns the full per-frame list on every rank (all-reduce of disjoint slots)"""
+    import torch
+    t = torch.zeros(num_frames, dtype=torch.int64, device=device)
+    for i, c in local.items():
+        t[i] = int(c)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [int(v) for v in t.tolist()]

@@ -64,6 +64,14 @@ int ckd_free_host(void *h_ptr);
 int ckd_upload(ckd_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);   /* async on the stream */
 int ckd_download(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes); /* async on the stream */
 
+/* overlapped read-back for frame pipelines: the copy of a finished frame runs on the context's copy stream while the
+ * compute stream already renders the next one.  slot = 0/1 selects one of two in-flight copies; ckd_frame_slot(ctx, slot)
+ * are two device frame buffers to alternate between.  ckd_download_overlapped() orders the copy after everything enqueued
+ * on the compute stream so far; ckd_wait_download() blocks the host until that slot's copy has landed. */
+uint32_t *ckd_frame_slot(ckd_ctx *ctx, int slot);
+int ckd_download_overlapped(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, int slot);
+int ckd_wait_download(ckd_ctx *ctx, int slot);
+
 /* timing on the context's stream (CUDA events) */
 int ckd_timer_start(ckd_ctx *ctx);
 int ckd_timer_stop_ms(ckd_ctx *ctx, float *out_ms); /* synchronises */

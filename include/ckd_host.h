@@ -34,6 +34,12 @@ void CkdHost_SetTime(double seconds);
 // bytesPerPixel 4 = BGRA, 1 = luminance.  The pixels are copied.
 void CkdHost_RegisterImage(const char *path, const void *pixels, int width, int height, int bytesPerPixel);
 
+// Frame pipelining for offline / timeline rendering (not part of the reference's interface).  While enabled, X_Draw returns
+// as soon as the frame is enqueued: pDest is complete after the *second* following X_Draw call or after CkdHost_Flush().
+// The device->host copy of frame i then overlaps the rendering of frame i+1 (two device frame buffers, copy stream).
+void CkdHost_SetPipelined(bool enabled);
+void CkdHost_Flush();
+
 // main.h:49 / main.cpp:175-180
 void SetLastError(const std::string &description);
 const std::string &CkdHost_GetLastError();
