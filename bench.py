@@ -112,6 +112,9 @@ class ClockSampler:
 
 
 def dist_setup(n_gpus):
+    # rank 0 must print exactly one JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -115,7 +115,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 constexpr int kBlurWarps = 4;                   // warps per CTA: one per SM sub-partition (a 1-warp CTA always lands on sub-partition 0)
 
-template <bool VERT, bool INPLACE>
+template <bool VERT, bool INPLACE, bool SUBEDGES>
 __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t *pDest, const uint8_t *pSrc, unsigned numLines, unsigned len, unsigned pitch, OldBlurSetup s)
 {
 	extern __shared__ __align__(16) uint8_t s_rings[]; // per warp: input ring, output ring
@@ -154,6 +154,21 @@ __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t 
 	};
 	auto flushStage = [&](unsigned p0)
 	{
+		uint4 v[4]; // all four shared-memory reads first, then the four global stores
+		#pragma unroll
+		for (unsigned k = 0; k < 4; ++k)
+		{
+			if (VERT)
+			{
+				const unsigned pos = p0 + k*16 + (lane >> 1);
+				v[k] = *reinterpret_cast<const uint4 *>(s_out + (pos & (kRing-1))*32 + (lane & 1)*16);
+			}
+			else
+			{
+				const unsigned pos = p0 + (k*4 + (lane & 3))*4;
+				v[k] = *reinterpret_cast<const uint4 *>(s_out + (lane >> 2)*kPitchH + (pos & (kRing-1))*4);
+			}
+		}
 		#pragma unroll
 		for (unsigned k = 0; k < 4; ++k)
 		{
@@ -161,13 +176,13 @@ __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t 
 			{
 				const unsigned pos = p0 + k*16 + (lane >> 1), col = line0 + (lane & 1)*4;
 				if (pos < len && col + 3 < numLines)
-					*reinterpret_cast<uint4 *>(pDest + (size_t(pos)*pitch + col)*4) = *reinterpret_cast<const uint4 *>(s_out + (pos & (kRing-1))*32 + (lane & 1)*16);
+					*reinterpret_cast<uint4 *>(pDest + (size_t(pos)*pitch + col)*4) = v[k];
 			}
 			else
 			{
 				const unsigned pos = p0 + (k*4 + (lane & 3))*4, line = line0 + (lane >> 2);
 				if (pos < len && line < numLines)
-					*reinterpret_cast<uint4 *>(pDest + (size_t(line)*pitch + pos)*4) = *reinterpret_cast<const uint4 *>(s_out + (lane >> 2)*kPitchH + (pos & (kRing-1))*4);
+					*reinterpret_cast<uint4 *>(pDest + (size_t(line)*pitch + pos)*4) = v[k];
 			}
 		}
 	};
@@ -197,15 +212,24 @@ __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t 
 	auto subAt = [&](unsigned pos) -> int { return INPLACE ? int(s_out[ringAt(pos)]) : int(s_in[ringAt(pos)]); };
 
 	// one steady-state step: Add + Sub + Div (deprecated/boxblur.cpp:104-110) with the four saturating 16-bit operations folded:
-	// max(min(acc + a, 65535) - b, 0) == max(min(acc + (a - b), 65535 - b), 0), a single DPX add-min-relu
+	// max(min(acc + a, 65535) - b, 0) == max(min(acc + (a - b), 65535 - b), 0), a single DPX add-min-relu.
+	// Odd kernels (SUBEDGES == false) shift the remainder out entirely (px >> 8 == 0): a == px, b == spx.
+	// Div: pmulhuw + packuswb == min((acc*div) >> 16, 255) whenever div <= 32768 (every kernel wider than 1 pixel; a 1-pixel
+	// kernel has div == 0): the "word read as signed" case of packuswb cannot occur, and (acc*div) >> 16 == umulhi(acc, div << 16).
+	const unsigned fullDivHi = fullDiv << 16;
+	const bool plainDiv = fullDiv <= 32768u;
 	auto steady = [&](int px, int spx) -> unsigned
 	{
-		const int a = addRem + (px - (px >> sh));
-		addRem = px >> sh;
-		const int b = subRem + (spx - (spx >> sh));
-		subRem = spx >> sh;
+		int a = px, b = spx;
+		if (SUBEDGES)
+		{
+			a = addRem + (px - (px >> 1));
+			addRem = px >> 1;
+			b = subRem + (spx - (spx >> 1));
+			subRem = spx >> 1;
+		}
 		acc = __viaddmin_s32_relu(acc, a - b, 65535 - b);
-		return old_div(unsigned(acc), fullDiv);
+		return plainDiv ? min(__umulhi(unsigned(acc), fullDivHi), 255u) : old_div(unsigned(acc), fullDiv);
 	};
 
 	for (unsigned stage = 0; stage < numStages; ++stage)
@@ -341,26 +365,22 @@ static int OldBlurPass(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, un
 	{
 		const unsigned blocks = ckd_div_up(numLines, 8*kBlurWarps);
 		const size_t smem = size_t(kBlurWarps)*2*kRingBytes;
-		static bool attrSet = false;
-		if (!attrSet)
+		#define CKD_BLUR_LAUNCH(V, I, E) do { \
+			if (!ctx->blurAttrSet[variant]) { CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<V, I, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); ctx->blurAttrSet[variant] = true; } \
+			old_blur_staged_kernel<V, I, E><<<blocks, kBlurWarps*32, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s); } while (0)
+		const int variant = (vert ? 4 : 0) | (inPlace ? 2 : 0) | (s.subEdges ? 1 : 0);
+		switch (variant)
 		{
-			CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			attrSet = true;
+		case 0: CKD_BLUR_LAUNCH(false, false, false); break;
+		case 1: CKD_BLUR_LAUNCH(false, false, true); break;
+		case 2: CKD_BLUR_LAUNCH(false, true, false); break;
+		case 3: CKD_BLUR_LAUNCH(false, true, true); break;
+		case 4: CKD_BLUR_LAUNCH(true, false, false); break;
+		case 5: CKD_BLUR_LAUNCH(true, false, true); break;
+		case 6: CKD_BLUR_LAUNCH(true, true, false); break;
+		default: CKD_BLUR_LAUNCH(true, true, true); break;
 		}
-		const unsigned threads = kBlurWarps*32;
-		if (vert)
-		{
-			if (inPlace) old_blur_staged_kernel<true, true><<<blocks, threads, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s);
-			else         old_blur_staged_kernel<true, false><<<blocks, threads, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s);
-		}
-		else
-		{
-			if (inPlace) old_blur_staged_kernel<false, true><<<blocks, threads, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s);
-			else         old_blur_staged_kernel<false, false><<<blocks, threads, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s);
-		}
+		#undef CKD_BLUR_LAUNCH
 	}
 	else
 	{
