@@ -249,6 +249,7 @@ extern "C" int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device)
 	const size_t offCos = carve(kCkdCosTabSize*sizeof(float2));
 	const size_t offVox = carve(8192*sizeof(int));
 	const size_t offRay = carve(size_t(res_y)*8*sizeof(float) + 4096);
+	const size_t offCounters = carve(256);
 
 	err = cudaMalloc(&ctx->d_pool, total);
 	if (err != cudaSuccess) { delete ctx; return ckd_cuda_fail(err, "cudaMalloc(pool)", __FILE__, __LINE__); }
@@ -268,6 +269,7 @@ extern "C" int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device)
 	ctx->d_cosLUT2 = reinterpret_cast<float2 *>(base + offCos);
 	ctx->d_voxelTables = reinterpret_cast<int *>(base + offVox);
 	ctx->d_rayParams = reinterpret_cast<float *>(base + offRay);
+	ctx->d_tileCounters = reinterpret_cast<unsigned *>(base + offCounters);
 
 	int rc = CKD_OK;
 	do

@@ -52,6 +52,8 @@ struct ckd_ctx {
 	int32_t *d_polarMap = nullptr, *d_polarInvMap = nullptr; // 2 ints per pixel
 	int *d_voxelTables = nullptr;     // per-frame projection / lighting tables for ball & twister
 	float *d_rayParams = nullptr;     // per-ray host-computed parameters (ball fan deltas, twister origins)
+	unsigned *d_tileCounters = nullptr; // two alternating work-queue counters of the raymarch kernels
+	unsigned long long tileLaunches = 0;
 
 	ckd_image_slot images[CKD_IMG_COUNT];
 
