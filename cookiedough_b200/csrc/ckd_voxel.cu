@@ -327,16 +327,15 @@ struct TunnelscapeFrame
 __global__ void __launch_bounds__(kRowsPerBlock*32) tunnelscape_kernel(uint32_t *__restrict__ pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
 	const uint32_t *__restrict__ fogGradient, const TunnelscapeFrame f)
 {
-	extern __shared__ uint32_t s_lines[]; // [kRowsPerBlock][resX]
+	// The spans of a ray pile up left to right without gaps, so they go straight to the row in global memory (neighbouring
+	// lanes write neighbouring pixels, L2 merges the sectors); what the ray leaves uncovered gets the clear colour at the end.
+	// No shared-memory line buffer: the resident warps per SM are bounded by registers only, which is what hides the L2
+	// gather latency of this kernel.
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const unsigned iRay = blockIdx.x*kRowsPerBlock + warp;
 	if (iRay >= unsigned(f.resY))
 		return;
-	uint32_t *line = s_lines + warp*f.resX;
-
-	for (int x = lane; x < f.resX; x += 32)
-		line[x] = f.clearColor;
-	__syncwarp();
+	uint32_t *line = pDest + size_t(iRay)*f.resX;
 
 	// tscape, tunnelscape.cpp:121-131
 	const float mapX = float(iRay)*f.mapStepX;
@@ -392,10 +391,9 @@ __global__ void __launch_bounds__(kRowsPerBlock*32) tunnelscape_kernel(uint32_t 
 		carryLastColor = shfl_color(color, 31);
 	}
 
-	__syncwarp();
-	uint32_t *row = pDest + size_t(iRay)*f.resX;
-	for (int x = lane*4; x < f.resX; x += 128)
-		*reinterpret_cast<uint4 *>(row + x) = *reinterpret_cast<const uint4 *>(line + x);
+	// memset32(g_renderTarget[0], s_pFogGradient[0], ...), tunnelscape.cpp:170: only the part no span covered
+	for (int x = max(f.resX - carryLastDrawn, 0) + lane; x < f.resX; x += 32)
+		line[x] = f.clearColor;
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -417,26 +415,13 @@ template <bool BEAMS>
 __global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
 	const uint32_t *__restrict__ auxMap /* beam mix or env map */, const int *__restrict__ tables, const int *__restrict__ rayDeltas, const BallFrame f)
 {
-	extern __shared__ uint32_t s_lines[]; // [kRowsPerBlock][resX]
+	// spans go straight to the row in global memory (see tunnelscape_kernel); with beams the reference does not clear the
+	// render target (ball.cpp:352-363), so whatever no span and no beam pixel covers simply keeps its previous content
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const unsigned iRay = blockIdx.x*kRowsPerBlock + warp;
 	if (iRay >= unsigned(f.resY))
 		return;
-	uint32_t *line = s_lines + warp*f.resX;
-	uint32_t *row = pDest + size_t(iRay)*f.resX;
-
-	if (BEAMS)
-	{
-		// no clear in this path (ball.cpp:352-363): pixels that are not written keep the render target's previous content
-		for (int x = lane*4; x < f.resX; x += 128)
-			*reinterpret_cast<uint4 *>(line + x) = *reinterpret_cast<const uint4 *>(row + x);
-	}
-	else
-	{
-		for (int x = lane; x < f.resX; x += 32)
-			line[x] = 0; // memset32(pDest, 0, kTargetSize), ball.cpp:342
-	}
-	__syncwarp();
+	uint32_t *line = pDest + size_t(iRay)*f.resX;
 
 	const int dX = rayDeltas[iRay*2], dY = rayDeltas[iRay*2+1];
 	const int *heightProj = tables, *projNorm0 = tables + 1024, *projNorm1 = tables + 2048, *projNorm2 = tables + 3072;
@@ -543,31 +528,37 @@ __global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest,
 
 		if (remainder <= unsigned(f.resX))
 		{
-			// 'curStep += alphaStep' is a serial float accumulation: lane 0 walks it, all lanes then shade in parallel
+			// 'curStep += alphaStep' is a serial float accumulation (ball.cpp:195-203).  Lanes take 32-pixel blocks in turn: the
+			// running value enters a block through a shuffle, every lane then needs the value after 'lane' more additions --
+			// which lane 0 of the block produces serially (32 dependent FADDs) and hands out with shuffles.
 			const float alphaStep = 1.f / float(remainder - 1);
-			if (lane == 0)
+			float blockStart = 0.f;
+			for (unsigned i0 = 0; i0 < remainder; i0 += 32)
 			{
-				float curStep = 0.f;
-				for (unsigned i = 0; i < remainder; ++i)
+				float cur = blockStart, mine = blockStart;
+				#pragma unroll
+				for (int k = 0; k < 32; ++k)
 				{
-					line[lastDrawnHeight + i] = __float_as_uint(curStep);
-					curStep += alphaStep;
+					if (lane == k) mine = cur;
+					cur += alphaStep;
+				}
+				blockStart = cur; // identical on every lane: all lanes run the same 32 additions
+				const unsigned i = i0 + lane;
+				if (i < remainder)
+				{
+					const float fBeamAlpha = smoothstepf(f.beamAlphaMin, fLuminosity, mine);
+					const unsigned beamAlpha = f2u_x86(fBeamAlpha);
+					line[lastDrawnHeight + i] = beamCol | (beamAlpha << 24);
 				}
 			}
-			__syncwarp();
-			for (unsigned i = lane; i < remainder; i += 32)
-			{
-				const float curStep = __uint_as_float(line[lastDrawnHeight + i]);
-				const float fBeamAlpha = smoothstepf(f.beamAlphaMin, fLuminosity, curStep);
-				const unsigned beamAlpha = f2u_x86(fBeamAlpha);
-				line[lastDrawnHeight + i] = beamCol | (beamAlpha << 24);
-			}
-			__syncwarp();
 		}
 	}
-
-	for (int x = lane*4; x < f.resX; x += 128)
-		*reinterpret_cast<uint4 *>(row + x) = *reinterpret_cast<const uint4 *>(line + x);
+	else
+	{
+		// memset32(pDest, 0, kTargetSize), ball.cpp:342: only the part no span covered
+		for (int x = min(int(carryLastDrawn), f.resX) + lane; x < f.resX; x += 32)
+			line[x] = 0;
+	}
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -578,72 +569,64 @@ __global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest,
 __global__ void __launch_bounds__(kRowsPerBlock*64) twister_kernel(uint32_t *__restrict__ pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
 	const int *__restrict__ tables, const int *__restrict__ rayOrigins, int resX, int resY)
 {
-	extern __shared__ uint32_t s_lines[]; // [kRowsPerBlock][resX]
+	// one warp per ray, spans straight to global memory (see tunnelscape_kernel); the uncovered rest of each half row is cleared
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int rowInBlock = warp >> 1, side = warp & 1;
 	const unsigned iRay = blockIdx.x*kRowsPerBlock + rowInBlock;
-	uint32_t *line = s_lines + rowInBlock*resX;
-	const bool rowValid = iRay < unsigned(resY);
-
-	// memset32(g_renderTarget[0], 0, kTargetSize), torus-twister.cpp:169: each of the two warps clears its half
+	if (iRay >= unsigned(resY))
+		return;
+	uint32_t *line = pDest + size_t(iRay)*resX;
 	const int half = resX >> 1;
-	for (int x = side*half + lane; x < (side+1)*half; x += 32)
-		line[x] = 0;
-	__syncthreads();
 
-	if (rowValid)
+	const int *heightProj = tables, *heightProjNorm = tables + 512;
+	const int kHalfMap = 1024/2;
+	const int fromX0 = rayOrigins[iRay*2], fromY = rayOrigins[iRay*2+1];
+
+	// vtwister_ray(pDest+xOffs, fromX, fromY, 512) and vtwister_ray(pDest+xOffs-1, fromX-512, fromY, -512), torus-twister.cpp:113-115
+	const int startX = (0 == side) ? fromX0 : fromX0 - kHalfMap;
+	const int dX = (0 == side) ? kHalfMap : -kHalfMap;
+	const int direction = (dX < 0) ? -1 : 1;
+	const int startPos = half + ((0 == side) ? 0 : -1);
+
+	unsigned carryLastHeight = 0, carryLastDrawn = 0;
+	Color16 carryLastColor = unpack16(sample_argb(colorMap, prep_uvs(startX, fromY, 1023u, 10u)));
+
+	for (unsigned base = 0; base < 512; base += 32)
 	{
-		const int *heightProj = tables, *heightProjNorm = tables + 512;
-		const int kHalfMap = 1024/2;
-		const int fromX0 = rayOrigins[iRay*2], fromY = rayOrigins[iRay*2+1];
+		const unsigned iStep = base + lane;
+		const int curX = int(unsigned(startX) - (iStep+1)*unsigned(dX));
+		const TexCoords t = prep_uvs(curX, fromY, 1023u, 10u);
+		const unsigned mapHeight = sample_u8(heightMap, t);
+		Color16 color = unpack16(sample_argb(colorMap, t));
 
-		// vtwister_ray(pDest+xOffs, fromX, fromY, 512) and vtwister_ray(pDest+xOffs-1, fromX-512, fromY, -512), torus-twister.cpp:113-115
-		const int startX = (0 == side) ? fromX0 : fromX0 - kHalfMap;
-		const int dX = (0 == side) ? kHalfMap : -kHalfMap;
-		const int direction = (dX < 0) ? -1 : 1;
-		const int startPos = half + ((0 == side) ? 0 : -1);
+		const unsigned heightNorm = (mapHeight*unsigned(__ldg(heightProjNorm + iStep))) >> 8;
+		const int litWhite = int(heightNorm & 0xffffu);
+		#pragma unroll
+		for (int i = 0; i < 4; ++i) color.c[i] = adds16(color.c[i], litWhite);
 
-		unsigned carryLastHeight = 0, carryLastDrawn = 0;
-		Color16 carryLastColor = unpack16(sample_argb(colorMap, prep_uvs(startX, fromY, 1023u, 10u)));
+		const unsigned height = (mapHeight*unsigned(__ldg(heightProj + iStep))) >> 8;
 
-		for (unsigned base = 0; base < 512; base += 32)
-		{
-			const unsigned iStep = base + lane;
-			const int curX = int(unsigned(startX) - (iStep+1)*unsigned(dX));
-			const TexCoords t = prep_uvs(curX, fromY, 1023u, 10u);
-			const unsigned mapHeight = sample_u8(heightMap, t);
-			Color16 color = unpack16(sample_argb(colorMap, t));
+		unsigned prevHeight = __shfl_up_sync(kFull, height, 1);
+		Color16 prevColor = shfl_up_color(color);
+		if (lane == 0) { prevHeight = carryLastHeight; prevColor = carryLastColor; }
 
-			const unsigned heightNorm = (mapHeight*unsigned(__ldg(heightProjNorm + iStep))) >> 8;
-			const int litWhite = int(heightNorm & 0xffffu);
-			#pragma unroll
-			for (int i = 0; i < 4; ++i) color.c[i] = adds16(color.c[i], litWhite);
+		unsigned newLastDrawn;
+		const unsigned drawnBefore = warp_excl_max(height, carryLastDrawn, newLastDrawn);
 
-			const unsigned height = (mapHeight*unsigned(__ldg(heightProj + iStep))) >> 8;
+		const bool visible = height > drawnBefore;
+		emit_spans(line, resX, visible, startPos + int(drawnBefore)*direction, direction, height - prevHeight, height - drawnBefore, prevColor, color);
 
-			unsigned prevHeight = __shfl_up_sync(kFull, height, 1);
-			Color16 prevColor = shfl_up_color(color);
-			if (lane == 0) { prevHeight = carryLastHeight; prevColor = carryLastColor; }
-
-			unsigned newLastDrawn;
-			const unsigned drawnBefore = warp_excl_max(height, carryLastDrawn, newLastDrawn);
-
-			const bool visible = height > drawnBefore;
-			emit_spans(line, resX, visible, startPos + int(drawnBefore)*direction, direction, height - prevHeight, height - drawnBefore, prevColor, color);
-
-			carryLastDrawn = newLastDrawn;
-			carryLastHeight = __shfl_sync(kFull, height, 31);
-			carryLastColor = shfl_color(color, 31);
-		}
+		carryLastDrawn = newLastDrawn;
+		carryLastHeight = __shfl_sync(kFull, height, 31);
+		carryLastColor = shfl_color(color, 31);
 	}
 
-	__syncthreads();
-	if (rowValid)
-	{
-		uint32_t *row = pDest + size_t(iRay)*resX;
-		for (int x = (side*32 + lane)*4; x < resX; x += 256)
-			*reinterpret_cast<uint4 *>(row + x) = *reinterpret_cast<const uint4 *>(line + x);
-	}
+	// memset32(g_renderTarget[0], 0, kTargetSize), torus-twister.cpp:169: the part of this half row no span covered
+	const int covered = min(int(carryLastDrawn), half);
+	if (0 == side)
+		for (int x = half + covered + lane; x < resX; x += 32) line[x] = 0;
+	else
+		for (int x = lane; x < half - covered; x += 32) line[x] = 0;
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -747,10 +730,8 @@ extern "C" int ckd_tunnelscape_draw(ckd_ctx *ctx, const ckd_tunnelscape_params *
 
 	f.clearColor = ctx->images[CKD_IMG_TSCAPE_FOG].firstPixel; // s_pFogGradient[0], tunnelscape.cpp:170
 
-	const size_t smem = size_t(kRowsPerBlock)*ctx->resX*4;
-	CKD_TRY(EnsureSmem(tunnelscape_kernel, smem));
 	ckd_prof_begin(ctx, "voxel_tunnelscape", 4.0*ctx->resX*ctx->resY);
-	tunnelscape_kernel<<<ckd_div_up(ctx->resY, kRowsPerBlock), kRowsPerBlock*32, smem, ctx->stream>>>(ctx->d_renderTarget[0],
+	tunnelscape_kernel<<<ckd_div_up(ctx->resY, kRowsPerBlock), kRowsPerBlock*32, 0, ctx->stream>>>(ctx->d_renderTarget[0],
 		static_cast<const uint8_t *>(ctx->images[CKD_IMG_TSCAPE_HEIGHT].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_TSCAPE_COLOR].d_pixels),
 		static_cast<const uint32_t *>(ctx->images[CKD_IMG_TSCAPE_FOG].d_pixels), f);
 	CKD_CHECK_LAUNCH(ctx);
@@ -860,20 +841,17 @@ extern "C" int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time,
 	CKD_CUDA(cudaMemcpyAsync(d_tables, tables, sizeof(int)*4096, cudaMemcpyHostToDevice, ctx->stream));
 	CKD_CUDA(cudaMemcpyAsync(d_rayDeltas, rayDeltas, sizeof(int)*2*ctx->resY, cudaMemcpyHostToDevice, ctx->stream));
 
-	const size_t smem = size_t(kRowsPerBlock)*ctx->resX*4;
 	const unsigned blocks = ckd_div_up(ctx->resY, kRowsPerBlock);
 	if (hasBeams)
 	{
-		CKD_TRY(EnsureSmem(ball_kernel<true>, smem));
-		ckd_prof_begin(ctx, "voxel_ball_beams", 8.0*ctx->resX*ctx->resY);
-		ball_kernel<true><<<blocks, kRowsPerBlock*32, smem, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
+		ckd_prof_begin(ctx, "voxel_ball_beams", 4.0*ctx->resX*ctx->resY);
+		ball_kernel<true><<<blocks, kRowsPerBlock*32, 0, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
 			static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_COLOR0].d_pixels), ctx->d_ballBeamMix, d_tables, d_rayDeltas, f);
 	}
 	else
 	{
-		CKD_TRY(EnsureSmem(ball_kernel<false>, smem));
 		ckd_prof_begin(ctx, "voxel_ball", 4.0*ctx->resX*ctx->resY);
-		ball_kernel<false><<<blocks, kRowsPerBlock*32, smem, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
+		ball_kernel<false><<<blocks, kRowsPerBlock*32, 0, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
 			static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_COLOR1].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_ENV].d_pixels), d_tables, d_rayDeltas, f);
 	}
 	CKD_CHECK_LAUNCH(ctx);
@@ -932,10 +910,8 @@ extern "C" int ckd_twister_draw(ckd_ctx *ctx, const ckd_twister_params *p, float
 	CKD_CUDA(cudaMemcpyAsync(d_tables, tables, sizeof(int)*1024, cudaMemcpyHostToDevice, ctx->stream));
 	CKD_CUDA(cudaMemcpyAsync(d_rayOrigins, rayOrigins, sizeof(int)*2*ctx->resY, cudaMemcpyHostToDevice, ctx->stream));
 
-	const size_t smem = size_t(kRowsPerBlock)*ctx->resX*4;
-	CKD_TRY(EnsureSmem(twister_kernel, smem));
 	ckd_prof_begin(ctx, "voxel_twister", 4.0*ctx->resX*ctx->resY);
-	twister_kernel<<<ckd_div_up(ctx->resY, kRowsPerBlock), kRowsPerBlock*64, smem, ctx->stream>>>(ctx->d_renderTarget[0],
+	twister_kernel<<<ckd_div_up(ctx->resY, kRowsPerBlock), kRowsPerBlock*64, 0, ctx->stream>>>(ctx->d_renderTarget[0],
 		static_cast<const uint8_t *>(ctx->images[CKD_IMG_TWISTER_HEIGHT].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_TWISTER_COLOR].d_pixels),
 		d_tables, d_rayOrigins, ctx->resX, ctx->resY);
 	CKD_CHECK_LAUNCH(ctx);
