@@ -96,13 +96,17 @@ __global__ void __launch_bounds__(128) old_blur_kernel(uint8_t *pDest, const uin
 // ring that is filled ahead of time with 16-byte cp.async copies (kPrefetch stages of 64 steps in flight), so the serial
 // walk never waits for HBM; results go to a second ring from which (a) the in-place trailing edge re-reads the pixels
 // "it already wrote" and (b) finished 64-step chunks are flushed with coalesced 16-byte stores.  Every global byte is
-// read once and written once; what remains is the dependent add/clamp chain of the recurrence itself.
+// read once and written once; what remains is the dependent add/clamp chain of the recurrence itself (2 ALU operations
+// per step).  To keep that chain the only thing a step waits for, the shared-memory loads of batch i+1 are issued before
+// the chain of batch i (the compiler cannot hoist them itself: it must assume the ring stores alias them), and in-place
+// kernels narrower than 15 pixels take their trailing edge from registers (KM > 0) instead of reading back the ring.
 
 constexpr unsigned kRing = 512;                 // ring length in steps: >= 255 (widest kernel) + (kPrefetch+1)*kStage
 constexpr unsigned kStage = 64;                 // steps per cp.async group / per flush
 constexpr int kPrefetch = 3;                    // groups in flight ahead of the one being consumed
-constexpr unsigned kPitchH = kRing*4 + 16;      // bytes per line in the horizontal layout (+16: lines land in different banks)
-constexpr unsigned kRingBytes = 8*kPitchH;      // >= kRing*32 (vertical layout)
+constexpr unsigned kMirror = 16;                // the blocked kernel repeats the first steps of the input ring behind its end
+constexpr unsigned kPitchH = (kRing + kMirror)*4 + 16; // bytes per line in the horizontal layout (+16: lines land in different banks)
+constexpr unsigned kRingBytes = 8*kPitchH;      // >= (kRing + kMirror)*32 (vertical layout)
 
 __device__ __forceinline__ void cp_async16(void *smemDst, const void *gmemSrc, bool valid)
 {
@@ -110,16 +114,32 @@ __device__ __forceinline__ void cp_async16(void *smemDst, const void *gmemSrc, b
 	const int bytes = valid ? 16 : 0; // 0 -> zero fill
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(gmemSrc), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smemDst, const void *gmemSrc, bool valid)
+{
+	const unsigned dst = unsigned(__cvta_generic_to_shared(smemDst));
+	const int bytes = valid ? 4 : 0; // 0 -> zero fill
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(gmemSrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 constexpr int kBlurWarps = 4;                   // warps per CTA: one per SM sub-partition (a 1-warp CTA always lands on sub-partition 0)
 
-template <bool VERT, bool INPLACE, bool SUBEDGES>
+template <bool B> struct BoolTag { static constexpr bool value = B; };
+
+// KM: the kernel median when it is < 8 and the blur runs in place (trailing edge from registers); 0: any width (from the ring)
+template <bool VERT, bool INPLACE, bool SUBEDGES, int KM>
 __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t *pDest, const uint8_t *pSrc, unsigned numLines, unsigned len, unsigned pitch, OldBlurSetup s)
 {
 	extern __shared__ __align__(16) uint8_t s_rings[]; // per warp: input ring, output ring
+	__shared__ unsigned short s_divTab[128];           // WeightToDiv16(startWeight + 16*i): the ramps at both ends of a line
+
 	const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned edgeSpan = s.edgeSpan, kM = (KM > 0) ? unsigned(KM) : s.kernelMedian, span = edgeSpan + kM;
+	if (threadIdx.x < kM)
+		s_divTab[threadIdx.x] = (unsigned short) WeightToDiv16(s.startWeight + 16*threadIdx.x);
+	__syncthreads();
+
 	uint8_t *s_in = s_rings + warp*(2*kRingBytes);
 	uint8_t *s_out = s_in + kRingBytes;
 
@@ -187,11 +207,12 @@ __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t 
 		}
 	};
 
-	const int sh = int(s.remainderShift);
-	const unsigned edgeSpan = s.edgeSpan, kM = s.kernelMedian, span = edgeSpan + kM;
+	constexpr int sh = SUBEDGES ? 1 : 8;             // remainderShift, deprecated/boxblur.cpp:62
 	const unsigned total = len + edgeSpan;           // step t adds pixel t (while t < len) and emits output t - edgeSpan
 	const unsigned numStages = (total + kStage - 1)/kStage;
 	const unsigned mainEnd = len - edgeSpan;         // outputs [kM, mainEnd) are the full-weight main pass
+	const unsigned fastBegin = (span + 7) & ~7u;     // steady-state batches cover the steps [fastBegin, fastEnd): Add + Sub + full weight
+	const unsigned fastEnd = len & ~7u;
 	const unsigned fullDiv = s.fullDiv;
 
 	#pragma unroll
@@ -202,22 +223,27 @@ __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t 
 	}
 
 	int acc = 0, addRem = 0, subRem = 0;
+	int hist[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };       // KM > 0: the last KM outputs of this lane, newest first
 	unsigned flushed = 0;
-	unsigned long long hist = 0;                    // the last 8 outputs of this lane, newest in the low byte (short in-place kernels)
-	const unsigned histShift = (kM - 1)*8;
-	const bool shortInPlace = INPLACE && kM < 8;
 
-	// value the trailing edge subtracts at output o: pixel o - kM of the *source as the reference sees it*: already blurred
-	// when running in place, the original otherwise
-	auto subAt = [&](unsigned pos) -> int { return INPLACE ? int(s_out[ringAt(pos)]) : int(s_in[ringAt(pos)]); };
+	auto pushHist = [&](int o)
+	{
+		if (KM > 0)
+		{
+			#pragma unroll
+			for (int i = 7; i > 0; --i)
+				if (i < KM) hist[i] = hist[i-1];
+			hist[0] = o;
+		}
+	};
 
 	// one steady-state step: Add + Sub + Div (deprecated/boxblur.cpp:104-110) with the four saturating 16-bit operations folded:
-	// max(min(acc + a, 65535) - b, 0) == max(min(acc + (a - b), 65535 - b), 0), a single DPX add-min-relu.
+	// max(min(acc + a, 65535) - b, 0) == max(min(acc + (a - b), 65535 - b), 0), an add and a min-relu on the dependent chain.
 	// Odd kernels (SUBEDGES == false) shift the remainder out entirely (px >> 8 == 0): a == px, b == spx.
-	// Div: pmulhuw + packuswb == min((acc*div) >> 16, 255) whenever div <= 32768 (every kernel wider than 1 pixel; a 1-pixel
-	// kernel has div == 0): the "word read as signed" case of packuswb cannot occur, and (acc*div) >> 16 == umulhi(acc, div << 16).
+	// Div: pmulhuw + packuswb == min((acc*div) >> 16, 255) because the full-weight divisor is <= 32768 for every kernel wider than
+	// one pixel (and 0 for a 1-pixel kernel): the "word read as signed" case of packuswb cannot occur, and
+	// (acc*div) >> 16 == umulhi(acc, div << 16).
 	const unsigned fullDivHi = fullDiv << 16;
-	const bool plainDiv = fullDiv <= 32768u;
 	auto steady = [&](int px, int spx) -> unsigned
 	{
 		int a = px, b = spx;
@@ -229,7 +255,61 @@ __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t 
 			subRem = spx >> 1;
 		}
 		acc = __viaddmin_s32_relu(acc, a - b, 65535 - b);
-		return plainDiv ? min(__umulhi(unsigned(acc), fullDivHi), 255u) : old_div(unsigned(acc), fullDiv);
+		return min(__umulhi(unsigned(acc), fullDivHi), 255u);
+	};
+
+	// any step, including the ramps at both ends of the line (deprecated/boxblur.cpp:84-102, 113-126)
+	auto slowStep = [&](unsigned t)
+	{
+		if (t < len)
+		{
+			const int px = int(s_in[ringAt(t)]);
+			acc = min(acc + addRem + (px - (px >> sh)), 65535);
+			addRem = px >> sh;
+		}
+		else if (SUBEDGES && t == len)
+			acc = min(acc + addRem, 65535); // deprecated/boxblur.cpp:113-115
+		if (t >= edgeSpan)
+		{
+			const unsigned o = t - edgeSpan;
+			unsigned div;
+			if (o < kM)
+				div = s_divTab[o];
+			else
+			{
+				// the trailing edge subtracts pixel o - kM of the *source as the reference sees it*: already blurred when running in place
+				const int spx = (KM > 0) ? hist[(KM > 0) ? KM-1 : 0] : int((INPLACE ? s_out : s_in)[ringAt(o - kM)]);
+				acc = max(acc - (subRem + (spx - (spx >> sh))), 0);
+				subRem = spx >> sh;
+				div = (o < mainEnd) ? fullDiv : s_divTab[len - 1 - o];
+			}
+			const unsigned outv = old_div(unsigned(acc), div);
+			pushHist(int(outv));
+			s_out[ringAt(o)] = uint8_t(outv);
+		}
+	};
+
+	// shared-memory reads of one batch of 8 steps
+	auto loadPx = [&](unsigned tb, int (&d)[8]) // tb is a multiple of 8: no wrap inside the batch
+	{
+		const uint8_t *inp = s_in + laneBase + (tb & (kRing-1))*kStep;
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) d[j] = int(inp[j*kStep]);
+	};
+	auto loadSpx = [&](unsigned tb, int (&d)[8])
+	{
+		const uint8_t *base = (INPLACE ? s_out : s_in) + laneBase;
+		const unsigned p = (tb - span) & (kRing-1);
+		if (p <= kRing-8)
+		{
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) d[j] = int(base[(p + j)*kStep]);
+		}
+		else
+		{
+			#pragma unroll
+			for (int j = 0; j < 8; ++j) d[j] = int(base[((p + j) & (kRing-1))*kStep]);
+		}
 	};
 
 	for (unsigned stage = 0; stage < numStages; ++stage)
@@ -241,82 +321,53 @@ __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t 
 
 		const unsigned t0 = stage*kStage;
 		const unsigned t1 = min(t0 + kStage, total);
+		unsigned t = t0;
 
-		if (t0 >= span && t1 <= len && t1 - t0 == kStage)
+		for (const unsigned headEnd = min(t1, fastBegin); t < headEnd; ++t)
+			slowStep(t);
+
+		const unsigned batchEnd = min(t1, fastEnd); // a multiple of 8
+		if (t < batchEnd)
 		{
-			for (unsigned tb = t0; tb < t1; tb += 8)
-			{
-				const uint8_t *inp = s_in + laneBase + (tb & (kRing-1))*kStep; // tb is a multiple of 8: no wrap inside the batch
-				const unsigned subPos = (tb - span) & (kRing-1), outPos = (tb - edgeSpan) & (kRing-1);
-				int px[8];
-				#pragma unroll
-				for (int j = 0; j < 8; ++j) px[j] = int(inp[j*kStep]);
+			int px[8], spx[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+			if (KM > 0) loadPx(t, px);
 
-				if (shortInPlace)
+			for (unsigned tb = t; tb < batchEnd; tb += 8)
+			{
+				// KM > 0: the next batch's pixels are requested before this batch's chain (the compiler cannot hoist them over the
+				// ring stores itself); KM == 0: plain loads at the top of the batch measured faster than carrying 16 more registers
+				int pxNext[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+				if (KM > 0) loadPx(tb + 8, pxNext);
+				else { loadPx(tb, px); loadSpx(tb, spx); }
+
+				const unsigned outPos = (tb - edgeSpan) & (kRing-1);
+				auto chain = [&](auto wrapTag)
 				{
-					// the subtracted pixel was produced fewer than 8 steps ago: take it from the register history
+					constexpr bool kWrap = decltype(wrapTag)::value;
+					uint8_t *outp = s_out + laneBase + (kWrap ? 0 : outPos*kStep);
 					#pragma unroll
 					for (int j = 0; j < 8; ++j)
 					{
-						const int spx = int((hist >> histShift) & 0xff);
-						const unsigned o = steady(px[j], spx);
-						hist = (hist << 8) | o;
-						s_out[laneBase + ((outPos + j) & (kRing-1))*kStep] = uint8_t(o);
+						const int sub = (KM > 0) ? hist[(KM > 0) ? KM-1 : 0] : spx[j];
+						const unsigned o = steady(px[j], sub);
+						pushHist(int(o));
+						if (kWrap) outp[((outPos + j) & (kRing-1))*kStep] = uint8_t(o);
+						else outp[j*kStep] = uint8_t(o);
 					}
-				}
-				else
+				};
+				if (outPos <= kRing-8) chain(BoolTag<false>()); else chain(BoolTag<true>());
+
+				if (KM > 0)
 				{
-					const uint8_t *subBase = (INPLACE ? s_out : s_in) + laneBase;
-					int spx[8];
-					if (subPos <= kRing-8 && outPos <= kRing-8)
-					{
-						#pragma unroll
-						for (int j = 0; j < 8; ++j) spx[j] = int(subBase[(subPos + j)*kStep]);
-						uint8_t *outp = s_out + laneBase + outPos*kStep;
-						#pragma unroll
-						for (int j = 0; j < 8; ++j) outp[j*kStep] = uint8_t(steady(px[j], spx[j]));
-					}
-					else
-					{
-						#pragma unroll
-						for (int j = 0; j < 8; ++j) spx[j] = int(subBase[((subPos + j) & (kRing-1))*kStep]);
-						#pragma unroll
-						for (int j = 0; j < 8; ++j) s_out[laneBase + ((outPos + j) & (kRing-1))*kStep] = uint8_t(steady(px[j], spx[j]));
-					}
+					#pragma unroll
+					for (int j = 0; j < 8; ++j) px[j] = pxNext[j];
 				}
 			}
+			t = batchEnd;
 		}
-		else
-		{
-			for (unsigned t = t0; t < t1; ++t)
-			{
-				if (t < len)
-				{
-					const int px = int(s_in[ringAt(t)]);
-					acc = min(acc + addRem + (px - (px >> sh)), 65535);
-					addRem = px >> sh;
-				}
-				else if (t == len && s.subEdges)
-					acc = min(acc + addRem, 65535); // deprecated/boxblur.cpp:113-115
-				if (t >= edgeSpan)
-				{
-					const unsigned o = t - edgeSpan;
-					unsigned div;
-					if (o < kM)
-						div = WeightToDiv16(s.startWeight + 16*o);
-					else
-					{
-						const int spx = subAt(o - kM);
-						acc = max(acc - (subRem + (spx - (spx >> sh))), 0);
-						subRem = spx >> sh;
-						div = (o < mainEnd) ? fullDiv : WeightToDiv16(s.startWeight + 16*(len - 1 - o));
-					}
-					const unsigned outv = old_div(unsigned(acc), div);
-					hist = (hist << 8) | outv;
-					s_out[ringAt(o)] = uint8_t(outv);
-				}
-			}
-		}
+
+		for (; t < t1; ++t)
+			slowStep(t);
 		__syncwarp();
 
 		const unsigned done = (t1 > edgeSpan) ? t1 - edgeSpan : 0;
@@ -332,6 +383,375 @@ __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t 
 	{
 		flushStage(flushed);
 		flushed += kStage;
+	}
+}
+
+// ---- blocked version: kernels of 15 pixels and wider ------------------------------------------------------------------
+// The trailing edge of step t is the output of step t - kM (kM = kernel median), so inside a block of kM consecutive steps
+// every operand of the recurrence  acc' = max(min(acc + d, h), 0)  is known up front and the block is a composition of
+// kM clamped additions.  Those compose in closed form -- clamp(x + D, L, H) followed by the step (d, h) is
+// clamp(x + D + d, step(L), step(H)) -- which makes the walk a scan:
+//   1. each of P lanes folds its share of the block (at most QT steps) into one (D, L, H) triple,
+//   2. a log2(P)-round shuffle scan composes the triples; applied to the accumulator the block started with, it hands
+//      every lane the accumulator its share starts with,
+//   3. each lane replays its steps with the real accumulator and emits the outputs.
+// A lane's trailing-edge operands are the outputs the same lane produced one block earlier, so they stay in registers.
+// One CTA owns 8 lines (32 line-channels x P lanes); the rings, cp.async staging and 16-byte flushes are those of the
+// staged kernel above, shared by the CTA.  In place only: out of place the trailing edge is the untouched source, there is
+// no recurrence to break up and the staged kernel does.  The input ring repeats its first kMirror steps behind its end so that a lane
+// reads its few consecutive steps with immediate offsets.  Bit-exact with the serial walk: the composition is exact
+// integer algebra.
+
+template <bool VERT, bool SUBEDGES, int LOG2P, int QT>
+__global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *pDest, unsigned numLines, unsigned len, unsigned pitch, OldBlurSetup s)
+{
+	extern __shared__ __align__(16) uint8_t s_rings[]; // input ring, output ring
+	__shared__ unsigned short s_divTab[128];           // WeightToDiv16(startWeight + 16*i): the ramps at both ends of a line
+
+	constexpr unsigned P = 1u << LOG2P, C = 32u >> LOG2P; // parts per block, line-channels per warp
+	const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const unsigned edgeSpan = s.edgeSpan, kM = s.kernelMedian, span = edgeSpan + kM;
+	if (tid < kM)
+		s_divTab[tid] = (unsigned short) WeightToDiv16(s.startWeight + 16*tid);
+
+	uint8_t *s_in = s_rings;
+	uint8_t *s_out = s_rings + kRingBytes;
+
+	// lane -> (line-channel, part of the block)
+	const unsigned part = lane / C, sub = lane % C;
+	const unsigned lc = warp*C + sub;
+	const unsigned r = lc >> 2, chan = lc & 3;
+	const unsigned line0 = blockIdx.x*8;
+
+	// both rings are line-major for either direction (a "line" of the vertical pass is an image column): consecutive steps of
+	// a line-channel are 4 bytes apart, the 8 lines land in different banks
+	constexpr unsigned kStep = 4;
+	const unsigned laneBase = r*kPitchH + chan;
+
+	// the first 128 threads move the 64 steps starting at p0 between global memory and the rings: 16 bytes each along a row
+	// (horizontal), or 4 x 4 bytes, one image row each, 8 neighbouring columns per row (vertical)
+	auto loadStage = [&](unsigned p0)
+	{
+		if (tid < 128)
+		{
+			if (VERT)
+			{
+				const unsigned col = tid & 7, line = line0 + col;
+				#pragma unroll
+				for (unsigned k = 0; k < 4; ++k)
+				{
+					const unsigned pos = p0 + (tid >> 3) + k*16;
+					const bool valid = pos < len && line < numLines;
+					const uint8_t *src = valid ? pDest + (size_t(pos)*pitch + line)*4 : pDest;
+					cp_async4(s_in + col*kPitchH + (pos & (kRing-1))*4, src, valid);
+					if ((pos & (kRing-1)) < kMirror)
+						cp_async4(s_in + col*kPitchH + (kRing + (pos & (kRing-1)))*4, src, valid);
+				}
+			}
+			else
+			{
+				const unsigned pos = p0 + (tid & 15)*4, line = line0 + (tid >> 4);
+				const bool valid = pos < len && line < numLines;
+				const uint8_t *src = valid ? pDest + (size_t(line)*pitch + pos)*4 : pDest;
+				cp_async16(s_in + (tid >> 4)*kPitchH + (pos & (kRing-1))*4, src, valid);
+				if ((pos & (kRing-1)) < kMirror)
+					cp_async16(s_in + (tid >> 4)*kPitchH + (kRing + (pos & (kRing-1)))*4, src, valid);
+			}
+		}
+	};
+	auto flushStage = [&](unsigned p0)
+	{
+		if (tid < 128)
+		{
+			if (VERT)
+			{
+				const unsigned col = tid & 7, line = line0 + col;
+				uint32_t v[4];
+				#pragma unroll
+				for (unsigned k = 0; k < 4; ++k)
+					v[k] = *reinterpret_cast<const uint32_t *>(s_out + col*kPitchH + ((p0 + (tid >> 3) + k*16) & (kRing-1))*4);
+				#pragma unroll
+				for (unsigned k = 0; k < 4; ++k)
+				{
+					const unsigned pos = p0 + (tid >> 3) + k*16;
+					if (pos < len && line < numLines)
+						*reinterpret_cast<uint32_t *>(pDest + (size_t(pos)*pitch + line)*4) = v[k];
+				}
+			}
+			else
+			{
+				const unsigned pos = p0 + (tid & 15)*4, line = line0 + (tid >> 4);
+				if (pos < len && line < numLines)
+					*reinterpret_cast<uint4 *>(pDest + (size_t(line)*pitch + pos)*4) = *reinterpret_cast<const uint4 *>(s_out + (tid >> 4)*kPitchH + (pos & (kRing-1))*4);
+			}
+		}
+	};
+
+	constexpr int sh = SUBEDGES ? 1 : 8;             // remainderShift, deprecated/boxblur.cpp:62
+	const unsigned total = len + edgeSpan;           // step t adds pixel t (while t < len) and emits output t - edgeSpan
+	const unsigned mainEnd = len - edgeSpan;         // outputs [kM, mainEnd) are the full-weight main pass
+	const unsigned fullDiv = s.fullDiv, fullDivHi = fullDiv << 16;
+
+	// this lane's share of every block: steps [s0, s0 + cnt) of the block, cnt is QT or QT - 1 (the host picks QT = ceil(kM/P))
+	const unsigned s0 = (part*kM) >> LOG2P;
+	const unsigned cnt = (((part + 1)*kM) >> LOG2P) - s0;
+	const unsigned srcCarry = (part == 0) ? (P-1)*C + sub : lane - C;
+	const unsigned srcLast = (P-1)*C + sub;
+
+	#pragma unroll
+	for (int p = 0; p < kPrefetch; ++p)
+	{
+		loadStage(p*kStage);
+		cp_async_commit();
+	}
+	int x0 = 0;                                      // accumulator at the start of the block (same on every lane)
+	int outPrev[QT];                                 // this lane's outputs of the previous block
+	#pragma unroll
+	for (int q = 0; q < QT; ++q) outPrev[q] = 0;
+	int lastOut1 = 0, lastOut2 = 0;                  // this lane's last output one and two blocks ago
+
+	__syncthreads();                                 // s_divTab
+
+	// shared-memory byte accesses through 32-bit shared addresses (one base, immediate offsets)
+	const unsigned inBase = unsigned(__cvta_generic_to_shared(s_in)) + laneBase;
+	const unsigned outBase = unsigned(__cvta_generic_to_shared(s_out)) + laneBase;
+	// the lane's share is QT or QT - 1 steps: the last step is the only one that can fall outside it
+	const int lastMine = (cnt == unsigned(QT)) ? 1 : 0;
+
+	// one block.  kSteady: every step is Add + Sub at full weight and all operands exist
+	auto block = [&](unsigned tb, auto steadyTag)
+	{
+		constexpr bool kSteady = decltype(steadyTag)::value;
+		const unsigned t0 = tb + s0;
+
+		// even kernels: the remainder the first step subtracts belongs to the output before this lane's share
+		int carry = 0;
+		if (SUBEDGES)
+			carry = __shfl_sync(0xffffffffu, (part == P-1) ? lastOut2 : lastOut1, srcCarry);
+
+		// 1. fold this lane's steps: operands (deprecated/boxblur.cpp:17-36, the four saturating operations of Add + Sub folded
+		//    into d = a - b, h = 65535 - b as in the staged kernel) and the (D, L, H) triple of their composition.
+		//    A step past the lane's share reads as zero pixels: d = 0, h = 65535, the identity.
+		const unsigned inAddr = inBase + ((t0 - 1) & (kRing-1))*kStep; // +0: pixel t0 - 1, +(1 + q)*kStep: pixel t0 + q (the ring's mirror: no wrap)
+		int pxs[QT + 1];
+		#pragma unroll
+		for (int q = 0; q <= QT; ++q)
+		{
+			unsigned v;
+			asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(inAddr + q*kStep) : "memory");
+			pxs[q] = int(v);
+		}
+
+		int d[QT], h[QT];
+		int D = 0, L = 0, H = 65535;
+		int prevPx = 0, prevS = 0;
+		if (SUBEDGES)
+		{
+			prevPx = (kSteady || (t0 >= 1 && t0 <= len)) ? pxs[0] : 0;
+			prevS = (kSteady || t0 >= span + 1) ? carry : 0;
+		}
+		#pragma unroll
+		for (int q = 0; q < QT; ++q)
+		{
+			const unsigned t = t0 + q;
+			const int m = (q == QT-1) ? lastMine : 1;
+			int px = pxs[1 + q]*m, spx = outPrev[q]*m, a;
+			if (!kSteady)
+			{
+				if (t >= len) px = 0;
+				if (t < span || t >= total) spx = 0;
+			}
+			a = (prevPx >> sh) + (px - (px >> sh));
+			if (!kSteady && t > len) a = 0;                  // t == len: the pending remainder, deprecated/boxblur.cpp:113-115
+			int b = (prevS >> sh) + (spx - (spx >> sh));
+			if (SUBEDGES && q == QT-1) { a *= m; b *= m; }   // the pending remainders belong to the next lane's first step
+			prevPx = px; prevS = spx;
+			d[q] = a - b;
+			h[q] = 65535 - b;
+			D += d[q];
+			L = __viaddmin_s32_relu(L, d[q], h[q]);
+			H = __viaddmin_s32_relu(H, d[q], h[q]);
+		}
+
+		// 2. inclusive scan over the parts: (D, L, H) becomes the composition of parts 0..part
+		#pragma unroll
+		for (unsigned round = 0; round < unsigned(LOG2P); ++round)
+		{
+			const unsigned delta = C << round;
+			const int De = __shfl_up_sync(0xffffffffu, D, delta), Le = __shfl_up_sync(0xffffffffu, L, delta), He = __shfl_up_sync(0xffffffffu, H, delta);
+			if (part >= (1u << round))
+			{
+				// x -> clamp(clamp(x + De, Le, He) + D, L, H) == clamp(x + De + D, clamp(Le + D, L, H), clamp(He + D, L, H))
+				const int Ln = max(__viaddmin_s32(Le, D, H), L), Hn = max(__viaddmin_s32(He, D, H), L);
+				D += De; L = Ln; H = Hn;
+			}
+		}
+		const int accEnd = max(__viaddmin_s32(x0, D, H), L);           // accumulator after this lane's share
+		int acc = __shfl_up_sync(0xffffffffu, accEnd, C);               // ... and before it
+		if (part == 0) acc = x0;
+		x0 = __shfl_sync(0xffffffffu, accEnd, srcLast);                 // the next block starts where the last part ends
+
+		// 3. replay with the real accumulator, emit outputs (Div, deprecated/boxblur.cpp:39-42).  A step past the lane's share
+		//    computes garbage that nothing reads: its slot of outPrev is masked when it is used.
+		int o[QT];
+		#pragma unroll
+		for (int q = 0; q < QT; ++q)
+		{
+			const unsigned t = t0 + q;
+			acc = __viaddmin_s32_relu(acc, d[q], h[q]);
+			if (kSteady)
+				o[q] = int(min(__umulhi(unsigned(acc), fullDivHi), 255u)); // the full-weight divisor is <= 32768: see the staged kernel
+			else
+			{
+				const unsigned oi = (t >= edgeSpan && t < total) ? t - edgeSpan : 0;
+				const unsigned div = (oi < kM) ? s_divTab[oi] : (oi < mainEnd) ? fullDiv : s_divTab[len - 1 - oi];
+				o[q] = int(old_div(unsigned(acc), div));
+			}
+			outPrev[q] = o[q];
+		}
+		if (SUBEDGES)
+		{
+			lastOut2 = lastOut1;
+			lastOut1 = lastMine ? o[QT-1] : o[(QT >= 2) ? QT-2 : 0];
+		}
+
+		// stores: a step outside the share (or outside the line, at the ramps) goes to a dummy slot behind the ring
+		const unsigned outPos = (t0 - edgeSpan) & (kRing-1);
+		const unsigned dummy = outBase + (kRing + kMirror - 1)*kStep;
+		if (kSteady && outPos + QT <= kRing)
+		{
+			const unsigned addr0 = outBase + outPos*kStep;
+			#pragma unroll
+			for (int q = 0; q < QT; ++q)
+			{
+				const unsigned addr = (q < QT-1 || lastMine) ? addr0 + q*kStep : dummy;
+				asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(o[q]) : "memory");
+			}
+		}
+		else
+		{
+			#pragma unroll
+			for (int q = 0; q < QT; ++q)
+			{
+				const unsigned t = t0 + q;
+				bool emit = (q < QT-1) || lastMine;
+				if (!kSteady) emit = emit && t >= edgeSpan && t < total;
+				const unsigned addr = emit ? outBase + ((outPos + q) & (kRing-1))*kStep : dummy;
+				asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(o[q]) : "memory");
+			}
+		}
+	};
+
+	unsigned readyEnd = 0;                           // pixels [0, readyEnd) have landed in the ring
+	unsigned flushNext = kStage + edgeSpan;          // a 64-output chunk is complete once the steps reach this
+	auto advance = [&](unsigned te)                  // pixels up to the end of the block must have landed
+	{
+		while (readyEnd < te)
+		{
+			loadStage(readyEnd + kPrefetch*kStage);
+			cp_async_commit();
+			cp_async_wait<kPrefetch>();
+			__syncthreads();
+			readyEnd += kStage;
+		}
+	};
+	auto retire = [&](unsigned te)                   // finished 64-output chunks go out with 16-byte stores
+	{
+		if (te >= flushNext)
+		{
+			__syncthreads();
+			do
+			{
+				flushStage(flushNext - kStage - edgeSpan);
+				flushNext += kStage;
+			}
+			while (te >= flushNext);
+		}
+	};
+
+	// ramp up, steady state, ramp down
+	unsigned tb = 0;
+	for (; tb < span + 1 && tb < total; tb += kM)
+	{
+		const unsigned te = min(tb + kM, total);
+		advance(min(te, len));
+		block(tb, BoolTag<false>());
+		retire(te);
+	}
+	for (; tb + kM <= len; tb += kM)
+	{
+		advance(tb + kM);
+		block(tb, BoolTag<true>());
+		retire(tb + kM);
+	}
+	for (; tb < total; tb += kM)
+	{
+		const unsigned te = min(tb + kM, total);
+		advance(min(te, len));
+		block(tb, BoolTag<false>());
+		retire(te);
+	}
+
+	cp_async_wait<0>();
+	__syncthreads();
+	for (unsigned p0 = flushNext - kStage - edgeSpan; p0 < len; p0 += kStage)
+		flushStage(p0);
+}
+
+template <bool VERT, bool SUBEDGES>
+static cudaError_t LaunchBlocked(ckd_ctx *ctx, uint8_t *p, unsigned numLines, unsigned len, unsigned pitch, const OldBlurSetup &s)
+{
+	// Shape of a block: P = 1 << log2P lanes per line-channel, QT = ceil(kM/P) steps each.  Measured on B200 at 4K the fewest
+	// parts that keep QT <= 8 win: every extra scan round costs more than the warps it adds hide.
+	const unsigned blocks = ckd_div_up(numLines, 8), kM = s.kernelMedian;
+	const unsigned log2P = (kM <= 32) ? 2 : (kM <= 64) ? 3 : 4;
+	const int qt = int((kM + (1u << log2P) - 1) >> log2P); // every lane then owns qt or qt - 1 steps
+
+	const size_t smem = 2*kRingBytes;
+	#define CKD_BLOCKED(LOG2P, QT) old_blur_blocked_kernel<VERT, SUBEDGES, LOG2P, QT><<<blocks, 32 << LOG2P, smem, ctx->stream>>>(p, numLines, len, pitch, s)
+	#define CKD_BLOCKED_QT(LOG2P) switch (qt) { case 2: CKD_BLOCKED(LOG2P, 2); break; case 3: CKD_BLOCKED(LOG2P, 3); break; case 4: CKD_BLOCKED(LOG2P, 4); break; \
+		case 5: CKD_BLOCKED(LOG2P, 5); break; case 6: CKD_BLOCKED(LOG2P, 6); break; case 7: CKD_BLOCKED(LOG2P, 7); break; default: CKD_BLOCKED(LOG2P, 8); break; }
+	switch (log2P)
+	{
+	case 2: CKD_BLOCKED_QT(2); break;
+	case 3: CKD_BLOCKED_QT(3); break;
+	default: CKD_BLOCKED_QT(4); break;
+	}
+	#undef CKD_BLOCKED_QT
+	#undef CKD_BLOCKED
+	return cudaSuccess;
+}
+
+template <bool VERT, bool INPLACE, bool SUBEDGES, int KM>
+static cudaError_t LaunchStaged(ckd_ctx *ctx, uint8_t *pDest, const uint8_t *pSrc, unsigned numLines, unsigned len, unsigned pitch, const OldBlurSetup &s)
+{
+	const unsigned blocks = ckd_div_up(numLines, 8*kBlurWarps);
+	const size_t smem = size_t(kBlurWarps)*2*kRingBytes;
+	bool &attrSet = ctx->blurAttrSet[(((VERT ? 1 : 0)*2 + (INPLACE ? 1 : 0))*2 + (SUBEDGES ? 1 : 0))*8 + KM];
+	if (!attrSet)
+	{
+		const cudaError_t err = cudaFuncSetAttribute(old_blur_staged_kernel<VERT, INPLACE, SUBEDGES, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+		if (cudaSuccess != err)
+			return err;
+		attrSet = true;
+	}
+	old_blur_staged_kernel<VERT, INPLACE, SUBEDGES, KM><<<blocks, kBlurWarps*32, smem, ctx->stream>>>(pDest, pSrc, numLines, len, pitch, s);
+	return cudaSuccess;
+}
+
+template <bool VERT, bool SUBEDGES>
+static cudaError_t LaunchStagedInPlace(ckd_ctx *ctx, uint8_t *p, unsigned numLines, unsigned len, unsigned pitch, const OldBlurSetup &s)
+{
+	switch (s.kernelMedian)
+	{
+	case 1: return LaunchStaged<VERT, true, SUBEDGES, 1>(ctx, p, p, numLines, len, pitch, s);
+	case 2: return LaunchStaged<VERT, true, SUBEDGES, 2>(ctx, p, p, numLines, len, pitch, s);
+	case 3: return LaunchStaged<VERT, true, SUBEDGES, 3>(ctx, p, p, numLines, len, pitch, s);
+	case 4: return LaunchStaged<VERT, true, SUBEDGES, 4>(ctx, p, p, numLines, len, pitch, s);
+	case 5: return LaunchStaged<VERT, true, SUBEDGES, 5>(ctx, p, p, numLines, len, pitch, s);
+	case 6: return LaunchStaged<VERT, true, SUBEDGES, 6>(ctx, p, p, numLines, len, pitch, s);
+	case 7: return LaunchStaged<VERT, true, SUBEDGES, 7>(ctx, p, p, numLines, len, pitch, s);
+	default: return LaunchStaged<VERT, true, SUBEDGES, 0>(ctx, p, p, numLines, len, pitch, s);
 	}
 }
 
@@ -363,24 +783,31 @@ static int OldBlurPass(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, un
 	ckd_prof_begin(ctx, vert ? "old_blur_v" : "old_blur_h", 8.0*numLines*lineLen);
 	if (aligned && !overlap)
 	{
-		const unsigned blocks = ckd_div_up(numLines, 8*kBlurWarps);
-		const size_t smem = size_t(kBlurWarps)*2*kRingBytes;
-		#define CKD_BLUR_LAUNCH(V, I, E) do { \
-			if (!ctx->blurAttrSet[variant]) { CKD_CUDA(cudaFuncSetAttribute(old_blur_staged_kernel<V, I, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); ctx->blurAttrSet[variant] = true; } \
-			old_blur_staged_kernel<V, I, E><<<blocks, kBlurWarps*32, smem, ctx->stream>>>(pDest, pSrc, numLines, lineLen, pitch, s); } while (0)
+		cudaError_t err;
 		const int variant = (vert ? 4 : 0) | (inPlace ? 2 : 0) | (s.subEdges ? 1 : 0);
-		switch (variant)
+		// The serial walk runs one warp per 8 lines; once that alone puts three warps on every SM (vertical passes at 4K) it holds
+		// its own against the scan up to medium kernels.  Measured on B200, see profiles/r01_notes.md.
+		const unsigned blockedFrom = (numLines/8 >= 3u*unsigned(ctx->numSMs)) ? 20 : 8;
+		if (inPlace && s.kernelMedian >= blockedFrom)
 		{
-		case 0: CKD_BLUR_LAUNCH(false, false, false); break;
-		case 1: CKD_BLUR_LAUNCH(false, false, true); break;
-		case 2: CKD_BLUR_LAUNCH(false, true, false); break;
-		case 3: CKD_BLUR_LAUNCH(false, true, true); break;
-		case 4: CKD_BLUR_LAUNCH(true, false, false); break;
-		case 5: CKD_BLUR_LAUNCH(true, false, true); break;
-		case 6: CKD_BLUR_LAUNCH(true, true, false); break;
-		default: CKD_BLUR_LAUNCH(true, true, true); break;
+			if (vert) err = s.subEdges ? LaunchBlocked<true, true>(ctx, pDest, numLines, lineLen, pitch, s) : LaunchBlocked<true, false>(ctx, pDest, numLines, lineLen, pitch, s);
+			else err = s.subEdges ? LaunchBlocked<false, true>(ctx, pDest, numLines, lineLen, pitch, s) : LaunchBlocked<false, false>(ctx, pDest, numLines, lineLen, pitch, s);
 		}
-		#undef CKD_BLUR_LAUNCH
+		else
+		{
+			switch (variant)
+			{
+			case 0: err = LaunchStaged<false, false, false, 0>(ctx, pDest, pSrc, numLines, lineLen, pitch, s); break;
+			case 1: err = LaunchStaged<false, false, true, 0>(ctx, pDest, pSrc, numLines, lineLen, pitch, s); break;
+			case 2: err = LaunchStagedInPlace<false, false>(ctx, pDest, numLines, lineLen, pitch, s); break;
+			case 3: err = LaunchStagedInPlace<false, true>(ctx, pDest, numLines, lineLen, pitch, s); break;
+			case 4: err = LaunchStaged<true, false, false, 0>(ctx, pDest, pSrc, numLines, lineLen, pitch, s); break;
+			case 5: err = LaunchStaged<true, false, true, 0>(ctx, pDest, pSrc, numLines, lineLen, pitch, s); break;
+			case 6: err = LaunchStagedInPlace<true, false>(ctx, pDest, numLines, lineLen, pitch, s); break;
+			default: err = LaunchStagedInPlace<true, true>(ctx, pDest, numLines, lineLen, pitch, s); break;
+			}
+		}
+		CKD_CUDA(err);
 	}
 	else
 	{

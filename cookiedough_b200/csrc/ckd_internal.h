@@ -29,7 +29,7 @@ struct ckd_ctx {
 	cudaStream_t copyStream = nullptr;             // read-back overlapped with rendering (ckd_download_overlapped)
 	cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
 	bool copyPending[2] = { false, false };
-	bool blurAttrSet[8] = {};                      // opt-in shared-memory size set for the staged blur variants on this device
+	bool blurAttrSet[64] = {};                     // opt-in shared-memory size set for the staged blur variants on this device
 	unsigned long long launches = 0;
 
 	// device twins of the reference's global buffers (all carved out of one allocation, with guard rows)

@@ -9,6 +9,7 @@ from cookiedough_b200.assets import Assets
 from oracle import ref as oref
 import post_cases as pc
 
+STRENGTHS = tuple(float(a) for a in sys.argv[1:]) or (0.01, 0.02, 0.05, 0.11, 0.33, 1.0)
 for res_y in (720, 2160):
     res_x = res_y * 16 // 9
     assets = Assets(res_x, res_y)
@@ -19,7 +20,7 @@ for res_y in (720, 2160):
     d_a = ctx.to_device(src, pad_elems=4 * res_x)
     d_b = ctx.to_device(src, pad_elems=4 * res_x)
     for kind in ("h", "v", "hv"):
-        for strength in (0.01, 0.02, 0.05, 0.11, 0.33, 1.0):
+        for strength in STRENGTHS:
             for inplace in (True, False):
                 ra = oref.aligned_u32(n, pad=4 * res_x); ra[:] = src
                 rb = oref.aligned_u32(n, pad=4 * res_x); rb[:] = src
@@ -28,8 +29,10 @@ for res_y in (720, 2160):
                 ctx.old_blur(kind, d_a, d_a if inplace else d_b, res_x, res_y, strength)
                 out = ctx.download(d_a, (n,))
                 ok = np.array_equal(out, ra)
-                ts = []
+                ctx.profile_begin()  # CUDA events around every launch, inside the library: no Python in the timed interval
                 for _ in range(5):
-                    ctx.timer_start(); ctx.old_blur(kind, d_a, d_a if inplace else d_b, res_x, res_y, strength); ts.append(ctx.timer_stop_ms())
-                print(f"{res_x}x{res_y} old_blur_{kind:2s} s={strength:<5} {'inplace' if inplace else 'copy   '} {'OK  ' if ok else 'FAIL'} {np.median(ts)*1e3:8.1f} us")
+                    ctx.old_blur(kind, d_a, d_a if inplace else d_b, res_x, res_y, strength)
+                stats = ctx.profile_end()
+                us = sum(v["total_ms"] for v in stats.values())/5*1e3
+                print(f"{res_x}x{res_y} old_blur_{kind:2s} s={strength:<5} K={max(1, min(255, int(strength*255 + 0.5))):3d} {'inplace' if inplace else 'copy   '} {'OK  ' if ok else 'FAIL'} {us:8.1f} us")
     ctx.close()
