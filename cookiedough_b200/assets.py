@@ -49,6 +49,50 @@ SPEC = {
     "assets/demo/tpb_xbox_tp-263x243.png": (243, 263, False, False, False),
 }
 
+# the compositor's layers and sprites (code/demo.cpp:198-374), in load order.  Output-sized layers are nearest-upscaled with
+# the resolution like the effects' own art; sprites and the 1280x568 credit logos stay as they are (the reference places them
+# with compile-time constants); the ribbon strip scales with the resolution so that the part-12 strided read (hard-coded
+# stride 2160, code/demo.cpp:883) stays inside the image at 4K.
+_CREDITS = (
+    ["assets/credits/Credits_Tag_Superplek_outlined.png", "assets/credits/Credits_Tag_Comatron_Featuring_Celin_outlined.png",
+     "assets/credits/Credits_Tag_Jade_outlined.png", "assets/credits/Credits_Tag_ErnstHot_outlined_new.png"]
+    + [f"assets/credits/comatron_anim/comatron_{i}.png" for i in range(1, 6)]
+    + [f"assets/credits/animplek/animplek{i}.png" for i in range(5)]
+    + [f"assets/credits/jade&nytrik/jade&nytrik{i}.png" for i in range(5)]
+    + [f"assets/credits/animhot0/animhot{i}.png" for i in range(5)])
+_LAYERS = (
+    ["assets/demo/tpb-06-dirty-vignette-1280x720.png"]
+    + [f"assets/spikeball/Layer 2023_{i}.png" for i in range(1, 5)]
+    + ["assets/spikeball/Vignette_CoolFilmLook.png", "assets/spikeball/Vignette_Layer02_inverted.png",
+       "assets/spikeball/SpikeyBall_byPass_BG_Overlay.png", "assets/spikeball/nytrik-TheYearWas_Overlay_LensDirt.jpg"]
+    + [f"assets/tunnels/layer 1995_{i}.png" for i in range(1, 5)]
+    + [f"assets/tunnels/layer 2006_{i}.png" for i in range(1, 5)]
+    + ["assets/tunnels/nytrik-TheYearWas_Overlay_LensDirt.png", "assets/tunnels/Vignette_CoolFilmLook.png",
+       "assets/tunnels/Vignette_Layer02_inverted.png", "assets/demo/nytrik-god-layer-720p.png", "assets/scape/revision-logo_white.png",
+       "assets/ball/Vignette_Sparta300.png", "assets/greetings/Bokeh_Lens_Dirt_51.png"]
+    + [f"assets/greetings/Greetings_Part{i}_BG_Overlay.png" for i in range(1, 5)]
+    + ["assets/greetings/Vignette_CoolFilmLook.png", "assets/nautilus/Vignette.png", "assets/nautilus/GlassDirt_Distorted2.png",
+       "assets/nautilus/JacquesCousteau_Silhouette2.png", "assets/nautilus/JacquesCousteau1_Silhouette.png",
+       "assets/nautilus/JacquesCousteau1_Silhouette_RimMask.png", "assets/nautilus/JacquesCousteau_Silhouette2_RimMask.png",
+       "assets/nautilus/JacquesCousteau_Text.png", "assets/closeup/raker-LensDirt5_invert.png", "assets/closeup/VignetteForRaker.png",
+       "assets/closeup/Vignette_CoolFilmLook.png", "assets/underwater/LensDirt3_invert.png",
+       "assets/underwater/love prism_alpha 1280_720.png"])
+_SPRITES = dict(
+    [(f"assets/demo/tpb-06-disco-guy/{n}.png", (128, 128)) for n in ("1", "1b", "2", "2b", "3", "3b", "4", "4b")]
+    + [("assets/demo/are-we-done-1100x57.png", (57, 1100)), ("assets/closeup/raker_textSmall.png", (115, 624)),
+       ("assets/shooting/Lenz.png", (64, 64)), ("assets/demo/GPU-joke.png", (160, 960))])
+RIBBONS = "assets/demo/ribbons.png"  # 2160x720, scaled by res_y/720
+
+DEMO_SPEC = {}
+for _p in _CREDITS:
+    DEMO_SPEC[_p] = (568, 1280, False, False, False)
+for _p in _LAYERS:
+    DEMO_SPEC[_p] = (720, 1280, False, True, False)
+for _p, (_h, _w) in _SPRITES.items():
+    DEMO_SPEC[_p] = (_h, _w, False, False, False)
+DEMO_SPEC[RIBBONS] = (720, 2160, False, False, False)
+SPEC.update(DEMO_SPEC)
+
 
 def default_npz_path():
     return os.environ.get("CKD_ASSETS", os.path.join(_REPO, "oracle", "_ref", "assets.npz"))
@@ -104,8 +148,8 @@ def _synthetic(path, h, w, gray):
     g = np.roll(lum, w // 7, axis=1)
     r = np.roll(lum, h // 5, axis=0) if h > 1 else np.roll(lum, w // 11, axis=1)
     a = np.full_like(lum, 255)
-    if "halo" in path or "background" in path or "blur-map" in path or "foggradient" in path:
-        a = np.roll(lum, w // 3, axis=1)
+    if "halo" in path or "background" in path or "blur-map" in path or "foggradient" in path or path in DEMO_SPEC:
+        a = np.roll(lum, w // 3, axis=1)  # the compositor's layers are mixed by their own alpha: keep it varied
     if "foggradient" in path:
         ramp = (np.arange(w, dtype=np.int64) * 200 // max(w - 1, 1)).astype(np.uint8)[None, :]
         b, g, r = ramp, (ramp // 2 + 20).astype(np.uint8), (255 - ramp).astype(np.uint8) // 3
@@ -142,8 +186,15 @@ class Assets:
                 arr = _nearest_resize(arr, self.res_y, self.res_x)
             elif fx_sized:
                 arr = _nearest_resize(arr, self.fx_y, self.fx_x)
+            elif path == RIBBONS:
+                arr = _nearest_resize(arr, h * self.res_y // 720, w * self.res_y // 720)
             self._cache[path] = np.ascontiguousarray(arr)
         return self._cache[path]
 
-    def paths(self):
-        return list(SPEC.keys())
+    def paths(self, demo=False):
+        """the images of the five effects and Shared_Create; with demo=True also the compositor's (code/demo.cpp:198-374)"""
+        return [p for p in SPEC if demo or p not in DEMO_SPEC]
+
+    def drop(self, path):
+        """forget the cached array (4K layers are 33 MB each: callers that have handed one over can release it)"""
+        self._cache.pop(path, None)

@@ -382,6 +382,14 @@ extern "C" int ckd_upload(ckd_ctx *ctx, void *d_dst, const void *h_src, size_t b
 	return CKD_OK;
 }
 
+extern "C" int ckd_copy(ckd_ctx *ctx, void *d_dst, const void *d_src, size_t bytes)
+{
+	CKD_REQUIRE(ctx && d_dst && d_src, "null argument");
+	CKD_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	ctx->launches++;
+	return CKD_OK;
+}
+
 extern "C" int ckd_download(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
 {
 	CKD_REQUIRE(ctx && h_dst && d_src, "null argument");

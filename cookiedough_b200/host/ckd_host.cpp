@@ -5,7 +5,7 @@
 // the per-effect Create/Draw/Destroy shims that read the same tracks the reference reads, and host-buffer wrappers of
 // the 2D post ops.
 
-#include "../../include/ckd_host.h"
+#include "ckd_host_internal.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -322,9 +322,13 @@ void CkdHost_SetPipelined(bool enabled)
 	s_pipelined = enabled;
 }
 
+static uint32_t *s_composeTarget = nullptr;     // non-null while Demo_Draw composes a frame on the device
+
 // device buffer the next X_Draw renders into: the single frame twin, or the free slot of the two-deep pipeline
 static uint32_t *Target()
 {
+	if (nullptr != s_composeTarget)
+		return s_composeTarget;
 	if (!s_pipelined)
 		return ckd_frame(s_ctx);
 	Check(ckd_wait_download(s_ctx, s_slot), "X_Draw"); // the copy that last read this buffer must have finished
@@ -333,7 +337,7 @@ static uint32_t *Target()
 
 static void Finish(int rc, uint32_t *pDest, const char *what)
 {
-	if (!Check(rc, what))
+	if (!Check(rc, what) || nullptr != s_composeTarget)
 		return;
 	const size_t bytes = size_t(ckd_res_x(s_ctx))*ckd_res_y(s_ctx)*sizeof(uint32_t);
 	if (s_pipelined)
@@ -344,6 +348,35 @@ static void Finish(int rc, uint32_t *pDest, const char *what)
 	}
 	if (Check(ckd_download(s_ctx, pDest, ckd_frame(s_ctx), bytes), what))
 		Check(ckd_sync(s_ctx), what);
+}
+
+namespace ckdhost
+{
+	bool Check(int rc, const char *what) { return ::Check(rc, what); }
+
+	bool FindImage(const char *path, ImageView &view)
+	{
+		auto it = s_images.find(path);
+		if (it == s_images.end())
+			return false;
+		view = { it->second.pixels.data(), it->second.width, it->second.height, it->second.bpp };
+		return true;
+	}
+
+	void ReleaseImage(const char *path) { s_images.erase(path); }
+
+	uint32_t *BeginCompose()
+	{
+		s_composeTarget = nullptr;
+		s_composeTarget = Target();
+		return s_composeTarget;
+	}
+
+	void EndCompose(uint32_t *pDest)
+	{
+		s_composeTarget = nullptr;
+		Finish(CKD_OK, pDest, "Demo_Draw");
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -889,6 +922,25 @@ void ckdhost_destroy()
 {
 	Twister_Destroy(); Landscape_Destroy(); Ball_Destroy(); Tunnelscape_Destroy(); Shadertoy_Destroy();
 	Rocket::Land();
+	CkdHost_Destroy();
+}
+
+// Demo_Create / Demo_Draw / Demo_Destroy, demo.h:8-10
+int ckdhost_demo_create() { return Demo_Create() ? 0 : -1; }
+
+int ckdhost_demo_draw(uint32_t *pDest, double seconds, float delta)
+{
+	s_lastError.clear();
+	CkdHost_SetTime(seconds);
+	const bool running = Demo_Draw(pDest, float(seconds), delta);
+	if (!s_lastError.empty())
+		return -2;
+	return running ? 1 : 0;
+}
+
+void ckdhost_demo_destroy()
+{
+	Demo_Destroy();
 	CkdHost_Destroy();
 }
 

@@ -1,0 +1,21 @@
+// ckd_host_internal.h -- what the compositor (ckd_demo.cpp) shares with the effect shims (ckd_host.cpp)
+#pragma once
+
+#include "../../include/ckd_host.h"
+
+#include <stddef.h>
+
+namespace ckdhost
+{
+	bool Check(int rc, const char *what);          // false + SetLastError when rc != CKD_OK
+
+	// registered (pre-decoded) image, as handed to CkdHost_RegisterImage; nullptr when the path is unknown
+	struct ImageView { const void *pixels; int width, height, bpp; };
+	bool FindImage(const char *path, ImageView &view);
+	void ReleaseImage(const char *path);           // drop the host copy (after it went to the device)
+
+	// While composing, X_Draw(pDest, ...) renders into d_frame and leaves it on the device (pDest is ignored):
+	// the compositor downloads the finished frame once.
+	uint32_t *BeginCompose();                      // returns the device frame the effects will render into
+	void EndCompose(uint32_t *pDest);              // device frame -> pDest (pipelined or synchronous, like X_Draw)
+}

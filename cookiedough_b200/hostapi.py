@@ -33,6 +33,9 @@ def _lib():
     L.ckdhost_track_i.argtypes = [C.c_char_p]
     L.ckdhost_draw.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_float]
     L.ckdhost_post.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_uint]
+    L.ckdhost_demo_create.argtypes = []
+    L.ckdhost_demo_draw.argtypes = [C.c_void_p, C.c_double, C.c_float]
+    L.ckdhost_demo_destroy.argtypes = []
     L._host_bound = True
     return L
 
@@ -67,16 +70,23 @@ class RocketOnly:
 class Host:
     """CkdHost_Create + Rocket::Launch + the five X_Create (code/main.cpp:263-279, code/demo.cpp:140-148)"""
 
-    def __init__(self, res_x, res_y, device, assets, rocket_source=None):
+    def __init__(self, res_x, res_y, device, assets, rocket_source=None, demo=False):
+        """demo=True: Demo_Create (code/demo.cpp:138-367) instead of the bare effects: also loads the compositor's art"""
         self.L = _lib()
         self.res_x, self.res_y = res_x, res_y
+        self.demo = bool(demo)
         source = rocket_source or default_rocket_source()
         if self.L.ckdhost_create(res_x, res_y, device, str(source).encode()) != 0:
             raise capi.CkdError(self.L.ckdhost_last_error().decode())
-        for path in capi.IMAGE_SLOTS:
+        paths = list(capi.IMAGE_SLOTS)
+        if self.demo:
+            paths += [p for p in assets.paths(demo=True) if p not in capi.IMAGE_SLOTS]
+        for path in paths:
             arr = assets[path]
             self.L.ckdhost_register_image(path.encode(), arr.ctypes.data, arr.shape[1], arr.shape[0], 1 if arr.dtype == np.uint8 else 4)
-        rc = self.L.ckdhost_launch()
+            if self.demo and arr.nbytes > (8 << 20):
+                assets.drop(path)  # the host layer copied it; 4K layers are 33 MB each
+        rc = self.L.ckdhost_demo_create() if self.demo else self.L.ckdhost_launch()
         if rc != 0:
             raise capi.CkdError(f"host launch failed ({rc}): {self.L.ckdhost_last_error().decode()}")
         self.ctx_handle = self.L.ckdhost_context()
@@ -111,6 +121,17 @@ class Host:
             raise capi.CkdError(f"{effect}: {self.L.ckdhost_last_error().decode()}")
         return out
 
+    def demo_draw(self, out, seconds=None, delta=1.6667):
+        """Demo_Draw(pDest, time, delta) at 'seconds' (default: the time last set); -> False when the demo is over"""
+        assert self.demo
+        if seconds is not None:
+            self.time = float(seconds)
+        ptr = out if isinstance(out, int) else out.ctypes.data
+        rc = self.L.ckdhost_demo_draw(C.c_void_p(ptr), C.c_double(self.time), C.c_float(delta))
+        if rc < 0:
+            raise capi.CkdError(f"Demo_Draw: {self.L.ckdhost_last_error().decode()}")
+        return rc == 1
+
     def post(self, op, dst, src, a=0, b=0, f0=0.0, f1=0.0, u=0):
         rc = self.L.ckdhost_post(POST_IDS[op], dst.ctypes.data, src.ctypes.data if src is not None else None, a, b, C.c_float(f0), C.c_float(f1), u)
         if rc != 0:
@@ -124,4 +145,7 @@ class Host:
         self.L.ckdhost_flush()
 
     def close(self):
-        self.L.ckdhost_destroy()
+        if self.demo:
+            self.L.ckdhost_demo_destroy()
+        else:
+            self.L.ckdhost_destroy()

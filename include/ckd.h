@@ -63,6 +63,7 @@ int ckd_malloc_host(void **out_h_ptr, size_t bytes); /* pinned */
 int ckd_free_host(void *h_ptr);
 int ckd_upload(ckd_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);   /* async on the stream */
 int ckd_download(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes); /* async on the stream */
+int ckd_copy(ckd_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);       /* device to device, async on the stream (the compositor's memcpy, demo.cpp:407-449) */
 
 /* overlapped read-back for frame pipelines: the copy of a finished frame runs on the context's copy stream while the
  * compute stream already renders the next one.  slot = 0/1 selects one of two in-flight copies; ckd_frame_slot(ctx, slot)

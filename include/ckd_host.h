@@ -90,6 +90,15 @@ bool Twister_Create();
 void Twister_Destroy();
 void Twister_Draw(uint32_t *pDest, float time, float delta);
 
+// ---- demo.h:8-10: the compositor.  Demo_Create = Rocket::Launch + the five X_Create + the compositor's tracks and art
+//      (every image of demo.cpp:198-374 and shared-resources.cpp:27-34 must have been registered); Demo_Draw advances
+//      Rocket itself (CkdHost_SetTime gives the time source), renders the current part's effect and lays the part's art
+//      over it on the device, then copies the frame to pDest.  Returns false when the demo is over. -----------------------
+
+bool Demo_Create();
+void Demo_Destroy();
+bool Demo_Draw(uint32_t *pDest, float time, float delta);
+
 // ---- 2D post chain on HOST buffers (polar.h:7-17, deprecated/boxblur.h:21-41, boxblur.h:7-20, fx-blitter.h:26-33,
 //      util.h:57-122).  pDest/pSrc may alias where the reference allows it. ---------------------------------------------
 

@@ -19,6 +19,7 @@ Patch list (applied on the fly to a throw-away symlink tree in a temp dir, see S
     P3a boxblur.cpp:18         kMaxRes 2048 -> 4096 (4K scratch)
     P3b shadertoy.cpp:185      blur-map scratch (1280*720)/2 px -> kFxMapBytes
     P3c main.h:37-38           kResX/kResY (4K build only)
+    P3d demo.cpp:26            static_assert(kResX == 1280 && kResY == 720) dropped (4K build only)
 The reference's CMake build is not used (it needs SDL2/DevIL/BASS); flags per SURVEY 8c:
     g++ -std=c++20 -O3 -msse4.1 -fopenmp -fno-exceptions -DSYNC_PLAYER ; gcc -O3 -DSYNC_PLAYER for Rocket's C.
 """
@@ -37,41 +38,19 @@ OUT = os.path.join(HERE, "_ref")
 CPP_UNITS = [
     "shadertoy.cpp", "landscape.cpp", "tunnelscape.cpp", "ball.cpp", "torus-twister.cpp",
     "polar.cpp", "boxblur.cpp", "deprecated/boxblur.cpp", "fx-blitter.cpp", "util.cpp",
-    "shared-resources.cpp", "sincos-lut.cpp", "fast-cosine.cpp", "rocket.cpp",
+    "shared-resources.cpp", "sincos-lut.cpp", "fast-cosine.cpp", "rocket.cpp", "demo.cpp",
 ]
 C_UNITS = ["track.c", "device.c"]  # 3rdparty/rocket-stripped/lib
 
 CXXFLAGS = ["-std=c++20", "-O3", "-msse4.1", "-fopenmp", "-fno-exceptions", "-DSYNC_PLAYER", "-w", "-fPIC"]
 CFLAGS = ["-O3", "-DSYNC_PLAYER", "-w", "-fPIC"]
 
-# images the five X_Create() calls + Shared_Create() load (path as passed to Image_Load*, is 8-bit?)
-ASSETS = [
-    ("assets/shadertoy/nytrik-hextexture.png", False),
-    ("assets/shadertoy/nytrik-hextexture-fx.png", False),
-    ("assets/shadertoy/close-up-blur-map-1.png", False),
-    ("assets/shadertoy/close-up-blur-map-2.png", False),
-    ("assets/scape/D17.png", True),
-    ("assets/scape/C17W-edit.png", False),
-    ("assets/scape/foggradient.jpg", False),
-    ("assets/scape/tscape-D7-edit.png", True),
-    ("assets/ball/hmap_1_1k.jpg", True),
-    ("assets/ball/hmap_2_1k.jpg", True),
-    ("assets/ball/hmap_3_1k.jpg", True),
-    ("assets/ball/hmap_4_1k.jpg", True),
-    ("assets/ball/hmap_5_1k.jpg", True),
-    ("assets/ball/colormap_1k.jpg", False),
-    ("assets/ball/colormap_2_1k.jpg", False),
-    ("assets/ball/beammap_1k_1.jpg", False),
-    ("assets/ball/beammap_1k_2.jpg", False),
-    ("assets/ball/beammap_1k_3-2.jpg", False),
-    ("assets/ball/envmap3_1k.jpg", False),
-    ("assets/ball/nytrik-background_1280x720.png", False),
-    ("assets/ball/nytrik-background-2-1280x720.png", False),
-    ("assets/ball/halo.png", False),
-    ("assets/twister/hmap_2_1k.jpg", True),
-    ("assets/twister/colormap_1k.jpg", False),
-    ("assets/twister/nytrik-background_1280x720.png", False),
-]
+# images the five X_Create() calls, Shared_Create() and Demo_Create() load: the list lives with the product's asset rules
+sys.path.insert(0, os.path.dirname(HERE))
+from cookiedough_b200.assets import SPEC as _SPEC  # noqa: E402
+
+MISSING = {"assets/scape/tscape-C7W-edit.png"}  # listed in the reference's .MISSING_LARGE_BLOBS: synthesised from C17W-edit
+ASSETS = [(path, spec[2]) for path, spec in _SPEC.items() if path not in MISSING]
 
 
 def _patch(text, pattern, repl, count, what):
@@ -119,6 +98,7 @@ def make_tree(tmp, res_x, res_y):
             t = _patch(t, r"constexpr size_t kResX = 1280;", f"constexpr size_t kResX = {res_x};", 1, "P3c-x")
             return _patch(t, r"constexpr size_t kResY = 720;", f"constexpr size_t kResY = {res_y};", 1, "P3c-y")
         rewrite("main.h", p3c)
+        rewrite("demo.cpp", lambda t: _patch(t, r"static_assert\(kResX == 1280 && kResY == 720\);", "", 1, "P3d"))
     return code
 
 

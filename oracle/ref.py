@@ -61,12 +61,19 @@ class Reference:
     _instances = {}
 
     @classmethod
-    def get(cls, res_y=720, assets=None):
+    def get(cls, res_y=720, assets=None, demo=False):
+        """one instance per resolution and process (the reference keeps its state in globals).  demo=True also runs
+        Demo_Create (code/demo.cpp:138-374), which needs the compositor's images; it cannot be added afterwards."""
         if res_y not in cls._instances:
-            cls._instances[res_y] = cls(res_y, assets)
-        return cls._instances[res_y]
+            # CKD_REF_DEMO="720[,2160]": create these resolutions with the compositor even when the first caller did not ask
+            demo = demo or str(res_y) in os.environ.get("CKD_REF_DEMO", "").split(",")
+            cls._instances[res_y] = cls(res_y, assets, demo)
+        inst = cls._instances[res_y]
+        if demo and not inst.demo:
+            raise RuntimeError("the reference was already created without the compositor in this process")
+        return inst
 
-    def __init__(self, res_y=720, assets=None):
+    def __init__(self, res_y=720, assets=None, demo=False):
         self.lib = C.CDLL(lib_path(res_y))
         L = self.lib
         L.ref_last_error.restype = C.c_char_p
@@ -124,14 +131,18 @@ class Reference:
             from cookiedough_b200.assets import Assets
             assets = Assets(self.res_x, self.res_y)
         self.assets = assets
+        self.demo = bool(demo)
+        L.ref_create_demo.argtypes = [C.c_char_p]
+        L.ref_demo_draw.argtypes = [_U32P, C.c_float, C.c_float]
         self._keep = []
-        for path in assets.paths():
+        for path in assets.paths(demo=self.demo):
             arr = assets[path]
             self._keep.append(arr)
             L.ref_register_image(path.encode(), arr.ctypes.data, arr.nbytes)
-        rc = L.ref_create(DATA_DIR.encode())
+        rc = (L.ref_create_demo if self.demo else L.ref_create)(DATA_DIR.encode())
         if rc != 0:
             raise RuntimeError(f"ref_create failed ({rc}): {L.ref_last_error().decode()}")
+        self._keep = []  # Image_Load* copied the pixels
 
     # -- timeline -------------------------------------------------------------------------------
     def set_row(self, row):
@@ -154,6 +165,14 @@ class Reference:
             out = self.frame()
         rc = self.lib.ref_draw(EFFECTS[effect], _p32(out), C.c_float(self.time), C.c_float(delta))
         assert rc == 0
+        return out
+
+    def demo_draw(self, out=None, delta=1.6667):
+        """Demo_Draw(pDest, time, delta) (code/demo.cpp:469-1023) at the pinned time; it advances Rocket itself"""
+        assert self.demo
+        if out is None:
+            out = self.frame()
+        self.lib.ref_demo_draw(_p32(out), C.c_float(self.time), C.c_float(delta))
         return out
 
     def fxmap(self, i):

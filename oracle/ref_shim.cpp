@@ -32,6 +32,7 @@
 #include "tunnelscape.h"
 #include "ball.h"
 #include "torus-twister.h"
+#include "demo.h"
 
 #include <unistd.h>
 #include <string.h>
@@ -102,6 +103,8 @@ void ref_register_image(const char *path, const void *pData, size_t numBytes)
 	s_images[path] = { pData, numBytes };
 }
 
+static bool s_withDemo = false;
+
 // baseDir must contain "sync/" with the binary Rocket tracks (code/rocket.cpp:30)
 int ref_create(const char *baseDir)
 {
@@ -121,17 +124,38 @@ int ref_create(const char *baseDir)
 	if (0 == result && !Polar_Create()) result = -4;
 	if (0 == result && !FxBlitter_Create()) result = -5;
 	if (0 == result && !BoxBlur_Create()) result = -6;
-	if (0 == result && !Rocket::Launch()) result = -7;
-	if (0 == result && !Twister_Create()) result = -8;
-	if (0 == result && !Landscape_Create()) result = -9;
-	if (0 == result && !Ball_Create()) result = -10;
-	if (0 == result && !Tunnelscape_Create()) result = -11;
-	if (0 == result && !Shadertoy_Create()) result = -12;
+	if (s_withDemo)
+	{
+		// Demo_Create = Rocket::Launch + the five X_Create + the compositor's tracks and art (code/demo.cpp:138-374)
+		if (0 == result && !Demo_Create()) result = -14;
+	}
+	else
+	{
+		if (0 == result && !Rocket::Launch()) result = -7;
+		if (0 == result && !Twister_Create()) result = -8;
+		if (0 == result && !Landscape_Create()) result = -9;
+		if (0 == result && !Ball_Create()) result = -10;
+		if (0 == result && !Tunnelscape_Create()) result = -11;
+		if (0 == result && !Shadertoy_Create()) result = -12;
+	}
 
 	if (0 != chdir(cwd))
 		return -13;
 
 	return result;
+}
+
+// the same with the compositor (needs every image of code/demo.cpp:198-374 registered)
+int ref_create_demo(const char *baseDir)
+{
+	s_withDemo = true;
+	return ref_create(baseDir);
+}
+
+// Demo_Draw, code/demo.cpp:469-1023: runs Rocket::Boost() itself; returns 0 when the demo is over
+int ref_demo_draw(uint32_t *pDest, float time, float delta)
+{
+	return Demo_Draw(pDest, time, delta) ? 1 : 0;
 }
 
 void ref_set_time(double seconds)

@@ -9,6 +9,10 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 GOLDEN = os.path.join(REPO, "tests", "golden")
 
+# the reference keeps its state in globals: one instance per resolution and process.  The 720p one is created with the
+# compositor (Demo_Create) so that the Demo_Draw tests can share it with everything else.
+os.environ.setdefault("CKD_REF_DEMO", "720")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with `pytest -m gpu`")

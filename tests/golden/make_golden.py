@@ -14,6 +14,8 @@ pins are outputs of the reference itself, run here:
   golden_post_720.json      2D post chain ops on seeded buffers: sha256 of the result.
   rsqrt_table_golden.npy    the 2x1024-entry RSQRTPS table of the CPU that generated the goldens (the float effects
                             depend on it; tests install it with ckd_set_rsqrt_table before comparing).
+  golden_demo_720.json      Demo_Draw (effect + the part's layers) at rows of the real timeline that reach every part and
+                            every optional layer; synthetic assets; sha256 + crop per frame.
   tracks.json               all keys of target/directors-cut.rocket (row, value, interpolation) for the host-side
                             Rocket tests.
 
@@ -169,6 +171,43 @@ def render_cases(mode, out_path):
         json.dump(cases, f)
 
 
+# Demo_Draw (the compositor, code/demo.cpp:469-1023): rows of the real timeline that reach every part and every optional
+# layer of a part (found by scanning the tracks: shooting star, credit logo blurs and cross-fades, Cousteau blur, the three
+# Moonraker text paths, the 1995/2006 logo fades, ribbons vs. full warp, disco guys with and without strip blur, the GPU joke)
+DEMO_ROWS = [
+    0, 300, 450, 482, 508, 700, 980, 1000, 1030, 1046,            # part 2: landscape, shooting star + trail, overlay, Revision logo warp/blur
+    1104, 1300, 1500, 1712, 1900, 2060, 2092,                     # part 3: ball without / with beams
+    1996, 2008, 2020,                                             # part 1: twister
+    2100, 2200, 2364, 2510, 2700, 3064, 3108, 3130, 3142,         # part 5: plasma + credit logos (anim blend, H/V blur)
+    3250, 3600, 3716, 4000, 4180,                                 # part 8: distant spikes + title logos
+    4204, 4246, 4300, 4400, 4720, 4900,                           # part 4: tunnelscape + 1995 logos
+    4500, 4996, 5050, 5100, 5200,                                 # part 9: tunnel + 2006 logos
+    5300, 5378, 5700, 5906, 6026, 6158, 6284,                     # part 6: nautilus, Cousteau 1/2, blur
+    6290, 6418, 6628, 6656, 6684, 6700, 6728, 6778, 6808, 6812, 7074, 7332,  # part 7: close-up spikes, dirt 1/2/3, Moonraker text paths
+    7340, 7600, 7882, 8122, 8254, 8380,                           # part 10: sinuses + love prism blur, dirt
+    8500, 8900, 9300, 9390,                                       # part 11: greetings
+    9410, 9482, 9524, 9548, 9556, 9726, 9794, 9892,               # part 12: ribbons / full warp, blur
+    9924, 9950, 9972, 9980, 10142, 10300, 10310, 10354, 10396,    # part 13: disco guys (strip blur), credits, GPU joke
+]
+
+
+def demo_cases(out_path):
+    from cookiedough_b200.assets import Assets
+    from oracle import ref as oref
+
+    R = oref.Reference.get(720, Assets(1280, 720, force_synthetic=True), demo=True)
+    cases = {}
+    for row in DEMO_ROWS:
+        time_s = float(np.float32(row / oref.ROW_RATE))
+        R.set_time(time_s)
+        part = int(round(R.track("demo:Effect")))
+        frame = R.demo_draw()
+        cases[str(row)] = {"row": row, "time": time_s, "part": part, "sha256": hashlib.sha256(frame.astype("<u4").tobytes()).hexdigest(), "crop": crop_of(frame)}
+        print(f"  row {row:6d} part {part:2d} {cases[str(row)]['sha256'][:16]}")
+    with open(out_path, "w") as f:
+        json.dump(cases, f)
+
+
 def post_cases(out_path):
     from cookiedough_b200.assets import Assets
     from oracle import ref as oref
@@ -190,6 +229,8 @@ def main():
         mode, out_path = sys.argv[2], sys.argv[3]
         if mode == "post":
             post_cases(out_path)
+        elif mode == "demo":
+            demo_cases(out_path)
         else:
             render_cases(mode, out_path)
         return
@@ -197,6 +238,25 @@ def main():
     from oracle import ref as oref
     if not oref.available(720):
         sys.exit("oracle/_ref is missing: run `python oracle/build_ref.py` first")
+
+    meta = {"generator": "tests/golden/make_golden.py", "cpu": platform.processor() or platform.machine(), "assets": "synthetic (cookiedough_b200/assets.py)", "res": [1280, 720]}
+    with open("/proc/cpuinfo") as f:
+        for line in f:
+            if line.startswith("model name"):
+                meta["cpu"] = line.split(":", 1)[1].strip()
+                break
+
+    # the compositor's frames live in their own file: `make_golden.py --only demo` refreshes just those
+    with tempfile.TemporaryDirectory() as tmp:
+        part = os.path.join(tmp, "demo.json")
+        print("[demo]")
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "--child", "demo", part])
+        with open(part) as f:
+            demo = json.load(f)
+    with open(os.path.join(HERE, "golden_demo_720.json"), "w") as f:
+        json.dump({"meta": meta, "frames": demo}, f, indent=1)
+    if sys.argv[1:3] == ["--only", "demo"]:
+        return
 
     with tempfile.TemporaryDirectory() as tmp:
         parts = {}
@@ -207,12 +267,6 @@ def main():
             with open(part) as f:
                 parts[mode] = json.load(f)
 
-    meta = {"generator": "tests/golden/make_golden.py", "cpu": platform.processor() or platform.machine(), "assets": "synthetic (cookiedough_b200/assets.py)", "res": [1280, 720]}
-    with open("/proc/cpuinfo") as f:
-        for line in f:
-            if line.startswith("model name"):
-                meta["cpu"] = line.split(":", 1)[1].strip()
-                break
     with open(os.path.join(HERE, "golden_effects_720.json"), "w") as f:
         json.dump({"meta": meta, "timeline": parts["timeline"], "scenario": parts["scenario"]}, f, indent=1)
     with open(os.path.join(HERE, "golden_post_720.json"), "w") as f:
