@@ -390,52 +390,74 @@ def run_ours(args):
     return 0
 
 
+def timeline_reference(args):
+    """reference arm of the timeline workload: the reference's own Demo_Draw on the host cores, on a bounded sample"""
+    from cookiedough_b200 import sharding
+    from cookiedough_b200.assets import Assets
+    from oracle import ref as oref
+    base = {"impl": "reference", "metric": "Mpixel/s", "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+            "config": {"workload": "timeline-4k", "frames": args.frames, "res": [RES_X, RES_Y]}}
+    if not oref.available(RES_Y):
+        base["unavailable"] = "oracle/_ref (compiled reference) is not present in this checkout"
+        print(json.dumps(base))
+        return 0
+    R = oref.Reference.get(RES_Y, Assets(RES_X, RES_Y), demo=True)
+    times = sharding.timeline_times(args.frames)
+    stride = max(1, args.frames // 40)
+    sample = list(range(0, args.frames, stride))          # ~40 frames spread over every part
+    out = R.frame()
+
+    def step():
+        for i in sample:
+            R.set_time(times[i])
+            R.demo_draw(out)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = len(sample) * RES_X * RES_Y * args.steps / dt / 1e6
+    base.update({"value": value, "fps": len(sample) * args.steps / dt, "ms_per_step": 1e3 * dt / args.steps, "gpu_launches": 0,
+                 "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cpu_threads(), "kind": "reference",
+                                  "sample": f"every {stride}th frame of the {args.frames}-frame timeline ({len(sample)} frames per step) through the reference's Demo_Draw at {RES_X}x{RES_Y}"},
+                 "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
+    return 0
+
+
 def run_timeline(args):
-    """BASELINE config 5 without the compositor's art overlays (SURVEY f1 is a 'next' row): for every frame the effect
-    entry point of the part that is active at that time (demo:Effect, code/demo.cpp:507-1003) renders a 4K frame.
-    Frames shard by index (frame i -> rank i mod N); total work is fixed, so this line reports strong scaling."""
+    """BASELINE config 5: the directors-cut timeline through Demo_Draw (code/demo.cpp:469-1023) -- the part's effect plus its
+    layers, composed on the device -- at 3840x2160.  Frames shard by index (frame i -> rank i mod N, no data-path collective);
+    the total work is fixed, so this line reports strong scaling.  'value': frames stay on the device; 'e2e': every frame is
+    copied to a pinned host buffer inside the timed region (pipelined_value: with the host layer's two-deep frame pipeline)."""
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        return timeline_reference(args)
     rank, world, local, dist = dist_setup(args.gpus)
     import torch
-    from cookiedough_b200 import capi, hostapi, sharding
+    from cookiedough_b200 import hostapi, sharding
     from cookiedough_b200.assets import Assets
 
     torch.cuda.set_device(local)
     assets = Assets(RES_X, RES_Y)
-    host = hostapi.Host(RES_X, RES_Y, local, assets)
+    host = hostapi.Host(RES_X, RES_Y, local, assets, demo=True)
     ctx = host.context()
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     times = sharding.timeline_times(args.frames)
     mine = sharding.frames_for_rank(args.frames, rank, world)
-    abi_effect = {"spikey_close": ("spikey", True), "spikey_distant": ("spikey", False)}
-    h_frame = ctx.malloc_host(RES_X * RES_Y * 4)
-
-    def plan(i):
-        host.set_time(times[i])
-        part = capi.geti(host.track("demo:Effect"))
-        if part == 12 and capi.geti(host.track("demo:FullWarpTPB")) == 0:
-            return None
-        return sharding.EFFECT_OF_PART.get(part)
+    frame_bytes = RES_X * RES_Y * 4
+    h_frames = [ctx.malloc_host(frame_bytes) for _ in range(2)]
 
     def pass_device():
-        n = 0
         for i in mine:
-            eff = plan(i)
-            if eff is None:
-                continue
-            name, close = abi_effect.get(eff, (eff, None))
-            ctx.draw(name, capi.params_from_tracks(name, host.track), float(np.float32(host.time)), close=close)
-            n += 1
-        return n
+            host.demo_draw(0, times[i])          # pDest == nullptr: the composed frame stays on the device
 
     def pass_e2e():
-        n = 0
-        for i in mine:
-            eff = plan(i)
-            if eff is None:
-                continue
-            host.draw(eff, h_frame)
-            n += 1
-        return n
+        for k, i in enumerate(mine):
+            host.demo_draw(h_frames[k & 1], times[i])
 
     def barrier():
         torch.cuda.synchronize()
@@ -448,35 +470,47 @@ def run_timeline(args):
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    rendered = 0
     for _ in range(args.steps):
-        rendered = pass_device()
+        pass_device()
     ev1.record()
     torch.cuda.synchronize()
     ms = sharding.reduce_max(dist, ev0.elapsed_time(ev1), device="cuda")
     launches = ctx.launch_count() - launches0
+
     barrier()
     t0 = time.perf_counter()
     pass_e2e()
     torch.cuda.synchronize()
     e2e_s = sharding.reduce_max(dist, time.perf_counter() - t0, device="cuda")
-    if dist is not None:
-        total_rendered = torch.tensor([rendered], device="cuda", dtype=torch.int64)
-        dist.all_reduce(total_rendered)
-        rendered_all = int(total_rendered.item())
-    else:
-        rendered_all = rendered
+
+    host.set_pipelined(True)
+    barrier()
+    t0 = time.perf_counter()
+    pass_e2e()
+    host.flush()
+    e2e_pipe_s = sharding.reduce_max(dist, time.perf_counter() - t0, device="cuda")
+    host.set_pipelined(False)
+
+    # a checksum of checksums over the whole timeline: the same on any number of ranks (frames are pure functions of time)
+    local_sums = {}
+    frame = np.zeros((RES_Y, RES_X), dtype=np.uint32)
+    for i in mine[::max(1, len(mine) // 8)]:
+        host.demo_draw(frame, times[i])
+        local_sums[i] = sharding.frame_checksum(frame)
+    sums = sharding.gather_checksums(dist, local_sums, args.frames, device="cuda")
+
     if rank == 0:
-        px = rendered_all * RES_X * RES_Y
+        px = args.frames * RES_X * RES_Y
         print(json.dumps({
             "metric": "Mpixel/s", "value": px * args.steps / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "fps": rendered_all * args.steps / (ms * 1e-3), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "fps": args.frames * args.steps / (ms * 1e-3), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
-            "config": {"workload": "timeline-4k", "frames": args.frames, "frames_with_effect_layer": rendered_all, "res": [RES_X, RES_Y],
-                       "sharding": "frame i -> rank i mod N, no data-path collective", "compositor_overlays": "not rendered (SURVEY f1, next)"},
-            "e2e": {"value": px / e2e_s / 1e6, "unit": "Mpixel/s", "fps": rendered_all / e2e_s, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": rendered_all * RES_X * RES_Y * 4},
-            "gpu_launches": int(launches)}))
+            "config": {"workload": "timeline-4k", "frames": args.frames, "res": [RES_X, RES_Y], "api": "Demo_Draw (effect + the part's layers, composed on the device)",
+                       "sharding": "frame i -> rank i mod N, no data-path collective",
+                       "assets": "procedural stand-ins" if assets.synthetic else "reference art (oracle/_ref/assets.npz), layers nearest-upscaled x3"},
+            "e2e": {"value": px / e2e_s / 1e6, "unit": "Mpixel/s", "fps": args.frames / e2e_s, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": args.frames * frame_bytes, "pipelined_value": px / e2e_pipe_s / 1e6, "pipelined_fps": args.frames / e2e_pipe_s},
+            "gpu_launches": int(launches), "frame_checksums_crc32": {str(i): c for i, c in enumerate(sums) if c}}))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -491,13 +525,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="effect-suite-4k", choices=["effect-suite-4k", "timeline-4k"],
-                    help="timeline-4k: the 600-frame directors-cut timeline (effect layer of each part, BASELINE config 5), frame i -> rank i mod N (strong scaling)")
+                    help="timeline-4k: the 600-frame directors-cut timeline through Demo_Draw (BASELINE config 5), frame i -> rank i mod N (strong scaling)")
     ap.add_argument("--frames", type=int, default=600)
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
     if args.workload == "timeline-4k":
         return run_timeline(args)
+    if args.impl == "reference":
+        return run_reference(args)
     return run_ours(args)
 
 

@@ -339,6 +339,8 @@ static void Finish(int rc, uint32_t *pDest, const char *what)
 {
 	if (!Check(rc, what) || nullptr != s_composeTarget)
 		return;
+	if (nullptr == pDest)
+		return; // extension: a null pDest leaves the finished frame on the device (ckd_frame / ckd_frame_slot)
 	const size_t bytes = size_t(ckd_res_x(s_ctx))*ckd_res_y(s_ctx)*sizeof(uint32_t);
 	if (s_pipelined)
 	{

@@ -40,6 +40,9 @@ void CkdHost_RegisterImage(const char *path, const void *pixels, int width, int 
 void CkdHost_SetPipelined(bool enabled);
 void CkdHost_Flush();
 
+// Extension to every X_Draw / Demo_Draw below: pDest == nullptr renders the frame and leaves it on the device
+// (ckd_frame(CkdHost_Context()), or the current ckd_frame_slot while pipelined) instead of copying it to the host.
+
 // main.h:49 / main.cpp:175-180
 void SetLastError(const std::string &description);
 const std::string &CkdHost_GetLastError();
