@@ -787,7 +787,7 @@ static int OldBlurPass(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, un
 		const int variant = (vert ? 4 : 0) | (inPlace ? 2 : 0) | (s.subEdges ? 1 : 0);
 		// The serial walk runs one warp per 8 lines; once that alone puts three warps on every SM (vertical passes at 4K) it holds
 		// its own against the scan up to medium kernels.  Measured on B200, see profiles/r01_notes.md.
-		const unsigned blockedFrom = (numLines/8 >= 3u*unsigned(ctx->numSMs)) ? 20 : 8;
+		const unsigned blockedFrom = (numLines/8 >= 3u*unsigned(ctx->numSMs)) ? 24 : 8;
 		if (inPlace && s.kernelMedian >= blockedFrom)
 		{
 			if (vert) err = s.subEdges ? LaunchBlocked<true, true>(ctx, pDest, numLines, lineLen, pitch, s) : LaunchBlocked<true, false>(ctx, pDest, numLines, lineLen, pitch, s);

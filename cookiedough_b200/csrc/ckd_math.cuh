@@ -62,28 +62,56 @@ __device__ __forceinline__ float smoothstepf(float a, float b, float t)         
 // The 2049-entry table is staged in shared memory as 2048 (LUT[i], LUT[i+1]-LUT[i]) pairs: one 8-byte LDS per call and the
 // difference (the same IEEE subtraction the reference performs per call) is paid once at start-up.
 
-__device__ __forceinline__ float lutcosf(const float2 *__restrict__ lut2, float angle)
+// The table is addressed through its 32-bit shared-window address (CosLut) and read with ld.shared: a generic float2* makes
+// the compiler rebuild the shared base (S2UR + UMOV + ULEA) next to every lookup, and these kernels are issue bound.
+typedef unsigned CosLut;
+
+__device__ __forceinline__ float lutcosf(CosLut lut, float angle)
 {
 	angle = fabsf(angle);
 	angle *= (1.f/k2PI)*2048; // constant folds in float exactly like the reference's (1.f/k2PI)*kCosTabSize
 	// int(angle) & 2047 with cvttss2si semantics: angle is >= 0 or NaN here, so only the upper bound can overflow
-	// (-> 0x80000000, index 0); NaN converts to 0 on both machines.  (An F2I-free variant built on the 2^23 rounding
-	// trick was measured slower: these kernels are issue bound, not XU bound -- profiles/r01_notes.md.)
-	const int index = (angle < 2147483648.f) ? (__float2int_rz(angle) & 2047) : 0;
-	const float2 pair = lut2[index];           // (LUT[i], LUT[i+1] - LUT[i])
+	// (-> 0x80000000, index 0); NaN converts to 0 on both machines.  The unsigned conversion is exact below 2^32 and saturates
+	// above: bit 31 of it is set exactly when cvttss2si overflows, and its sign smear clears the index -- one shift instead of
+	// a compare and a select.  (An F2I-free variant built on the 2^23 rounding trick was measured slower: these kernels are
+	// issue bound, not XU bound -- profiles/r01_notes.md.)
+	const unsigned u = __float2uint_rz(angle);
+	const unsigned index = u & 2047u & ~unsigned(int(u) >> 31);
+	float2 pair;                               // (LUT[i], LUT[i+1] - LUT[i])
+	asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pair.x), "=f"(pair.y) : "r"(lut + index*8u));
 	return pair.x + pair.y*(angle - truncf(angle)); // lerpf(a, b, t) = a + (b-a)*t, Math.h:52-56
 }
 
 // ARRESTED_DEV_LEGACY (main.h:9): lutsinf(a) = lutcosf(a + pi/2)
+__device__ __forceinline__ float lutsinf(CosLut lut, float angle)
+{
+	return lutcosf(lut, angle + kPI*0.5f);
+}
+
+// the same on the table where it lies in global memory (TapeWarp32: two lookups per pixel, not worth staging)
+__device__ __forceinline__ float lutcosf(const float2 *__restrict__ lut2, float angle)
+{
+	angle = fabsf(angle);
+	angle *= (1.f/k2PI)*2048;
+	const unsigned u = __float2uint_rz(angle);
+	const float2 pair = __ldg(lut2 + (u & 2047u & ~unsigned(int(u) >> 31)));
+	return pair.x + pair.y*(angle - truncf(angle));
+}
 __device__ __forceinline__ float lutsinf(const float2 *__restrict__ lut2, float angle)
 {
 	return lutcosf(lut2, angle + kPI*0.5f);
 }
 
-__device__ __forceinline__ void stage_cos_lut(float2 *s_lut2, const float2 *__restrict__ g_lut2)
+// copies the table into shared memory (all threads of the CTA), synchronises, and returns its handle.  The handle is produced
+// by a volatile asm *after* the barrier, so no lookup (a pure asm that depends on it) can be scheduled above the barrier.
+__device__ __forceinline__ CosLut stage_cos_lut(float2 *s_lut2, const float2 *__restrict__ g_lut2)
 {
 	for (int i = threadIdx.y*blockDim.x + threadIdx.x; i < 2048; i += blockDim.x*blockDim.y)
 		s_lut2[i] = g_lut2[i];
+	__syncthreads();
+	CosLut lut;
+	asm volatile("mov.u32 %0, %1;" : "=r"(lut) : "r"(unsigned(__cvta_generic_to_shared(s_lut2))) : "memory");
+	return lut;
 }
 
 // ---- RSQRTPS emulation (shadertoy-util.h:89,260,265) --------------------------------------------------------------
@@ -353,21 +381,21 @@ __device__ __forceinline__ void fast_norm3(const RsqrtTab tab, vec3 &v)
 __device__ __forceinline__ float fast_len3(const vec3 &v) { return sqrtf(dp_ps3(v, v)); }
 
 // Shadertoy::rotX/rotY/rotZ, shadertoy-util.h:31-59
-__device__ __forceinline__ void rotX(const float2 *lut, float angle, float &Y, float &Z)
+__device__ __forceinline__ void rotX(CosLut lut, float angle, float &Y, float &Z)
 {
 	const float cosine = lutcosf(lut, angle), sine = lutsinf(lut, angle);
 	const float rY = cosine*Y + -sine*Z;
 	const float rZ = sine*Y + cosine*Z;
 	Y = rY; Z = rZ;
 }
-__device__ __forceinline__ void rotY(const float2 *lut, float angle, float &X, float &Z)
+__device__ __forceinline__ void rotY(CosLut lut, float angle, float &X, float &Z)
 {
 	const float cosine = lutcosf(lut, angle), sine = lutsinf(lut, angle);
 	const float rX = cosine*X + sine*Z;
 	const float rZ = -sine*X + cosine*Z;
 	X = rX; Z = rZ;
 }
-__device__ __forceinline__ void rotZ(const float2 *lut, float angle, float &X, float &Y)
+__device__ __forceinline__ void rotZ(CosLut lut, float angle, float &X, float &Y)
 {
 	const float cosine = lutcosf(lut, angle), sine = lutsinf(lut, angle);
 	const float rX = cosine*X + sine*Y;

@@ -44,7 +44,7 @@ __device__ __forceinline__ float vlerp(float a, float b, float f) { return a + f
 
 struct Env
 {
-	const float2 *lut;   // shared-memory cosine LUT
+	CosLut lut;          // shared-memory cosine LUT
 	RsqrtTab rsqrt;
 	FrameGeom geom;
 };
@@ -61,7 +61,7 @@ struct PlasmaFrame
 	float gamma;
 };
 
-__device__ __forceinline__ float fPlasma(const float2 *lut, float px, float py, float pz, float time)
+__device__ __forceinline__ float fPlasma(CosLut lut, float px, float py, float pz, float time)
 {
 	const float sine = 0.2f*lutsinf(lut, px-py);
 	const float fX = sine + lutcosf(lut, px*0.33f);
@@ -119,7 +119,7 @@ struct NautilusFrame
 	Rot roll;
 };
 
-__device__ __forceinline__ float fNautilus(const float2 *lut, const NautilusFrame &f, float px, float py, float pz)
+__device__ __forceinline__ float fNautilus(CosLut lut, const NautilusFrame &f, float px, float py, float pz)
 {
 	const float cosX = lutcosf(lut, lutcosf(lut, px + f.gx)*px - lutcosf(lut, py + f.gy)*py);
 	const float cosY = lutcosf(lut, pz*0.33f*px - f.gz*py);
@@ -198,7 +198,7 @@ struct SpikeyFrame
 };
 
 template <bool GOLDEN_ANGLE>
-__device__ __forceinline__ float fSpikey(const float2 *lut, const SpikeyFrame &f, float px, float py, float pz)
+__device__ __forceinline__ float fSpikey(CosLut lut, const SpikeyFrame &f, float px, float py, float pz)
 {
 	// fSpikey1 (kGoldenAngle) / fSpikey2 (kGoldenRatio), shadertoy.cpp:418-430
 	constexpr float scale = (GOLDEN_ANGLE ? kGoldenAngle : kGoldenRatio)*0.1f;
@@ -351,7 +351,7 @@ struct SinusesFrame
 	float specPow, gamma, offsX;
 };
 
-__device__ __forceinline__ float fSinMap(const float2 *lut, float px0, float py0, float pZ)
+__device__ __forceinline__ float fSinMap(CosLut lut, float px0, float py0, float pZ)
 {
 	const float zMod = pZ*0.314f;
 	const float pathCos = lutcosf(lut, zMod);
@@ -429,7 +429,7 @@ struct LauraFrame
 	Rot yaw, pitch, roll;
 };
 
-__device__ __forceinline__ float fLaura(const float2 *lut, float px, float py, float pz)
+__device__ __forceinline__ float fLaura(CosLut lut, float px, float py, float pz)
 {
 	return lutcosf(lut, px)+lutcosf(lut, py)+lutcosf(lut, pz) + 1.f;
 }
@@ -536,12 +536,11 @@ __global__ void __launch_bounds__(kTileX*kTileY) raymarch_kernel(const Effect ef
 	const float2 *__restrict__ g_lut2, const RsqrtTab rsqrt, const TileQueue queue)
 {
 	__shared__ float2 s_lut2[2048];
-	stage_cos_lut(s_lut2, g_lut2);
 	if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0)
 		*queue.nextCounter = 0;
-	__syncthreads();
+	const CosLut lut = stage_cos_lut(s_lut2, g_lut2);
 
-	Env env = { s_lut2, rsqrt, geom };
+	Env env = { lut, rsqrt, geom };
 
 	unsigned iX, iY;
 	while (next_tile(queue, iX, iY))
@@ -578,10 +577,9 @@ __global__ void __launch_bounds__(kTileX*kTileY) tunnel_kernel(const TunnelFrame
 	const uint32_t *__restrict__ tex, const uint32_t *__restrict__ texGlow, const FrameGeom geom, const float2 *__restrict__ g_lut2, const RsqrtTab rsqrt, const TileQueue queue)
 {
 	__shared__ float2 s_lut2[2048];
-	stage_cos_lut(s_lut2, g_lut2);
 	if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0)
 		*queue.nextCounter = 0;
-	__syncthreads();
+	const CosLut lut = stage_cos_lut(s_lut2, g_lut2);
 
 	unsigned iX, iY;
 	while (next_tile(queue, iX, iY))
@@ -597,7 +595,7 @@ __global__ void __launch_bounds__(kTileX*kTileY) tunnel_kernel(const TunnelFrame
 		fast_norm3(rsqrt, dir);
 
 		float A = dir.x*dir.x + dir.y*dir.y;
-		A += f.flowerScale*lutcosf(s_lut2, atan2f_ref(dir.y, dir.x)*f.flowerFreq + f.flowerPhase);
+		A += f.flowerScale*lutcosf(lut, atan2f_ref(dir.y, dir.x)*f.flowerFreq + f.flowerPhase);
 
 		const float absX = fabsf(dir.x), absY = fabsf(dir.y);
 		const float box = absX > absY ? absX : absY;
