@@ -873,79 +873,138 @@ __device__ __forceinline__ unsigned scale_fp22(float value)
 	return unsigned(__float2ll_rz(scaled));
 }
 
-// One (line, channel) per thread.  Element i of a line lives at base + line*lineStride + i*stepStride (in pixels); the
-// reference reads up to 2 elements past the end of a line (boxblur.cpp:171,185), which in its (transposed) layout are the
-// first elements of the next line, or whatever follows the buffer for the last line: 'numLines' bounds that to zero here.
-__global__ void __launch_bounds__(128) new_blur_kernel(uint8_t *pDest, const uint8_t *pSrc, unsigned numLines, unsigned lineLen,
-	size_t srcLineStride, size_t srcStepStride, size_t dstLineStride, size_t dstStepStride, NewBlurSetup s)
+// The sums are plain 32-bit integers without saturation, so the running window of a line is a difference of prefix sums:
+// with E(m) = px[m] + (((px[m+1] - px[m])*alpha16) >> 16) (iAdd / iSub, boxblur.cpp:37-61) and P(n) = E(0) + ... + E(n-1), the
+// accumulator in front of output k is
+//     iSum0 + P(iSpan + 1 + min(k, len - iSpan)) - P(iSpan + 1) - P(max(k - iSpan, 0)),
+// iSum0 = px[0] + ... + px[iSpan-1] + ((px[iSpan]*alpha16) >> 16) (boxblur.cpp:150-157).  One CTA owns one line: the line is
+// staged in shared memory with coalesced loads, every thread folds a chunk of consecutive E into a local prefix, a block
+// scan offsets the chunks, and the outputs -- two 16-byte prefix reads, the 10:22 scale, the pack -- go out coalesced.
+// Lines are contiguous (vertical passes run on a transposed copy, like the reference's own Transpose32 round trip,
+// boxblur.cpp:215-299), so the two elements the reference reads past the end of a line (boxblur.cpp:171,185) are simply the
+// next two elements of the buffer; past the end of the buffer they read as 0.  Exact: integer sums in any order.
+constexpr int kNewBlurThreads = 256;
+
+__global__ void __launch_bounds__(kNewBlurThreads) new_blur_line_kernel(uint32_t *__restrict__ pDest, const uint32_t *__restrict__ pSrc, unsigned numLines, unsigned len, NewBlurSetup s)
 {
-	const unsigned t = blockIdx.x*blockDim.x + threadIdx.x;
-	const unsigned line = t >> 2, chan = t & 3;
-	if (line >= numLines)
-		return;
+	extern __shared__ __align__(16) uint8_t s_mem[];
+	// element m of either array lives at slot m + (m >> 4): a thread walks consecutive elements, neighbouring threads start a
+	// chunk apart, and the extra slot per 16 elements keeps their accesses on different banks
+	auto slot = [](unsigned m) -> unsigned { return m + (m >> 4); };
+	int4 *s_P = reinterpret_cast<int4 *>(s_mem);                          // P(0..len+1)
+	uint32_t *s_px = reinterpret_cast<uint32_t *>(s_P + slot(len + 2) + 1); // px[0..len+1]
+	__shared__ int4 s_warpTotals[kNewBlurThreads/32];
+	__shared__ int s_first[4];                                            // px[0] + ... + px[iSpan-1] per channel
 
-	auto Read = [&](unsigned i) -> int
+	const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const unsigned line = blockIdx.x;
+	const size_t total = size_t(numLines)*len, base = size_t(line)*len;
+
+	if (tid < 4) s_first[tid] = 0;
+	for (unsigned i = tid; i < len + 2; i += kNewBlurThreads)
+		s_px[slot(i)] = (base + i < total) ? pSrc[base + i] : 0u;
+	__syncthreads();
+
+	// chunk of consecutive elements per thread: E(m) for m in [m0, m1), local exclusive prefix into s_P
+	const unsigned perThread = (len + 1 + kNewBlurThreads - 1)/kNewBlurThreads; // E(0..len) -> P(0..len+1)
+	const unsigned m0 = min(tid*perThread, len + 1), m1 = min(m0 + perThread, len + 1);
+	int4 run = make_int4(0, 0, 0, 0), first = make_int4(0, 0, 0, 0);
+	uint32_t A = (m0 < m1) ? s_px[slot(m0)] : 0u;
+	for (unsigned m = m0; m < m1; ++m)
 	{
-		unsigned l = line;
-		if (i >= lineLen) { i -= lineLen; ++l; }
-		if (l >= numLines) return 0;
-		return int(pSrc[(size_t(l)*srcLineStride + size_t(i)*srcStepStride)*4 + chan]);
-	};
-
-	uint8_t *dst = pDest + (size_t(line)*dstLineStride)*4 + chan;
-	const size_t dstStep = dstStepStride*4;
-	size_t writeIdx = 0;
-
-	int iSum = 0;
-	unsigned tail = 0, head = 0;
-
-	// calculate sum at first pixel (median), boxblur.cpp:150-157
-	for (unsigned i = 0; i < s.iSpan; ++i)
-		iSum += Read(head++);
-	iSum += (Read(head)*s.iAlpha) >> 16;
-
-	// iAdd / iSub, boxblur.cpp:37-61: sum +/-= A + (((B-A)*alpha16) >> 16), arithmetic shift
-	int headA = Read(head+1), headB;
-	for (unsigned i = 0; i < s.iSpan; ++i)
+		const uint32_t B = s_px[slot(m + 1)];
+		s_P[slot(m)] = run;
+		const int a0 = int(A & 0xff), a1 = int((A >> 8) & 0xff), a2 = int((A >> 16) & 0xff), a3 = int(A >> 24);
+		const int b0 = int(B & 0xff), b1 = int((B >> 8) & 0xff), b2 = int((B >> 16) & 0xff), b3 = int(B >> 24);
+		run.x += a0 + (((b0 - a0)*s.iAlpha) >> 16);
+		run.y += a1 + (((b1 - a1)*s.iAlpha) >> 16);
+		run.z += a2 + (((b2 - a2)*s.iAlpha) >> 16);
+		run.w += a3 + (((b3 - a3)*s.iAlpha) >> 16);
+		if (m < s.iSpan) { first.x += a0; first.y += a1; first.z += a2; first.w += a3; }
+		A = B;
+	}
+	if (m0 < s.iSpan && m0 < m1)
 	{
-		dst[writeIdx] = uint8_t(new_div_pack(iSum, scale_fp22(s.halfScale + float(i)*s.dScale)));
-		writeIdx += dstStep;
-		headB = Read(head+2);
-		iSum += headA + (((headB-headA)*s.iAlpha) >> 16);
-		headA = headB;
-		++head;
+		atomicAdd(&s_first[0], first.x); atomicAdd(&s_first[1], first.y); atomicAdd(&s_first[2], first.z); atomicAdd(&s_first[3], first.w);
 	}
 
-	int tailA = Read(tail), tailB;
-	const unsigned fullLen = lineLen - s.iSpan*2;
-	for (unsigned i = 0; i < fullLen; ++i)
+	// block exclusive scan of the chunk totals
+	int4 incl = run;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
 	{
-		dst[writeIdx] = uint8_t(new_div_pack(iSum, s.iScale));
-		writeIdx += dstStep;
-		headB = Read(head+2);
-		iSum += headA + (((headB-headA)*s.iAlpha) >> 16);
-		headA = headB;
-		++head;
-		tailB = Read(tail+1);
-		iSum -= tailA + (((tailB-tailA)*s.iAlpha) >> 16);
-		tailA = tailB;
-		++tail;
+		const int x = __shfl_up_sync(0xffffffffu, incl.x, d), y = __shfl_up_sync(0xffffffffu, incl.y, d), z = __shfl_up_sync(0xffffffffu, incl.z, d), w = __shfl_up_sync(0xffffffffu, incl.w, d);
+		if (lane >= unsigned(d)) { incl.x += x; incl.y += y; incl.z += z; incl.w += w; }
 	}
-
-	for (unsigned i = s.iSpan; i > 0; --i)
+	if (lane == 31) s_warpTotals[warp] = incl;
+	__syncthreads();
+	int4 offset = make_int4(incl.x - run.x, incl.y - run.y, incl.z - run.z, incl.w - run.w);
+	for (unsigned w = 0; w < warp; ++w)
 	{
-		dst[writeIdx] = uint8_t(new_div_pack(iSum, scale_fp22(s.halfScale + float(i-1)*s.dScale)));
-		writeIdx += dstStep;
-		tailB = Read(tail+1);
-		iSum -= tailA + (((tailB-tailA)*s.iAlpha) >> 16);
-		tailA = tailB;
-		++tail;
+		const int4 t = s_warpTotals[w];
+		offset.x += t.x; offset.y += t.y; offset.z += t.z; offset.w += t.w;
+	}
+	for (unsigned m = m0; m < m1; ++m)
+	{
+		int4 v = s_P[slot(m)];
+		v.x += offset.x; v.y += offset.y; v.z += offset.z; v.w += offset.w;
+		s_P[slot(m)] = v;
+	}
+	if (m1 == len + 1 && m0 < m1) // the thread that owns the last E also provides P(len + 1)
+		s_P[slot(len + 1)] = make_int4(offset.x + run.x, offset.y + run.y, offset.z + run.z, offset.w + run.w);
+	__syncthreads();
+
+	// outputs
+	const uint32_t pivot = s_px[slot(s.iSpan)];
+	int4 sum0 = s_P[slot(s.iSpan + 1)]; // subtracted below
+	sum0.x = s_first[0] + ((int(pivot & 0xff)*s.iAlpha) >> 16) - sum0.x;
+	sum0.y = s_first[1] + ((int((pivot >> 8) & 0xff)*s.iAlpha) >> 16) - sum0.y;
+	sum0.z = s_first[2] + ((int((pivot >> 16) & 0xff)*s.iAlpha) >> 16) - sum0.z;
+	sum0.w = s_first[3] + ((int(pivot >> 24)*s.iAlpha) >> 16) - sum0.w;
+
+	for (unsigned k = tid; k < len; k += kNewBlurThreads)
+	{
+		const int4 hi = s_P[slot(s.iSpan + 1 + min(k, len - s.iSpan))];
+		const int4 lo = s_P[slot((k > s.iSpan) ? k - s.iSpan : 0)];
+		unsigned scale = s.iScale;
+		if (k < s.iSpan) scale = scale_fp22(s.halfScale + float(k)*s.dScale);                        // boxblur.cpp:160-174
+		else if (k >= len - s.iSpan) scale = scale_fp22(s.halfScale + float(len - 1 - k)*s.dScale);  // boxblur.cpp:196-207
+		const uint32_t out = new_div_pack(sum0.x + hi.x - lo.x, scale) | (new_div_pack(sum0.y + hi.y - lo.y, scale) << 8)
+			| (new_div_pack(sum0.z + hi.z - lo.z, scale) << 16) | (new_div_pack(sum0.w + hi.w - lo.w, scale) << 24);
+		pDest[base + k] = out;
 	}
 }
 
-// HorzBlur32, boxblur.cpp:87-212, on lines described by strides (natural layout, no transposes)
-static int NewBlurLines(ckd_ctx *ctx, uint32_t *d_dest, uint32_t *d_scratch, const uint32_t *d_src,
-	unsigned numLines, unsigned lineLen, size_t lineStride, size_t stepStride, float strength, float gain, unsigned numPasses)
+// Transpose32, boxblur.cpp:215-268: pDest[x*yRes + y] = pSrc[y*xRes + x]
+__global__ void __launch_bounds__(256) transpose32_kernel(uint32_t *__restrict__ pDest, const uint32_t *__restrict__ pSrc, unsigned xRes, unsigned yRes)
+{
+	__shared__ uint32_t s_tile[32][33];
+	const unsigned x0 = blockIdx.x*32, y0 = blockIdx.y*32;
+	for (unsigned j = threadIdx.y; j < 32; j += 8)
+	{
+		const unsigned x = x0 + threadIdx.x, y = y0 + j;
+		if (x < xRes && y < yRes) s_tile[j][threadIdx.x] = pSrc[size_t(y)*xRes + x];
+	}
+	__syncthreads();
+	for (unsigned j = threadIdx.y; j < 32; j += 8)
+	{
+		const unsigned y = y0 + threadIdx.x, x = x0 + j;
+		if (x < xRes && y < yRes) pDest[size_t(x)*yRes + y] = s_tile[threadIdx.x][j];
+	}
+}
+
+static int Transpose32(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned xRes, unsigned yRes)
+{
+	ckd_prof_begin(ctx, "transpose32", 8.0*xRes*yRes);
+	transpose32_kernel<<<dim3(ckd_div_up(xRes, 32), ckd_div_up(yRes, 32)), dim3(32, 8), 0, ctx->stream>>>(d_dest, d_src, xRes, yRes);
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}
+
+// HorzBlur32, boxblur.cpp:87-212, numPasses passes over contiguous lines, ping-pong between two buffers.
+// d_a receives pass 0, d_b pass 1, ...; returns the buffer the last pass wrote.
+static int NewBlurPasses(ckd_ctx *ctx, uint32_t *d_a, uint32_t *d_b, const uint32_t *d_src, unsigned numLines, unsigned lineLen,
+	float strength, float gain, unsigned numPasses, const char *what, uint32_t **d_result)
 {
 	CKD_REQUIRE(numPasses > 0, "numPasses must be > 0");
 
@@ -968,21 +1027,26 @@ static int NewBlurLines(ckd_ctx *ctx, uint32_t *d_dest, uint32_t *d_scratch, con
 	s.halfScale = scale*0.5f;
 	s.dScale = s.halfScale/float(iSpan);
 
-	const uint32_t *pRead = d_src;
-	uint32_t *pDest = d_dest, *pScratch = d_scratch;
-	if (0 == (numPasses & 1))
-		std::swap(pDest, pScratch);
+	const size_t slots = size_t(lineLen + 2) + ((lineLen + 2) >> 4) + 2;
+	const size_t smem = slots*(sizeof(int4) + sizeof(uint32_t));
+	CKD_REQUIRE(smem <= 200*1024, "line too long for the blur's shared-memory staging");
+	if (!ctx->newBlurAttrSet)
+	{
+		CKD_CUDA(cudaFuncSetAttribute(new_blur_line_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024));
+		ctx->newBlurAttrSet = true;
+	}
 
-	const unsigned threads = numLines*4;
+	const uint32_t *pRead = d_src;
+	uint32_t *pWrite = d_a, *pOther = d_b;
 	for (unsigned iPass = 0; iPass < numPasses; ++iPass)
 	{
-		ckd_prof_begin(ctx, stepStride == 1 ? "new_blur_h" : "new_blur_v", 8.0*numLines*lineLen);
-		new_blur_kernel<<<ckd_div_up(threads, 128), 128, 0, ctx->stream>>>(reinterpret_cast<uint8_t *>(pDest), reinterpret_cast<const uint8_t *>(pRead),
-			numLines, lineLen, lineStride, stepStride, lineStride, stepStride, s);
+		ckd_prof_begin(ctx, what, 8.0*numLines*lineLen);
+		new_blur_line_kernel<<<numLines, kNewBlurThreads, smem, ctx->stream>>>(pWrite, pRead, numLines, lineLen, s);
 		CKD_CHECK_LAUNCH(ctx);
-		pRead = pDest;
-		std::swap(pDest, pScratch);
+		pRead = pWrite;
+		std::swap(pWrite, pOther);
 	}
+	*d_result = pOther; // after the swap: the buffer the last pass wrote
 	return CKD_OK;
 }
 
@@ -990,22 +1054,38 @@ extern "C" int ckd_new_blur_h(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_
 {
 	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
 	CKD_REQUIRE(size_t(x_res)*y_res <= size_t(ctx->resX)*ctx->resY, "image larger than the context's scratch buffers");
-	return NewBlurLines(ctx, d_dest, ctx->d_scratch[0], d_src, y_res, x_res, x_res, 1, strength, gain, num_passes);
+	// BoxBlur_Horz32, boxblur.cpp:270-279.  The last pass lands in d_dest; a pass never writes the buffer it reads (lines read
+	// two elements into their successor), so an in-place call goes through both scratch images.
+	uint32_t *d_result = nullptr;
+	if (d_dest == d_src)
+	{
+		CKD_TRY(NewBlurPasses(ctx, ctx->d_scratch[0], ctx->d_scratch[1], d_src, y_res, x_res, strength, gain, num_passes, "new_blur_h", &d_result));
+		return ckd_copy(ctx, d_dest, d_result, size_t(x_res)*y_res*4);
+	}
+	uint32_t *d_first = (num_passes & 1) ? d_dest : ctx->d_scratch[0], *d_second = (num_passes & 1) ? ctx->d_scratch[0] : d_dest;
+	return NewBlurPasses(ctx, d_first, d_second, d_src, y_res, x_res, strength, gain, num_passes, "new_blur_h", &d_result);
 }
 
 extern "C" int ckd_new_blur_v(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength, float gain, unsigned num_passes)
 {
 	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
 	CKD_REQUIRE(size_t(x_res)*y_res <= size_t(ctx->resX)*ctx->resY, "image larger than the context's scratch buffers");
-	// BoxBlur_Vert32, boxblur.cpp:281-299: lines are columns (length yRes), radius derives from yRes
-	return NewBlurLines(ctx, d_dest, ctx->d_scratch[0], d_src, x_res, y_res, 1, x_res, strength, gain, num_passes);
+	// BoxBlur_Vert32, boxblur.cpp:281-299: transpose, blur the columns as lines (length yRes, the radius derives from yRes), transpose back
+	uint32_t *d_result = nullptr;
+	CKD_TRY(Transpose32(ctx, ctx->d_scratch[1], d_src, x_res, y_res));
+	CKD_TRY(NewBlurPasses(ctx, ctx->d_scratch[0], ctx->d_scratch[1], ctx->d_scratch[1], x_res, y_res, strength, gain, num_passes, "new_blur_v", &d_result));
+	return Transpose32(ctx, d_dest, d_result, y_res, x_res);
 }
 
 extern "C" int ckd_new_blur(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength, float gain, unsigned num_passes)
 {
 	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
 	CKD_REQUIRE(size_t(x_res)*y_res <= size_t(ctx->resX)*ctx->resY, "image larger than the context's scratch buffers");
-	// BoxBlur_32, boxblur.cpp:301-318
-	CKD_TRY(NewBlurLines(ctx, ctx->d_scratch[1], ctx->d_scratch[0], d_src, y_res, x_res, x_res, 1, strength, gain, num_passes));
-	return NewBlurLines(ctx, d_dest, ctx->d_scratch[0], ctx->d_scratch[1], x_res, y_res, 1, x_res, strength, gain, num_passes);
+	// BoxBlur_32, boxblur.cpp:301-318: rows, then columns
+	uint32_t *d_rows = nullptr, *d_cols = nullptr;
+	CKD_TRY(NewBlurPasses(ctx, ctx->d_scratch[0], ctx->d_scratch[1], d_src, y_res, x_res, strength, gain, num_passes, "new_blur_h", &d_rows));
+	uint32_t *d_t = (d_rows == ctx->d_scratch[0]) ? ctx->d_scratch[1] : ctx->d_scratch[0];
+	CKD_TRY(Transpose32(ctx, d_t, d_rows, x_res, y_res));
+	CKD_TRY(NewBlurPasses(ctx, d_rows, d_t, d_t, x_res, y_res, strength, gain, num_passes, "new_blur_v", &d_cols));
+	return Transpose32(ctx, d_dest, d_cols, y_res, x_res);
 }

@@ -29,6 +29,7 @@ struct ckd_ctx {
 	cudaStream_t copyStream = nullptr;             // read-back overlapped with rendering (ckd_download_overlapped)
 	cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
 	bool copyPending[2] = { false, false };
+	bool newBlurAttrSet = false;                   // opt-in shared-memory size set for new_blur_line_kernel on this device
 	bool blurAttrSet[64] = {};                     // opt-in shared-memory size set for the staged blur variants on this device
 	unsigned long long launches = 0;
 
