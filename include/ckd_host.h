@@ -43,6 +43,15 @@ void CkdHost_Flush();
 // Extension to every X_Draw / Demo_Draw below: pDest == nullptr renders the frame and leaves it on the device
 // (ckd_frame(CkdHost_Context()), or the current ckd_frame_slot while pipelined) instead of copying it to the host.
 
+// ---- frame sink (replaces Display::Update, display.cpp:66-82, for headless rendering): a raw stream file
+//      ("CKDF" header + numFrames ARGB8888 frames) fed through a ring of host buffers by a writer thread.  Acquire a buffer,
+//      let X_Draw / Demo_Draw fill it, commit it with its frame index; frames land by index, so several processes (one per
+//      GPU) can share one file: one opens it with create = true, the others attach. -----------------------------------------
+bool CkdSink_Open(const char *path, unsigned resX, unsigned resY, unsigned numFrames, unsigned ringFrames, bool pinned, bool create);
+uint32_t *CkdSink_Acquire();
+bool CkdSink_Commit(uint32_t *frame, unsigned frameIndex);
+bool CkdSink_Close();
+
 // main.h:49 / main.cpp:175-180
 void SetLastError(const std::string &description);
 const std::string &CkdHost_GetLastError();

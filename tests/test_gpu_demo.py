@@ -117,3 +117,27 @@ def test_demo_draw_4k_child_process():
     worst = [line for line in r.stdout.splitlines() if line.startswith("worst exact %")]
     assert worst and float(worst[-1].split()[-1]) >= 99.5, r.stdout[-3000:]
     assert all(int(line.split("max")[1].split()[0]) <= 2 for line in r.stdout.splitlines() if line.startswith("row")), r.stdout[-3000:]
+
+
+def test_render_demo_stream_matches_demo_draw(tmp_path):
+    """tools/render_demo.py (f4: device frame -> pinned ring -> writer thread) writes the frames Demo_Draw produces"""
+    from oracle import ref as oref
+    if not oref.available(720):
+        pytest.skip("oracle/_ref not built")
+    from cookiedough_b200 import hostapi, sharding, sink
+    from cookiedough_b200.assets import Assets
+    path = tmp_path / "demo.ckdf"
+    frames = 24
+    r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "render_demo.py"), "--out", str(path), "--frames", str(frames), "--res", "720"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert sink.read_header(path) == (1280, 720, frames)
+    host = hostapi.Host(1280, 720, 0, Assets(1280, 720), demo=True)
+    try:
+        out = np.zeros((720, 1280), dtype=np.uint32)
+        times = sharding.timeline_times(frames)
+        for i in range(frames):
+            host.demo_draw(out, times[i])
+            assert np.array_equal(sink.read_frame(path, i), out), f"frame {i}"
+    finally:
+        host.close()
