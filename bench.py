@@ -55,6 +55,27 @@ FLOP_PER_FX_PIXEL = {
 }
 
 
+# what ncu says bounds each kernel (profiles/r01_notes.md): reported next to the roofline fraction so that a small HBM
+# fraction of a kernel that is not HBM bound is not misread
+LIMITER = {
+    "raymarch": "instruction issue (87 % issue-active) with the XU pipe (F2I/FRND of lutcosf) at 60-70 %; no FMA contraction allowed",
+    "old_blur": "integer ALU pipe + dependent chain of the saturating in-place recurrence (ALU 57 %, issue 62 %); DRAM traffic = algorithmic bytes",
+    "voxel": "L2 gather latency of the height/colour map samples (warp per ray)",
+    "polar_blit": "dependent map -> texel gather chain; DRAM traffic = algorithmic bytes",
+    "fx_blit_2x2": "L2 write-back of the 33 MB frame",
+    "blend": "HBM / L2 bandwidth",
+    "rect_blit": "HBM / L2 bandwidth (small rectangles: launch latency)",
+    "memset32": "launch latency (4 MB)",
+}
+
+
+def limiter_of(name):
+    for prefix, text in LIMITER.items():
+        if name.startswith(prefix):
+            return text
+    return None
+
+
 def measured_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -195,6 +216,14 @@ def run_ours(args):
     host = hostapi.Host(RES_X, RES_Y, local, assets)
     ctx = host.context()
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # The 12 frames of a step are independent: the device-resident leg renders them on --streams CUDA streams (one context =
+    # one set of render targets per stream), so the latency-bound casters and blurs of one frame overlap the issue-bound
+    # raymarcher of another.  The host-API legs (e2e) and the per-kernel profile use the single context of the host layer.
+    n_streams = max(1, args.streams)
+    side_streams = [torch.cuda.Stream() for _ in range(n_streams - 1)]
+    ctxs = [ctx] + [capi.Context(RES_X, RES_Y, local, assets) for _ in side_streams]
+    for c, st in zip(ctxs[1:], side_streams):
+        c.set_stream(st.cuda_stream)
 
     # parameters of every suite entry, evaluated once by the host layer's Rocket (the device-resident leg feeds them
     # straight to the C ABI; the e2e leg re-evaluates them per frame like the reference does)
@@ -203,11 +232,17 @@ def run_ours(args):
         host.set_row(row)
         cases.append((label, eff, host_eff, close, row, capi.params_from_tracks(eff, host.track), float(np.float32(host.time))))
 
-    d_frames = [ctx.malloc(RES_X * RES_Y * 4 + 65536) for _ in range(2)]  # alternate targets so no frame is rewritten back to back
+    # two targets per stream, alternated so that no frame is rewritten back to back
+    d_frames = [[c.malloc(RES_X * RES_Y * 4 + 65536) for _ in range(2)] for c in ctxs]
 
     def step_device(i):
         for j, (label, eff, host_eff, close, row, params, t) in enumerate(cases):
-            ctx.draw(eff, params, t, d_dest=d_frames[(i + j) & 1], close=close)
+            k = j % n_streams
+            ctxs[k].draw(eff, params, t, d_dest=d_frames[k][(i + j // n_streams) & 1], close=close)
+
+    def join_streams():
+        for st in side_streams:
+            torch.cuda.current_stream().wait_stream(st)
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,15 +266,18 @@ def run_ours(args):
             if i % 8 == 0:
                 torch.cuda.synchronize()
     barrier()
-    launches0 = ctx.launch_count()
+    launches0 = sum(c.launch_count() for c in ctxs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    ev0.record()                       # every stream is idle here (barrier above)
+    for st in side_streams:
+        st.wait_event(ev0)
     for i in range(args.steps):
         step_device(i)
+    join_streams()
     ev1.record()
     torch.cuda.synchronize()
     elapsed_ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - launches0
+    launches = sum(c.launch_count() for c in ctxs) - launches0
     if rank == 0:
         # keep the same load up briefly so the 100 ms sampler certainly sees the region's clocks
         t_load = time.perf_counter()
@@ -305,9 +343,11 @@ def run_ours(args):
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = measured_peaks()
         prof_steps = max(1, min(args.steps, 5))
+        torch.cuda.synchronize()
         ctx.profile_begin()
         for i in range(prof_steps):
-            step_device(i)
+            for j, (label, eff, host_eff, close, row, params, t) in enumerate(cases):
+                ctx.draw(eff, params, t, d_dest=d_frames[0][(i + j) & 1], close=close)
         stats = ctx.profile_end()
         total_ms = sum(s["total_ms"] for s in stats.values()) or 1.0
         fx_pixels = (RES_X // 2 + 4) * (RES_Y // 2 + 4)
@@ -327,10 +367,11 @@ def run_ours(args):
                 gbs = s["algo_bytes"] / s["launches"] / (avg_ms * 1e-3) / 1e9
                 entry.update({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak})
             entry["traffic"] = traffic.get(name)
+            entry["limiter"] = limiter_of(name)
             kernels[name] = entry
         dominant = max(kernels, key=lambda k: kernels[k]["share"])
         roofline = dict(kernels[dominant], kernel=dominant, peak_source=peak_src,
-                        timing="CUDA events around every launch, instrumented repeat of the timed steps")
+                        timing="CUDA events around every launch, instrumented single-stream repeat of the timed steps")
         # the HBM-bound kernel with the largest share, reported next to the dominant one
         hbm_kernels = [k for k in kernels if kernels[k]["bound"] == "hbm"]
         if hbm_kernels:
@@ -343,7 +384,7 @@ def run_ours(args):
             for _ in range(3):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                ctx.draw(eff, params, t, d_dest=d_frames[0], close=close)
+                ctx.draw(eff, params, t, d_dest=d_frames[0][0], close=close)
                 b.record()
                 torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
@@ -374,6 +415,7 @@ def run_ours(args):
             "ms_per_step": elapsed_ms / args.steps, "fps_per_effect_mean": 1e3 * len(SUITE) / (elapsed_ms / args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
             "config": {"workload": "effect-suite-4k", "res": [RES_X, RES_Y], "effects": [s[0] for s in SUITE], "rows": [s[4] for s in SUITE],
+                       "streams": n_streams,
                        "assets": "procedural stand-ins" if assets.synthetic else "reference art (oracle/_ref/assets.npz)",
                        "l2": f"no explicit flush: one step streams ~{working_set_mb:.0f} MB (frames, render targets, polar maps, textures) through the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
@@ -384,6 +426,8 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
+    for c in ctxs[1:]:
+        c.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -524,6 +568,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams (contexts) the device-resident leg spreads the 12 independent frames of a step over")
     ap.add_argument("--workload", default="effect-suite-4k", choices=["effect-suite-4k", "timeline-4k"],
                     help="timeline-4k: the 600-frame directors-cut timeline through Demo_Draw (BASELINE config 5), frame i -> rank i mod N (strong scaling)")
     ap.add_argument("--frames", type=int, default=600)

@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+"""How much does rendering independent frames on K streams (K contexts) help the device-resident suite throughput?"""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from cookiedough_b200 import capi, hostapi
+from cookiedough_b200.assets import Assets
+
+assets = Assets(bench.RES_X, bench.RES_Y)
+host = hostapi.Host(bench.RES_X, bench.RES_Y, 0, assets)
+cases = []
+for label, eff, host_eff, close, row in bench.SUITE:
+    host.set_row(row)
+    cases.append((label, eff, close, capi.params_from_tracks(eff, host.track), float(np.float32(host.time))))
+for K in (1, 2, 3, 4):
+    ctxs = [capi.Context(bench.RES_X, bench.RES_Y, 0, assets) for _ in range(K)]
+    streams = [torch.cuda.Stream() for _ in range(K)]
+    for c, s in zip(ctxs, streams):
+        c.set_stream(s.cuda_stream)
+    order = sorted(range(len(cases)), key=lambda j: j)  # round-robin
+    def step():
+        for j in order:
+            label, eff, close, params, t = cases[j]
+            ctxs[j % K].draw(eff, params, t, close=close)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    steps = 30
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    print(f"K={K}: {dt*1e3:.3f} ms/step  {bench.PIXELS_PER_STEP/dt/1e6:.0f} Mpixel/s")
+    for c in ctxs:
+        c.close()
+host.close()
