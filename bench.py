@@ -369,9 +369,24 @@ def run_ours(args):
             entry["traffic"] = traffic.get(name)
             entry["limiter"] = limiter_of(name)
             kernels[name] = entry
+        # The step's dominant kernel is raymarch_kernel<Effect>: one __global__ template, seven instantiations that the
+        # profiler names separately (52 % of the step together, 7-11 % each).  The headline roofline is that kernel --
+        # algorithmic FLOPs of all its launches over their summed time -- unless a single other kernel outweighs the family.
+        fam = [k for k in kernels if k.startswith("raymarch_") and k != "raymarch_tunnel"]
+        fam_share = sum(kernels[k]["share"] for k in fam)
         dominant = max(kernels, key=lambda k: kernels[k]["share"])
-        roofline = dict(kernels[dominant], kernel=dominant, peak_source=peak_src,
-                        timing="CUDA events around every launch, instrumented single-stream repeat of the timed steps")
+        if fam and fam_share > kernels[dominant]["share"]:
+            fam_ms = sum(kernels[k]["avg_ms"] * kernels[k]["launches_per_step"] for k in fam)
+            fam_flop = sum(FLOP_PER_FX_PIXEL[k] * fx_pixels * kernels[k]["launches_per_step"] for k in fam)
+            tf = fam_flop / (fam_ms * 1e-3) / 1e12
+            roofline = {"kernel": "raymarch_kernel<Effect> (" + ", ".join(k[len("raymarch_"):] for k in fam) + ")",
+                        "launches_per_step": sum(kernels[k]["launches_per_step"] for k in fam), "avg_ms": fam_ms / sum(kernels[k]["launches_per_step"] for k in fam),
+                        "share": fam_share, "bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
+                        "traffic": sum((kernels[k]["traffic"] or 0.0) for k in fam) / len(fam), "limiter": limiter_of("raymarch"),
+                        "peak_note": "FADD/FMUL issue rate without FMA contraction (bit parity forbids FMA): 148 SM x 128 lanes x clock"}
+        else:
+            roofline = dict(kernels[dominant], kernel=dominant)
+        roofline.update(peak_source=peak_src, timing="CUDA events around every launch, instrumented single-stream repeat of the timed steps")
         # the HBM-bound kernel with the largest share, reported next to the dominant one
         hbm_kernels = [k for k in kernels if kernels[k]["bound"] == "hbm"]
         if hbm_kernels:
