@@ -73,3 +73,27 @@ def test_no_cpu_fallback_without_gpu():
 def test_geti_matches_roundf():
     from cookiedough_b200.capi import geti
     assert [geti(v) for v in (0.4, 0.5, 1.5, 2.5, -0.5, -1.5, 511.7)] == [0, 1, 2, 3, -1, -2, 512]
+
+
+def test_host_layer_exports_the_reference_entry_points():
+    """include/ckd_host.h: the reference's own C++ names (demo.h, shadertoy.h, ..., util.h, rocket.h) plus the CkdHost_* /
+    CkdSink_* services must be exported with C++ linkage exactly as a caller compiled against the header expects them"""
+    from cookiedough_b200 import capi
+    header = open(os.path.join(REPO, "include", "ckd_host.h")).read()
+    header = re.sub(r"//.*", "", header)
+    declared = set(re.findall(r"^\s*(?:bool|void|float|double|int|uint32_t \*|ckd_ctx \*|SyncTrack|const std::string &)\s*\*?([A-Za-z_][A-Za-z0-9_]*)\s*\(", header, flags=re.M))
+    declared -= {"getf"}  # inline in the header
+    assert {"Demo_Create", "Demo_Draw", "Demo_Destroy", "Nautilus_Draw", "Landscape_Create", "Polar_BlitA", "BoxBlur32", "Mix32", "TapeWarp32",
+            "CkdHost_Create", "CkdSink_Open", "CkdSink_Commit", "Launch", "AddTrack", "SetLastError"} <= declared
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", "-C", capi.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (?:Rocket::)?([A-Za-z_][A-Za-z0-9_]*)(?:\[abi:cxx11\])?\(", syms))
+    missing = sorted(declared - exported)
+    assert not missing, f"include/ckd_host.h declares functions the library does not export: {missing}"
+
+
+def test_host_hooks_for_bindings_are_exported():
+    from cookiedough_b200 import capi
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for name in ("ckdhost_create", "ckdhost_launch", "ckdhost_draw", "ckdhost_post", "ckdhost_demo_create", "ckdhost_demo_draw", "ckdhost_demo_destroy",
+                 "ckdhost_set_pipelined", "ckdhost_flush", "ckdsink_open", "ckdsink_acquire", "ckdsink_commit", "ckdsink_close"):
+        assert hasattr(lib, name), name
