@@ -113,6 +113,10 @@ BLIT_OPS = {"BlitSrc32": 0, "BlitSrc32A": 1, "BlitAdd32": 2, "BlitAdd32A": 3}
 
 
 
+class BlendStep(C.Structure):  # ckd_blend_step
+    _fields_ = [("op", C.c_int), ("d_src", C.c_void_p), ("f_param", C.c_float), ("u_param", C.c_uint)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint), ("total_ms", C.c_double), ("algo_bytes", C.c_double)]
 
@@ -152,7 +156,7 @@ def load():
         "ckd_old_blur_h": ([VP, VP, VP, U, U, F], _I), "ckd_old_blur_v": ([VP, VP, VP, U, U, F], _I), "ckd_old_blur": ([VP, VP, VP, U, U, F], _I),
         "ckd_box_blur_scale": ([F], F),
         "ckd_new_blur_h": ([VP, VP, VP, U, U, F, F, U], _I), "ckd_new_blur_v": ([VP, VP, VP, U, U, F, F, U], _I), "ckd_new_blur": ([VP, VP, VP, U, U, F, F, U], _I),
-        "ckd_blend": ([VP, _I, VP, VP, U, F, U], _I),
+        "ckd_blend": ([VP, _I, VP, VP, U, F, U], _I), "ckd_blend_chain": ([VP, VP, VP, U, U], _I),
         "ckd_blit": ([VP, _I, VP, VP, U, U, U, F], _I),
         "ckd_mix_src_s": ([VP, VP, VP, U, U, U], _I),
         "ckd_memset32": ([VP, VP, C.c_uint32, SZ], _I),
@@ -326,6 +330,13 @@ class Context:
     def polar_blit(self, d_dest, d_src, inverse=False, alpha=False):
         fn = self.L.ckd_polar_blit_a if alpha else self.L.ckd_polar_blit
         self._check(fn(self.h, C.c_void_p(d_dest), C.c_void_p(d_src), int(inverse)))
+
+    def blend_chain(self, d_dest, steps, n):
+        """steps: [(op name, d_src or None, f_param, u_param)] applied per pixel in one pass (ckd_blend_chain)"""
+        arr = (BlendStep * len(steps))()
+        for a, (op, d_src, f, u) in zip(arr, steps):
+            a.op, a.d_src, a.f_param, a.u_param = BLEND_OPS[op], d_src, f, u
+        self._check(self.L.ckd_blend_chain(self.h, C.c_void_p(d_dest), arr, len(steps), n))
 
     def old_blur(self, kind, d_dest, d_src, w, h, strength):
         fn = {"h": self.L.ckd_old_blur_h, "v": self.L.ckd_old_blur_v, "hv": self.L.ckd_old_blur}[kind]

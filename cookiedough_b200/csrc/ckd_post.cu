@@ -216,6 +216,122 @@ template <int OP> static int LaunchBlend(ckd_ctx *ctx, uint32_t *d_dest, const u
 	return CKD_OK;
 }
 
+// per-op scalar parameters as the reference derives them from its arguments
+static BlendParams MakeBlendParams(ckd_blend_op op, float f_param, unsigned u_param)
+{
+	BlendParams p = { 0, 0 };
+	if (op == CKD_MIX32) p.u0 = u_param & 0xff;
+	else if (op == CKD_SOFTLIGHT32AA) p.u0 = ckdh::x86_f2u(ckdh::saturatef(f_param)*255.f); // util.cpp:311-312: alpha = saturatef(alpha)*255.f; iA = unsigned(alpha)
+	else if (op == CKD_FADE32) { p.u0 = u_param >> 24; p.u1 = u_param & 0xffffff; }
+	return p;
+}
+
+// ---- fused chain: up to kMaxChain blend ops applied to every pixel in one pass --------------------------------------
+// The compositor stacks 3-8 full-frame blends per frame (demo.cpp:511-1000); each is dest = f(dest, layer) per pixel, so a
+// chain keeps the pixel in registers and reads every layer once: (layers + 2) x 4 bytes per pixel instead of 12 per op.
+constexpr int kMaxChain = 8;
+struct ChainArgs
+{
+	const uint32_t *src[kMaxChain];   // nullptr: the op reads the running pixel itself (Fade32, or a source aliasing the destination)
+	BlendParams p[kMaxChain];
+	int op[kMaxChain];
+	int count;
+};
+
+// one step on 4 pixels: the switch is taken once per step (uniform across the grid), not once per pixel
+#define CKD_CHAIN_CASE(OP) case OP: d.x = blend_px<OP>(d.x, v.x, p); d.y = blend_px<OP>(d.y, v.y, p); d.z = blend_px<OP>(d.z, v.z, p); d.w = blend_px<OP>(d.w, v.w, p); break;
+__device__ __forceinline__ void chain_quad(int op, uint4 &d, const uint4 &v, const BlendParams &p)
+{
+	switch (op)
+	{
+	CKD_CHAIN_CASE(CKD_MIX32) CKD_CHAIN_CASE(CKD_MIXOVER32) CKD_CHAIN_CASE(CKD_ADD32) CKD_CHAIN_CASE(CKD_SUB32) CKD_CHAIN_CASE(CKD_EXCL32)
+	CKD_CHAIN_CASE(CKD_SOFTLIGHT32) CKD_CHAIN_CASE(CKD_SOFTLIGHT32A) CKD_CHAIN_CASE(CKD_SOFTLIGHT32AA) CKD_CHAIN_CASE(CKD_OVERLAY32)
+	CKD_CHAIN_CASE(CKD_OVERLAY32A) CKD_CHAIN_CASE(CKD_DARKEN32_50) CKD_CHAIN_CASE(CKD_MULSRC32) CKD_CHAIN_CASE(CKD_MULSRC32A)
+	CKD_CHAIN_CASE(CKD_MIXSRC32)
+	default: d.x = blend_px<CKD_FADE32>(d.x, v.x, p); d.y = blend_px<CKD_FADE32>(d.y, v.y, p); d.z = blend_px<CKD_FADE32>(d.z, v.z, p); d.w = blend_px<CKD_FADE32>(d.w, v.w, p); break;
+	}
+}
+#undef CKD_CHAIN_CASE
+
+__global__ void __launch_bounds__(256, 4) blend_chain_kernel(uint32_t *pDest, unsigned numQuads, unsigned numPixels, const ChainArgs args)
+{
+	const unsigned stride = gridDim.x*blockDim.x;
+	for (unsigned q = blockIdx.x*blockDim.x + threadIdx.x; q < numQuads; q += stride)
+	{
+		uint4 d = reinterpret_cast<const uint4 *>(pDest)[q];
+		// the first layers are requested before any arithmetic (they do not depend on the running pixel)
+		uint4 s[4];
+		#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			if (k < args.count && nullptr != args.src[k])
+				s[k] = __ldg(reinterpret_cast<const uint4 *>(args.src[k]) + q);
+		#pragma unroll 1
+		for (int k = 0; k < args.count; ++k)
+		{
+			uint4 v = d;
+			if (nullptr != args.src[k])
+				v = (k < 4) ? ((k == 0) ? s[0] : (k == 1) ? s[1] : (k == 2) ? s[2] : s[3]) : __ldg(reinterpret_cast<const uint4 *>(args.src[k]) + q);
+			chain_quad(args.op[k], d, v, args.p[k]);
+		}
+		reinterpret_cast<uint4 *>(pDest)[q] = d;
+	}
+	const unsigned tail = numQuads*4 + blockIdx.x*blockDim.x + threadIdx.x;
+	if (tail < numPixels)
+	{
+		uint4 d = make_uint4(pDest[tail], 0, 0, 0);
+		for (int k = 0; k < args.count; ++k)
+		{
+			const uint4 v = make_uint4((nullptr != args.src[k]) ? args.src[k][tail] : d.x, 0, 0, 0);
+			chain_quad(args.op[k], d, v, args.p[k]);
+		}
+		pDest[tail] = d.x;
+	}
+}
+
+extern "C" int ckd_blend_chain(ckd_ctx *ctx, uint32_t *d_dest, const ckd_blend_step *steps, unsigned num_steps, unsigned num_pixels)
+{
+	CKD_REQUIRE(ctx && d_dest && (steps || 0 == num_steps), "null argument");
+	if (0 == num_pixels)
+		return CKD_OK;
+	bool aligned = 0 == (reinterpret_cast<uintptr_t>(d_dest) & 15);
+	for (unsigned i = 0; i < num_steps; ++i)
+	{
+		CKD_REQUIRE(unsigned(steps[i].op) <= unsigned(CKD_FADE32), "unknown blend op");
+		CKD_REQUIRE(steps[i].op == CKD_FADE32 || steps[i].d_src, "null source");
+		aligned = aligned && 0 == (reinterpret_cast<uintptr_t>(steps[i].d_src) & 15);
+	}
+	if (!aligned)
+	{
+		// unaligned sub-rectangles: one ckd_blend per step
+		for (unsigned i = 0; i < num_steps; ++i)
+			CKD_TRY(ckd_blend(ctx, steps[i].op, d_dest, steps[i].d_src, num_pixels, steps[i].f_param, steps[i].u_param));
+		return CKD_OK;
+	}
+
+	for (unsigned first = 0; first < num_steps; first += kMaxChain)
+	{
+		ChainArgs args;
+		memset(&args, 0, sizeof(args));
+		args.count = int(std::min<unsigned>(kMaxChain, num_steps - first));
+		int layers = 0;
+		for (int k = 0; k < args.count; ++k)
+		{
+			const ckd_blend_step &step = steps[first + k];
+			const bool self = step.op == CKD_FADE32 || step.d_src == d_dest;
+			args.src[k] = self ? nullptr : step.d_src;
+			args.op[k] = int(step.op);
+			args.p[k] = MakeBlendParams(step.op, step.f_param, step.u_param);
+			layers += self ? 0 : 1;
+		}
+		const unsigned numQuads = num_pixels/4;
+		const unsigned blocks = std::max(1u, std::min(unsigned(ctx->numSMs)*16, ckd_div_up(std::max(numQuads, 1u), 256)));
+		ckd_prof_begin(ctx, "blend_chain", 4.0*(layers + 2)*num_pixels);
+		blend_chain_kernel<<<blocks, 256, 0, ctx->stream>>>(d_dest, numQuads, num_pixels, args);
+		CKD_CHECK_LAUNCH(ctx);
+	}
+	return CKD_OK;
+}
+
 extern "C" int ckd_blend(ckd_ctx *ctx, ckd_blend_op op, uint32_t *d_dest, const uint32_t *d_src, unsigned num_pixels, float f_param, unsigned u_param)
 {
 	CKD_REQUIRE(ctx && d_dest, "null argument");
@@ -223,27 +339,24 @@ extern "C" int ckd_blend(ckd_ctx *ctx, ckd_blend_op op, uint32_t *d_dest, const 
 	if (op == CKD_FADE32)
 		d_src = d_dest;
 
-	BlendParams p = { 0, 0 };
+	BlendParams p = MakeBlendParams(op, f_param, u_param);
 	switch (op)
 	{
-	case CKD_MIX32:         p.u0 = u_param & 0xff; return LaunchBlend<CKD_MIX32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_MIX32:         return LaunchBlend<CKD_MIX32>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_MIXOVER32:     return LaunchBlend<CKD_MIXOVER32>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_ADD32:         return LaunchBlend<CKD_ADD32>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_SUB32:         return LaunchBlend<CKD_SUB32>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_EXCL32:        return LaunchBlend<CKD_EXCL32>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_SOFTLIGHT32:   return LaunchBlend<CKD_SOFTLIGHT32>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_SOFTLIGHT32A:  return LaunchBlend<CKD_SOFTLIGHT32A>(ctx, d_dest, d_src, num_pixels, p);
-	case CKD_SOFTLIGHT32AA:
-		// util.cpp:311-312: alpha = saturatef(alpha)*255.f; iA = unsigned(alpha)
-		p.u0 = ckdh::x86_f2u(ckdh::saturatef(f_param)*255.f);
-		return LaunchBlend<CKD_SOFTLIGHT32AA>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_SOFTLIGHT32AA: return LaunchBlend<CKD_SOFTLIGHT32AA>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_OVERLAY32:     return LaunchBlend<CKD_OVERLAY32>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_OVERLAY32A:    return LaunchBlend<CKD_OVERLAY32A>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_DARKEN32_50:   return LaunchBlend<CKD_DARKEN32_50>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_MULSRC32:      return LaunchBlend<CKD_MULSRC32>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_MULSRC32A:     return LaunchBlend<CKD_MULSRC32A>(ctx, d_dest, d_src, num_pixels, p);
 	case CKD_MIXSRC32:      return LaunchBlend<CKD_MIXSRC32>(ctx, d_dest, d_src, num_pixels, p);
-	case CKD_FADE32:        p.u0 = u_param >> 24; p.u1 = u_param & 0xffffff; return LaunchBlend<CKD_FADE32>(ctx, d_dest, d_src, num_pixels, p);
+	case CKD_FADE32:        return LaunchBlend<CKD_FADE32>(ctx, d_dest, d_src, num_pixels, p);
 	}
 	CKD_REQUIRE(false, "unknown blend op");
 }

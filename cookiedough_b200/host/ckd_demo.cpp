@@ -100,13 +100,40 @@ bool LoadLayer(Layer &layer, const char *path, int minWidth, int minHeight)
 ckd_ctx *s_c = nullptr;
 unsigned s_resX = 0, s_resY = 0, s_outputSize = 0;
 
+// Consecutive blends onto the same buffer are recorded and issued as one fused pass (ckd_blend_chain): the pixel stays in
+// registers, every layer is read once.  Anything else that touches device memory flushes the recording first, so the
+// order of operations the reference performs is kept.
+uint32_t *s_chainDest = nullptr;
+unsigned s_chainPixels = 0;
+std::vector<ckd_blend_step> s_chain;
+
+bool FlushChain()
+{
+	if (s_chain.empty())
+		return true;
+	const bool ok = Check(ckd_blend_chain(s_c, s_chainDest, s_chain.data(), unsigned(s_chain.size()), s_chainPixels), "Demo_Draw: blend");
+	s_chain.clear();
+	return ok;
+}
+
 bool Blend(ckd_blend_op op, uint32_t *d_dest, const uint32_t *d_src, unsigned numPixels, float f = 0.f, unsigned u = 0)
 {
-	return Check(ckd_blend(s_c, op, d_dest, d_src, numPixels, f, u), "Demo_Draw: blend");
+	bool ok = true;
+	if (!s_chain.empty() && (d_dest != s_chainDest || numPixels != s_chainPixels))
+		ok = FlushChain();
+	// a layer that was itself produced by the pending chain cannot happen: the chain only ever writes its destination
+	s_chainDest = d_dest;
+	s_chainPixels = numPixels;
+	s_chain.push_back({ op, d_src, f, u });
+	return ok;
 }
+
+// every other device operation: flush the recorded blends, then run it
+#define CKD_DIRECT(call, what) (FlushChain(), Check((call), (what)))
+
 bool Blit(ckd_blit_op op, uint32_t *d_dest, const uint32_t *d_src, unsigned destResX, unsigned srcResX, unsigned yRes, float alpha = 1.f)
 {
-	return Check(ckd_blit(s_c, op, d_dest, d_src, destResX, srcResX, yRes, alpha), "Demo_Draw: blit");
+	return CKD_DIRECT(ckd_blit(s_c, op, d_dest, d_src, destResX, srcResX, yRes, alpha), "Demo_Draw: blit");
 }
 bool Full(ckd_blend_op op, uint32_t *d_dest, const Layer &layer, float f = 0.f) { return Blend(op, d_dest, layer.d, s_outputSize, f); }
 
@@ -139,7 +166,7 @@ const uint32_t *LogoBlend(float blend, const Layer *logos, int numLogos, unsigne
 	{
 		if (blend >= float(i) && blend < float(i+1))
 		{
-			Check(ckd_copy(s_c, d_target, logos[i].d, size_t(width)*height*4), "Demo_Draw: memcpy");
+			CKD_DIRECT(ckd_copy(s_c, d_target, logos[i].d, size_t(width)*height*4), "Demo_Draw: memcpy");
 			Blend(CKD_MIX32, d_target, logos[i+1].d, width*height, 0.f, iFactor);
 			break;
 		}
@@ -173,8 +200,8 @@ void DrawTestPattern(uint32_t *d_dest)
 	for (unsigned iY = 0; iY < fxY; ++iY)
 		for (unsigned iX = 0; iX < fxX; ++iX)
 			pattern[size_t(iY)*fxX + iX] = (iY < fxY/2) ? ((iY & 1) ? 0xffffffffu : 0u) : ((iX & 1) ? 0xffffffffu : 0u);
-	if (Check(ckd_upload(s_c, ckd_fxmap(s_c, 0), pattern.data(), pattern.size()*4), "FxBlitter_DrawTestPattern") && Check(ckd_sync(s_c), "FxBlitter_DrawTestPattern"))
-		Check(ckd_fx_blit_2x2(s_c, d_dest, ckd_fxmap(s_c, 0)), "FxBlitter_DrawTestPattern");
+	if (CKD_DIRECT(ckd_upload(s_c, ckd_fxmap(s_c, 0), pattern.data(), pattern.size()*4), "FxBlitter_DrawTestPattern") && Check(ckd_sync(s_c), "FxBlitter_DrawTestPattern"))
+		CKD_DIRECT(ckd_fx_blit_2x2(s_c, d_dest, ckd_fxmap(s_c, 0)), "FxBlitter_DrawTestPattern");
 }
 
 } // namespace
@@ -364,6 +391,7 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 	s_outputSize = s_resX*s_resY;
 	const unsigned kResX = s_resX, kResY = s_resY, kOutputSize = s_outputSize;
 
+	s_chain.clear();
 	uint32_t *d = ckdhost::BeginCompose();       // the device twin of pDest; X_Draw(pDest, ...) renders into it while composing
 	uint32_t *rt0 = ckd_render_target(s_c, 0), *rt1 = ckd_render_target(s_c, 1), *rt2 = ckd_render_target(s_c, 2), *rt3 = ckd_render_target(s_c, 3);
 
@@ -432,10 +460,10 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 				{
 					const float easeA = easeOutElasticf(alphaRev)*ckdh::kGoldenAngle;
 					const float easeB = easeInBackf(alphaRev)*ckdh::kGoldenRatio;
-					Check(ckd_tape_warp(s_c, rt0, s_revLogo.d, kResX, kResY, easeA, easeB), "Demo_Draw: TapeWarp32");
+					CKD_DIRECT(ckd_tape_warp(s_c, rt0, s_revLogo.d, kResX, kResY, easeA, easeB), "Demo_Draw: TapeWarp32");
 				}
 				else
-					Check(ckd_old_blur(s_c, rt0, s_revLogo.d, kResX, kResY, ckdh::BoxBlurScale((alphaRev-0.314f)*ckdh::k2PI)), "Demo_Draw: BoxBlur32");
+					CKD_DIRECT(ckd_old_blur(s_c, rt0, s_revLogo.d, kResX, kResY, ckdh::BoxBlurScale((alphaRev-0.314f)*ckdh::k2PI)), "Demo_Draw: BoxBlur32");
 				Blit(CKD_BLITSRC32A, d, rt0, kResX, kResX, kResY, alphaRev);
 			}
 
@@ -484,14 +512,14 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 				const float blurH = Rocket::getf(trackCreditLogoBlurH);
 				if (0.f != blurH)
 				{
-					Check(ckd_old_blur_h(s_c, rt0, pCur, kCredX, kCredY, ckdh::BoxBlurScale(blurH)), "Demo_Draw: HorizontalBoxBlur32");
+					CKD_DIRECT(ckd_old_blur_h(s_c, rt0, pCur, kCredX, kCredY, ckdh::BoxBlurScale(blurH)), "Demo_Draw: HorizontalBoxBlur32");
 					pCur = rt0;
 				}
 
 				const float blurV = Rocket::getf(trackCreditLogoBlurV);
 				if (0 != blurV)
 				{
-					Check(ckd_old_blur_v(s_c, rt0, pCur, kCredX, kCredY, ckdh::BoxBlurScale(blurV)), "Demo_Draw: VerticalBoxBlur32");
+					CKD_DIRECT(ckd_old_blur_v(s_c, rt0, pCur, kCredX, kCredY, ckdh::BoxBlurScale(blurV)), "Demo_Draw: VerticalBoxBlur32");
 					pCur = rt0;
 				}
 
@@ -517,7 +545,7 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 			if (0.f != hBlur)
 			{
 				hBlur = ckdh::BoxBlurScale(hBlur);
-				Check(ckd_old_blur_h(s_c, rt0, pCousteau, kResX, kResY, hBlur), "Demo_Draw: HorizontalBoxBlur32");
+				CKD_DIRECT(ckd_old_blur_h(s_c, rt0, pCousteau, kResX, kResY, hBlur), "Demo_Draw: HorizontalBoxBlur32");
 				pCousteau = rt0;
 			}
 
@@ -546,7 +574,7 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 
 					if (rakerText > 0.f && rakerText < 1.f)
 					{
-						Check(ckd_memset32(s_c, rt2, 0, kOutputSize), "Demo_Draw: memset32");
+						CKD_DIRECT(ckd_memset32(s_c, rt2, 0, kOutputSize), "Demo_Draw: memset32");
 						Blit(CKD_BLITSRC32, rt2 + (kResY-115)*kResX, s_closeSpike1961.d, kResX, 624, 115);
 						Blend(CKD_SOFTLIGHT32AA, d, rt2, kOutputSize, rakerText);
 					}
@@ -556,7 +584,7 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 						const float rakerBlur = ckdh::clampf(0.f, 100.f, Rocket::getf(trackCloseUpMoonrakerTextBlur));
 						if (rakerBlur >= 1.f)
 						{
-							Check(ckd_old_blur_h(s_c, rt3, pText, 624, 115, ckdh::BoxBlurScale(rakerBlur)), "Demo_Draw: HorizontalBoxBlur32");
+							CKD_DIRECT(ckd_old_blur_h(s_c, rt3, pText, 624, 115, ckdh::BoxBlurScale(rakerBlur)), "Demo_Draw: HorizontalBoxBlur32");
 							pText = rt3;
 						}
 						Blit(CKD_BLITSRC32, d + (kResY-115)*kResX, pText, kResX, 624, 115);
@@ -611,7 +639,7 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 			const float waterOverlayBlurHorz = ckdh::clampf(0.f, 100.f, Rocket::getf(trackLoveBlurHorz));
 			if (0.f != waterOverlayBlurHorz)
 			{
-				Check(ckd_old_blur_h(s_c, rt0, pWaterOverlay, kResX, kResY, ckdh::BoxBlurScale(waterOverlayBlurHorz)), "Demo_Draw: HorizontalBoxBlur32");
+				CKD_DIRECT(ckd_old_blur_h(s_c, rt0, pWaterOverlay, kResX, kResY, ckdh::BoxBlurScale(waterOverlayBlurHorz)), "Demo_Draw: HorizontalBoxBlur32");
 				pWaterOverlay = rt0;
 			}
 			Blit(CKD_BLITADD32A, d, pWaterOverlay, kResX, kResX, kResY, overlayA);
@@ -647,11 +675,11 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 			const bool warpAll = 0 != Rocket::geti(trackFullWarpTPB);
 			if (false == warpAll)
 			{
-				Check(ckd_memset32(s_c, rt0, 0xffffff, kOutputSize), "Demo_Draw: memset32");
-				Check(ckd_memset32(s_c, d, 0xffffff, kOutputSize), "Demo_Draw: memset32");
+				CKD_DIRECT(ckd_memset32(s_c, rt0, 0xffffff, kOutputSize), "Demo_Draw: memset32");
+				CKD_DIRECT(ckd_memset32(s_c, d, 0xffffff, kOutputSize), "Demo_Draw: memset32");
 
 				const int ribX = ckdh::clampi(0, int(kResX), Rocket::geti(trackRibbonsTPB));
-				Check(ckd_mix_src_s(s_c, d, s_ribbons.d + ribX, kResX, kResY-1, 2160), "Demo_Draw: MixSrc32S");
+				CKD_DIRECT(ckd_mix_src_s(s_c, d, s_ribbons.d + ribX, kResX, kResY-1, 2160), "Demo_Draw: MixSrc32S");
 
 				Full(CKD_MIXSRC32, rt0, s_nytrikTPB);
 
@@ -659,27 +687,27 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 				if (0.f != blurTPB)
 				{
 					blurTPB = ckdh::BoxBlurScale(blurTPB);
-					Check(ckd_old_blur_h(s_c, rt0, rt0, kResX, kResY, blurTPB), "Demo_Draw: HorizontalBoxBlur32");
+					CKD_DIRECT(ckd_old_blur_h(s_c, rt0, rt0, kResX, kResY, blurTPB), "Demo_Draw: HorizontalBoxBlur32");
 				}
 			}
 			else
 			{
 				Plasma_Draw(pDest, timer, delta);
 
-				Check(ckd_memset32(s_c, rt0, 0xffffff, kOutputSize), "Demo_Draw: memset32");
+				CKD_DIRECT(ckd_memset32(s_c, rt0, 0xffffff, kOutputSize), "Demo_Draw: memset32");
 				Full(CKD_MIXSRC32, rt0, s_nytrikTPB);
 
 				float blurTPB = Rocket::getf(trackBlurTPB);
 				if (0.f != blurTPB)
 				{
 					blurTPB = ckdh::BoxBlurScale(blurTPB);
-					Check(ckd_old_blur_v(s_c, rt0, rt0, kResX, kResY, blurTPB), "Demo_Draw: VerticalBoxBlur32");
+					CKD_DIRECT(ckd_old_blur_v(s_c, rt0, rt0, kResX, kResY, blurTPB), "Demo_Draw: VerticalBoxBlur32");
 				}
 			}
 
 			const float distortTPB = Rocket::getf(trackDistortTPB);
 			const float distortStrengthTPB = Rocket::getf(trackDistortStrengthTPB);
-			Check(ckd_tape_warp(s_c, rt1, rt0, kResX, kResY, distortStrengthTPB, distortTPB), "Demo_Draw: TapeWarp32");
+			CKD_DIRECT(ckd_tape_warp(s_c, rt1, rt0, kResX, kResY, distortStrengthTPB, distortTPB), "Demo_Draw: TapeWarp32");
 			Blend(CKD_MIXOVER32, d, rt1, kOutputSize);
 
 			Full(CKD_MULSRC32, d, s_nautilusVignette);
@@ -688,7 +716,7 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 
 	case 13: // disco guys and the GPU joke, demo.cpp:960-998
 		{
-			Check(ckd_memset32(s_c, d, 0, kOutputSize), "Demo_Draw: memset32");
+			CKD_DIRECT(ckd_memset32(s_c, d, 0, kOutputSize), "Demo_Draw: memset32");
 
 			const float discoGuys = ckdh::saturatef(Rocket::getf(trackDiscoGuys));
 			const float joke = ckdh::saturatef(Rocket::getf(trackCheapJoke));
@@ -705,14 +733,14 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 					if (discoGuys < 1.f)
 					{
 						uint32_t *pStrip = d + yOffs*kResX;
-						Check(ckd_old_blur_h(s_c, pStrip, pStrip, kResX, 128, ckdh::BoxBlurScale((1.f-discoGuys)*ckdh::k2PI*ckdh::kGoldenAngle)), "Demo_Draw: HorizontalBoxBlur32");
+						CKD_DIRECT(ckd_old_blur_h(s_c, pStrip, pStrip, kResX, 128, ckdh::BoxBlurScale((1.f-discoGuys)*ckdh::k2PI*ckdh::kGoldenAngle)), "Demo_Draw: HorizontalBoxBlur32");
 					}
 				}
 				Blit(CKD_BLITADD32A, d + (((kResX-1100)/2)-1) + (yOffs+130)*kResX, s_areWeDone.d, kResX, 1100, 57, discoGuys);
 			}
 			else if (joke > 0.f)
 			{
-				Check(ckd_memset32(s_c, d, 0, kOutputSize), "Demo_Draw: memset32");
+				CKD_DIRECT(ckd_memset32(s_c, d, 0, kOutputSize), "Demo_Draw: memset32");
 				Blit(CKD_BLITSRC32A, d + ((kResX-960)/2) + (((kResY-160)/2)*kResX), s_gpuJoke.d, kResX, 960, 160, joke);
 			}
 		}
@@ -731,6 +759,7 @@ bool Demo_Draw(uint32_t *pDest, float timer, float delta)
 		FadeFlash(d, fadeToBlack, fadeToWhite);
 	}
 
+	FlushChain();
 	ckdhost::EndCompose(pDest);
 	return true;
 }

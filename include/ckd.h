@@ -164,6 +164,10 @@ typedef enum ckd_blend_op {
 	CKD_FADE32 = 14       /* Fade32(dest, n, RGB, alpha)  u_param = alpha<<24 | RGB; src unused util.cpp:798 */
 } ckd_blend_op;
 int ckd_blend(ckd_ctx *ctx, ckd_blend_op op, uint32_t *d_dest, const uint32_t *d_src, unsigned num_pixels, float f_param, unsigned u_param);
+/* the same result as num_steps ckd_blend calls on d_dest, applied per pixel in one pass over the frame (the compositor's
+ * layer stacks, demo.cpp:511-1000).  A step whose source is d_dest itself reads the running pixel. */
+typedef struct ckd_blend_step { ckd_blend_op op; const uint32_t *d_src; float f_param; unsigned u_param; } ckd_blend_step;
+int ckd_blend_chain(ckd_ctx *ctx, uint32_t *d_dest, const ckd_blend_step *steps, unsigned num_steps, unsigned num_pixels);
 
 /* rectangular blits (util.cpp:707-796) */
 typedef enum ckd_blit_op {

@@ -118,3 +118,36 @@ def test_post_properties_4k(live2160):
     assert np.array_equal(ctx.download(d_a, (n,)), first)
     for d in (d_a, d_b, d_c, d_z, d_fx):
         ctx.free(d)
+
+
+def test_blend_chain_equals_sequential_blends(ctx_synth):
+    """ckd_blend_chain: every op of the compositor's layer stacks in one pass == the same ops one launch at a time"""
+    import numpy as np
+    import post_cases as pc
+    from cookiedough_b200 import capi
+    ctx = ctx_synth
+    n = 1280 * 720 - 3  # exercises the scalar tail as well
+    layers = [ctx.to_device(pc.seeded(n + 3, name)) for name in ("noise", "noise2", "smooth")]
+    start = pc.seeded(n + 3, "mix")
+    ops = list(capi.BLEND_OPS)
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        count = [1, 3, 8, 11, 15, 5][trial]
+        steps = []
+        for k in range(count):
+            op = ops[(trial * 5 + k * 3) % len(ops)]
+            src = None if op == "Fade32" else layers[int(rng.integers(0, 3))]
+            f = 0.37 if op == "SoftLight32AA" else 0.0
+            u = 77 if op == "Mix32" else ((200 << 24) | 0x123456) if op == "Fade32" else 0
+            steps.append((op, src, f, u))
+        d_seq = ctx.to_device(start)
+        d_chain = ctx.to_device(start)
+        if trial == 3:
+            steps[4] = (steps[4][0] if steps[4][0] != "Fade32" else "Add32", d_chain, steps[4][2], steps[4][3])  # a source aliasing the destination
+        for op, src, f, u in steps:
+            ctx.blend(op, d_seq, d_seq if src == d_chain else (src or d_seq), n, f, u)
+        ctx.blend_chain(d_chain, steps, n)
+        a = ctx.download(d_seq, (n + 3,))
+        b = ctx.download(d_chain, (n + 3,))
+        assert np.array_equal(a, b), f"trial {trial}: {[s[0] for s in steps]}"
+        assert np.array_equal(b[n:], start[n:]), "wrote past num_pixels"
