@@ -144,7 +144,7 @@ def load():
         "ckd_frame": ([VP], VP), "ckd_fxmap": ([VP, _I], VP), "ckd_render_target": ([VP, _I], VP),
         "ckd_malloc": ([VP, C.POINTER(VP), SZ], _I), "ckd_free": ([VP, VP], _I),
         "ckd_malloc_host": ([C.POINTER(VP), SZ], _I), "ckd_free_host": ([VP], _I),
-        "ckd_upload": ([VP, VP, VP, SZ], _I), "ckd_download": ([VP, VP, VP, SZ], _I), "ckd_copy": ([VP, VP, VP, SZ], _I),
+        "ckd_upload": ([VP, VP, VP, SZ], _I), "ckd_download": ([VP, VP, VP, SZ], _I), "ckd_copy": ([VP, VP, VP, SZ], _I), "ckd_pin_host": ([VP, SZ], _I), "ckd_unpin_host": ([VP], _I),
         "ckd_timer_start": ([VP], _I), "ckd_timer_stop_ms": ([VP, C.POINTER(F)], _I),
         "ckd_set_cos_lut": ([VP, C.POINTER(F)], _I),
         "ckd_set_rsqrt_table": ([VP, _U32P, _I], _I),

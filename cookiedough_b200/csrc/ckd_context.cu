@@ -375,6 +375,22 @@ extern "C" int ckd_free_host(void *h_ptr)
 	return CKD_OK;
 }
 
+// page-lock a caller-owned host buffer in place (the reference allocates pDest with an aligned malloc, main.cpp:307): frame
+// copies into pageable memory go through the driver's staging buffers at a fraction of the PCIe rate
+extern "C" int ckd_pin_host(void *h_ptr, size_t bytes)
+{
+	CKD_REQUIRE(h_ptr && bytes, "null argument");
+	CKD_CUDA(cudaHostRegister(h_ptr, bytes, cudaHostRegisterDefault));
+	return CKD_OK;
+}
+
+extern "C" int ckd_unpin_host(void *h_ptr)
+{
+	CKD_REQUIRE(h_ptr, "null argument");
+	CKD_CUDA(cudaHostUnregister(h_ptr));
+	return CKD_OK;
+}
+
 extern "C" int ckd_upload(ckd_ctx *ctx, void *d_dst, const void *h_src, size_t bytes)
 {
 	CKD_REQUIRE(ctx && d_dst && h_src, "null argument");

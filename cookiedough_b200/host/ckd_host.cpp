@@ -60,6 +60,18 @@ ckd_ctx *CkdHost_Context() { return s_ctx; }
 void CkdHost_SetRocketSource(const char *path) { s_rocketSource = path ? path : ""; }
 void CkdHost_SetTime(double seconds) { s_timeSec = seconds; }
 
+bool CkdHost_PinFrameBuffer(uint32_t *pDest)
+{
+	if (nullptr == s_ctx)
+	{
+		SetLastError("CkdHost_Create() has not been called");
+		return false;
+	}
+	return Check(ckd_pin_host(pDest, size_t(ckd_res_x(s_ctx))*ckd_res_y(s_ctx)*sizeof(uint32_t)), "CkdHost_PinFrameBuffer");
+}
+
+void CkdHost_UnpinFrameBuffer(uint32_t *pDest) { Check(ckd_unpin_host(pDest), "CkdHost_UnpinFrameBuffer"); }
+
 void CkdHost_RegisterImage(const char *path, const void *pixels, int width, int height, int bytesPerPixel)
 {
 	HostImage &img = s_images[path];
@@ -945,6 +957,9 @@ void ckdhost_demo_destroy()
 	Demo_Destroy();
 	CkdHost_Destroy();
 }
+
+int ckdhost_pin_frame_buffer(uint32_t *pDest) { return CkdHost_PinFrameBuffer(pDest) ? 0 : -1; }
+void ckdhost_unpin_frame_buffer(uint32_t *pDest) { CkdHost_UnpinFrameBuffer(pDest); }
 
 void ckdhost_set_pipelined(int enabled) { CkdHost_SetPipelined(0 != enabled); }
 void ckdhost_flush() { CkdHost_Flush(); }

@@ -137,6 +137,14 @@ class Host:
         if rc != 0:
             raise capi.CkdError(f"{op}: {self.L.ckdhost_last_error().decode()}")
 
+    def pin(self, out):
+        """CkdHost_PinFrameBuffer: page-lock a caller-owned numpy frame in place"""
+        if self.L.ckdhost_pin_frame_buffer(C.c_void_p(out.ctypes.data)) != 0:
+            raise capi.CkdError(self.L.ckdhost_last_error().decode())
+
+    def unpin(self, out):
+        self.L.ckdhost_unpin_frame_buffer(C.c_void_p(out.ctypes.data))
+
     def set_pipelined(self, enabled):
         """frame pipelining (CkdHost_SetPipelined): X_Draw returns once enqueued; call flush() before reading the buffers"""
         self.L.ckdhost_set_pipelined(int(bool(enabled)))

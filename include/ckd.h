@@ -61,6 +61,8 @@ int ckd_malloc(ckd_ctx *ctx, void **out_d_ptr, size_t bytes);
 int ckd_free(ckd_ctx *ctx, void *d_ptr);
 int ckd_malloc_host(void **out_h_ptr, size_t bytes); /* pinned */
 int ckd_free_host(void *h_ptr);
+int ckd_pin_host(void *h_ptr, size_t bytes);         /* page-lock a caller-owned buffer in place (e.g. the reference's pDest, main.cpp:307) */
+int ckd_unpin_host(void *h_ptr);
 int ckd_upload(ckd_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);   /* async on the stream */
 int ckd_download(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes); /* async on the stream */
 int ckd_copy(ckd_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);       /* device to device, async on the stream (the compositor's memcpy, demo.cpp:407-449) */

@@ -34,6 +34,11 @@ void CkdHost_SetTime(double seconds);
 // bytesPerPixel 4 = BGRA, 1 = luminance.  The pixels are copied.
 void CkdHost_RegisterImage(const char *path, const void *pixels, int width, int height, int bytesPerPixel);
 
+// Page-locks the caller's frame buffer in place (pDest of main.cpp:307 is an aligned malloc): X_Draw's copy-back then runs at
+// the full PCIe rate instead of through the driver's staging buffers.  Optional; undo before freeing the buffer.
+bool CkdHost_PinFrameBuffer(uint32_t *pDest);
+void CkdHost_UnpinFrameBuffer(uint32_t *pDest);
+
 // Frame pipelining for offline / timeline rendering (not part of the reference's interface).  While enabled, X_Draw returns
 // as soon as the frame is enqueued: pDest is complete after the *second* following X_Draw call or after CkdHost_Flush().
 // The device->host copy of frame i then overlaps the rendering of frame i+1 (two device frame buffers, copy stream).

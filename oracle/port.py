@@ -271,3 +271,292 @@ class Port:
         else:
             raise ValueError(effect)
         return dest
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the compositor: Demo_Draw, code/demo.cpp:469-1023 (BloodBlend/CreditBlend 393-467, FadeFlash 383-390) on top of the
+# primitives above.  T: oracle.rocket.Tracks positioned at the frame's time (Demo_Draw runs Rocket::Boost itself).
+# ---------------------------------------------------------------------------------------------------------------------
+
+_libm = C.CDLL("libm.so.6")
+for _n in ("powf", "fmodf"):
+    getattr(_libm, _n).restype = C.c_float
+    getattr(_libm, _n).argtypes = [C.c_float, C.c_float]
+_libm.sinf.restype = C.c_float
+_libm.sinf.argtypes = [C.c_float]
+
+K_PI = _f32(3.1415926535897932384626433832795)
+K_2PI = _f32(2.0) * K_PI
+K_GOLDEN_RATIO = _f32(1.61803398875)
+K_GOLDEN_ANGLE = _f32(2.39996)
+
+
+def _sat(v):
+    return _f32(max(0.0, min(1.0, float(v))))
+
+
+def _u8(v):
+    """float -> uint8_t as gcc compiles it on x86-64 (cvttss2si, low byte)"""
+    v = float(v)
+    return (int(v) & 0xFF) if -2147483648.0 <= v < 2147483648.0 else 0
+
+
+def _effect_params(effect, T):
+    from cookiedough_b200 import capi
+    cls, names = capi.TRACKS[effect]
+    types = dict(cls._fields_)
+    p = {name: 0 for name, _ in cls._fields_}
+    for field, track in names.items():
+        p[field] = T.geti(track) if types[field] is C.c_int else T.getf(track)
+    return p
+
+
+def _demo_draw(self, time_s, T):
+    A, W, H = self.assets, self.res_x, self.res_y
+    N = W * H
+    T.set_time(time_s)
+    if T.get("demo:quit") != 0.0:
+        return None  # demo is over (code/rocket.cpp:78-79)
+    timer = float(_f32(time_s))
+
+    def layer(path):
+        a = self.buf(A[path].size)
+        a[:] = np.ascontiguousarray(A[path]).ravel()
+        return a
+
+    def effect(name, ckd_effect, close=None):
+        return self.draw(ckd_effect, _effect_params(ckd_effect, T), timer, close=close).reshape(-1)
+
+    def fade_flash(d, to_black, to_white):
+        if to_white > 0.0:
+            self.blend("Fade32", d, None, uparam=(_u8(_f32(to_white) * _f32(255.0)) << 24) | 0xFFFFFF, n=N)
+        if to_black > 0.0:
+            self.blend("Fade32", d, None, uparam=(_u8(_f32(to_black) * _f32(255.0)) << 24), n=N)
+
+    def full(op, d, path, f=0.0):
+        self.blend(op, d, layer(path), fparam=f, n=N)
+
+    def logo_blend(blend, paths, width, height):
+        last = len(paths) - 1
+        factor = _libm.fmodf(C.c_float(blend), C.c_float(1.0))
+        i_factor = _u8(_f32(255.0) * _f32(factor))
+        if blend >= float(last):
+            return layer(paths[last])
+        target = self.buf(N)
+        for i in range(last):
+            if float(i) <= blend < float(i + 1):
+                src = layer(paths[i])
+                target[:src.size] = src
+                self.blend("Mix32", target, layer(paths[i + 1]), uparam=i_factor, n=width * height)
+                break
+        return target
+
+    fade_black, fade_white = T.getf("demo:FadeToBlack"), T.getf("demo:FadeToWhite")
+    part = T.geti("demo:Effect")
+
+    if part == 1:
+        d = effect("twister", "twister")
+        fade_flash(d, fade_black, fade_white)
+        full("SoftLight32A", d, "assets/closeup/Vignette_CoolFilmLook.png")
+        full("MulSrc32A", d, "assets/demo/tpb-06-dirty-vignette-1280x720.png")
+    elif part == 2:
+        d = effect("landscape", "landscape")
+        fade_flash(d, float(_sat(T.getf("demo:ScapeFade"))), 0.0)
+        if T.geti("shootingStar:Enabled") == 1:
+            x, y, alpha = T.geti("shootingStar:X"), T.geti("shootingStar:Y"), _f32(T.getf("shootingStar:A"))
+            lenz = layer("assets/shooting/Lenz.png")
+            self.blit("BlitAdd32A", d[y * W + x:], lenz, W, 64, 64, float(alpha))
+            trail = T.geti("shootingStar:Trail")
+            if trail > 0:
+                alpha_step = _f32(alpha / _f32(trail))
+                for _ in range(trail):
+                    x += 4; y -= 1; alpha = _f32(alpha - alpha_step)
+                    self.blit("BlitAdd32A", d[y * W + x:], lenz, W, 64, 64, float(alpha))
+        overlay = _sat(T.getf("demo:ScapeOverlay"))
+        if overlay != 0.0:
+            self.blit("BlitAdd32A", d, layer("assets/demo/nytrik-god-layer-720p.png"), W, W, H, float(overlay))
+        rev = _sat(T.getf("demo:ScapeRev"))
+        if rev != 0.0:
+            rt0 = self.buf(N)
+            logo = layer("assets/scape/revision-logo_white.png")
+            if rev < _f32(0.314):
+                c4 = _f32(_f32(2.0) * K_PI) / _f32(3.0)
+                if rev == 0.0:
+                    ease_a = _f32(0.0)
+                elif rev == 1.0:
+                    ease_a = _f32(1.0)
+                else:
+                    ease_a = _f32(_f32(_libm.powf(C.c_float(2.0), C.c_float(_f32(-10.0) * rev))) * _f32(_libm.sinf(C.c_float(_f32(_f32(rev * _f32(10.0)) - _f32(0.75)) * c4))) + _f32(1.0))
+                c1 = _f32(1.70158); c3 = _f32(c1 + _f32(1.0))
+                ease_b = _f32(_f32(_f32(_f32(c3 * rev) * rev) * rev) - _f32(_f32(c1 * rev) * rev))
+                self.tape_warp(rt0, logo, W, H, float(_f32(ease_a * K_GOLDEN_ANGLE)), float(_f32(ease_b * K_GOLDEN_RATIO)))
+            else:
+                self.old_blur("hv", rt0, logo, W, H, self.box_blur_scale(float(_f32(_f32(rev - _f32(0.314)) * K_2PI))))
+            self.blit("BlitSrc32A", d, rt0, W, W, H, float(rev))
+        fade_flash(d, fade_black, fade_white)
+        full("SoftLight32A", d, "assets/closeup/Vignette_CoolFilmLook.png")
+    elif part == 3:
+        d = effect("ball", "ball")
+        beams = T.geti("ball:HasBeams") != 0
+        if not beams:
+            full("MulSrc32", d, "assets/greetings/Vignette_CoolFilmLook.png")
+        else:
+            full("SoftLight32", d, "assets/ball/Vignette_Sparta300.png")
+        fade_flash(d, fade_black, fade_white)
+        if beams:
+            full("MulSrc32A", d, "assets/demo/tpb-06-dirty-vignette-1280x720.png")
+    elif part == 4:
+        d = effect("tunnelscape", "tunnelscape")
+        full("Sub32", d, "assets/tunnels/Vignette_Layer02_inverted.png")
+        full("MixSrc32", d, "assets/tunnels/nytrik-TheYearWas_Overlay_LensDirt.png")
+        show = _clampf(0.0, 3.0, T.getf("demo:Show1995"))
+        if show > 0.0:
+            self.blend("MixOver32", d, logo_blend(show, [f"assets/tunnels/layer 1995_{i}.png" for i in range(1, 5)], W, H), n=N)
+        full("Overlay32", d, "assets/tunnels/Vignette_CoolFilmLook.png")
+    elif part == 5:
+        d = effect("plasma", "plasma")
+        i_logo = max(0, min(4, T.geti("demo:CreditLogo")))
+        if i_logo != 0:
+            blend = _clampf(0.0, 4.0, T.getf("demo:CreditAnimBlend"))
+            stem = {1: "assets/credits/animplek/animplek{}.png", 2: "assets/credits/comatron_anim/comatron_{}.png",
+                    3: "assets/credits/jade&nytrik/jade&nytrik{}.png", 4: "assets/credits/animhot0/animhot{}.png"}[i_logo]
+            paths = [stem.format(i + 1 if i_logo == 2 else i) for i in range(5)]
+            cur = logo_blend(blend, paths, 1280, 568)
+            blur_h = T.getf("demo:CreditLogoBlurH")
+            if blur_h != 0.0:
+                rt0 = self.buf(N)
+                self.old_blur("h", rt0, cur, 1280, 568, self.box_blur_scale(blur_h))
+                cur = rt0
+            blur_v = T.getf("demo:CreditLogoBlurV")
+            if blur_v != 0:
+                rt0 = cur if blur_h != 0.0 else self.buf(N)
+                self.old_blur("v", rt0, cur, 1280, 568, self.box_blur_scale(blur_v))
+                cur = rt0
+            self.blit("BlitSrc32A", d[((H - 568) >> 1) * W:], cur, W, 1280, 568, _clampf(0.0, 1.0, T.getf("demo:CreditLogoAlpha")))
+    elif part == 6:
+        d = effect("nautilus", "nautilus")
+        full("SoftLight32", d, "assets/nautilus/Vignette.png")
+        full("SoftLight32", d, "assets/nautilus/GlassDirt_Distorted2.png")
+        fade_flash(d, fade_black, 0.0)
+        first = T.geti("demo:Cousteau") == 0
+        cousteau = layer("assets/nautilus/JacquesCousteau1_Silhouette.png" if first else "assets/nautilus/JacquesCousteau_Silhouette2.png")
+        full("Overlay32A", d, "assets/nautilus/JacquesCousteau1_Silhouette_RimMask.png" if first else "assets/nautilus/JacquesCousteau_Silhouette2_RimMask.png")
+        h_blur = T.getf("demo:CousteauHorzBlur")
+        if h_blur != 0.0:
+            rt0 = self.buf(N)
+            self.old_blur("h", rt0, cousteau, W, H, self.box_blur_scale(h_blur))
+            cousteau = rt0
+        self.blend("MixSrc32", d, cousteau, n=N)
+        fade_flash(d, 0.0, fade_white)
+        full("MixSrc32", d, "assets/nautilus/JacquesCousteau_Text.png")
+    elif part == 7:
+        d = effect("spikey_close", "spikey", close=True)
+        dirt = T.geti("demo:Dirt")
+        if dirt != 1:
+            full("MulSrc32", d, "assets/spikeball/Vignette_CoolFilmLook.png")
+        if dirt == 1:
+            raker = T.getf("closeSpike:Moonraker")
+            raker_text = _clampf(0.0, 2.0, T.getf("closeSpike:MoonrakerText"))
+            if raker > 0.0:
+                full("MulSrc32", d, "assets/closeup/VignetteForRaker.png")
+                full("SoftLight32AA", d, "assets/closeup/raker-LensDirt5_invert.png", raker)
+                text = layer("assets/closeup/raker_textSmall.png")
+                if 0.0 < raker_text < 1.0:
+                    rt2 = self.buf(N)
+                    self.blit("BlitSrc32", rt2[(H - 115) * W:], text, W, 624, 115)
+                    self.blend("SoftLight32AA", d, rt2, fparam=raker_text, n=N)
+                elif raker_text >= 1.0:
+                    raker_blur = _clampf(0.0, 100.0, T.getf("closeSpike:MoonrakerBlur"))
+                    if raker_blur >= 1.0:
+                        rt3 = self.buf(N)
+                        self.old_blur("h", rt3, text, 624, 115, self.box_blur_scale(raker_blur))
+                        text = rt3
+                    self.blit("BlitSrc32", d[(H - 115) * W:], text, W, 624, 115)
+                fade_flash(d, 0.0, fade_white)
+                full("Overlay32", d, "assets/closeup/raker-LensDirt5_invert.png")
+                fade_flash(d, fade_black, 0.0)
+        elif dirt == 2:
+            full("SoftLight32AA", d, "assets/greetings/Bokeh_Lens_Dirt_51.png", float(_f32(0.09) * K_GOLDEN_ANGLE))
+        elif dirt == 3:
+            full("SoftLight32AA", d, "assets/greetings/Bokeh_Lens_Dirt_51.png", float(_f32(0.075) * K_GOLDEN_ANGLE))
+        if dirt != 1:
+            fade_flash(d, fade_black, fade_white)
+    elif part == 8:
+        logo_idx = max(0, min(4, T.geti("demo:MainLogoIndex")))
+        d = effect("spikey_distant", "spikey", close=False)
+        fade_flash(d, fade_black, fade_white)
+        full("SoftLight32", d, "assets/spikeball/SpikeyBall_byPass_BG_Overlay.png")
+        full("Sub32", d, "assets/spikeball/Vignette_Layer02_inverted.png")
+        full("Excl32", d, "assets/spikeball/nytrik-TheYearWas_Overlay_LensDirt.jpg")
+        full("MulSrc32A", d, "assets/demo/tpb-06-dirty-vignette-1280x720.png")
+        if logo_idx != 0:
+            full("MixOver32", d, f"assets/spikeball/Layer 2023_{logo_idx}.png")
+        full("Overlay32", d, "assets/spikeball/Vignette_CoolFilmLook.png")
+    elif part == 9:
+        d = effect("tunnel", "tunnel")
+        full("Sub32", d, "assets/tunnels/Vignette_Layer02_inverted.png")
+        show = _clampf(0.0, 3.0, T.getf("demo:Show2006"))
+        if show > 0.0:
+            self.blend("MixOver32", d, logo_blend(show, [f"assets/tunnels/layer 2006_{i}.png" for i in range(1, 5)], W, H), n=N)
+    elif part == 10:
+        overlay_a = _sat(T.getf("demo:WaterLove"))
+        d = effect("sinuses", "sinuses")
+        overlay = layer("assets/underwater/love prism_alpha 1280_720.png")
+        blur = _clampf(0.0, 100.0, T.getf("demo:LoveBlurHorZ"))
+        if blur != 0.0:
+            rt0 = self.buf(N)
+            self.old_blur("h", rt0, overlay, W, H, self.box_blur_scale(blur))
+            overlay = rt0
+        self.blit("BlitAdd32A", d, overlay, W, W, H, float(overlay_a))
+        if T.geti("demo:Dirt") != 0:
+            full("MulSrc32", d, "assets/underwater/LensDirt3_invert.png")
+        fade_flash(d, fade_black, fade_white)
+    elif part == 11:
+        d = effect("laura", "laura")
+        full("Darken32_50", d, f"assets/greetings/Greetings_Part{T.geti('demo:GreetSwitch') + 1}_BG_Overlay.png")
+        full("SoftLight32", d, "assets/greetings/Bokeh_Lens_Dirt_51.png")
+        self.blit("BlitSrc32", d[24 + (((H - 243) // 2) + 227) * W:], layer("assets/demo/tpb_xbox_tp-263x243.png"), W, 263, 243)
+        full("Overlay32", d, "assets/greetings/Vignette_CoolFilmLook.png")
+    elif part == 12:
+        rt0 = self.buf(N); rt0[:] = 0xFFFFFF
+        if T.geti("demo:FullWarpTPB") == 0:
+            d = self.buf(N); d[:] = 0xFFFFFF
+            rib_x = max(0, min(W, T.geti("demo:RibbonsX")))
+            self.mix_src_s(d, layer("assets/demo/ribbons.png")[rib_x:], W, H - 1, 2160)
+            kind = "h"
+        else:
+            d = effect("plasma", "plasma")
+            kind = "v"
+        full("MixSrc32", rt0, "assets/demo/TPB-logo.png")
+        blur = T.getf("demo:BlurTPB")
+        if blur != 0.0:
+            self.old_blur(kind, rt0, rt0, W, H, self.box_blur_scale(blur))
+        rt1 = self.buf(N)
+        self.tape_warp(rt1, rt0, W, H, T.getf("demo:DistortStrengthTPB"), T.getf("demo:DistortTPB"))
+        self.blend("MixOver32", d, rt1, n=N)
+        full("MulSrc32", d, "assets/nautilus/Vignette.png")
+    elif part == 13:
+        d = self.buf(N)
+        guys, joke = _sat(T.getf("demo:DiscoGuys")), _sat(T.getf("demo:CheapGPU"))
+        if guys > 0.0:
+            x_start, y_offs = (W - 8 * 128) >> 1, ((H - 128) >> 1) + 16
+            for i, name in enumerate(("1", "1b", "2", "2b", "3", "3b", "4", "4b")):
+                t = _sat(T.getf(f"demo:DiscoGuy{i + 1}"))
+                s = _f32(_f32(_f32(t * t) * t) * _f32(_f32(t * _f32(_f32(t * _f32(6.0)) - _f32(15.0))) + _f32(10.0)))   # smootherstepf(0, 1, t)
+                s = _f32(_f32(0.0) + _f32(_f32(_f32(1.0) - _f32(0.0)) * s))
+                self.blit("BlitSrc32A", d[x_start + i * 128 + y_offs * W:], layer(f"assets/demo/tpb-06-disco-guy/{name}.png"), W, 128, 128, float(_f32(guys * s)))
+                if guys < 1.0:
+                    strip = d[y_offs * W:]
+                    self.old_blur("h", strip, strip, W, 128, self.box_blur_scale(float(_f32(_f32(_f32(_f32(1.0) - guys) * K_2PI) * K_GOLDEN_ANGLE))))
+            self.blit("BlitAdd32A", d[(((W - 1100) // 2) - 1) + (y_offs + 130) * W:], layer("assets/demo/are-we-done-1100x57.png"), W, 1100, 57, float(guys))
+        elif joke > 0.0:
+            self.blit("BlitSrc32A", d[((W - 960) // 2) + ((H - 160) // 2) * W:], layer("assets/demo/GPU-joke.png"), W, 960, 160, float(joke))
+    else:
+        raise ValueError(f"demo:Effect {part}: FxBlitter_DrawTestPattern is not restated")
+
+    if part not in (1, 2, 3, 6, 7, 8, 10):
+        fade_flash(d, fade_black, fade_white)
+    return d[:N].reshape(H, W)
+
+
+Port.demo_draw = _demo_draw

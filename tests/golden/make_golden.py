@@ -197,9 +197,12 @@ def demo_cases(out_path):
 
     R = oref.Reference.get(720, Assets(1280, 720, force_synthetic=True), demo=True)
     cases = {}
+    n = R.res_x * R.res_y
+    seed = (np.arange(n, dtype=np.uint32) * np.uint32(2654435761)).reshape(R.res_y, R.res_x)
     for row in DEMO_ROWS:
         time_s = float(np.float32(row / oref.ROW_RATE))
         R.set_time(time_s)
+        R.render_target(0)[:] = seed   # the ball's beam path keeps stale render-target pixels: make every frame history-free
         part = int(round(R.track("demo:Effect")))
         frame = R.demo_draw()
         cases[str(row)] = {"row": row, "time": time_s, "part": part, "sha256": hashlib.sha256(frame.astype("<u4").tobytes()).hexdigest(), "crop": crop_of(frame)}

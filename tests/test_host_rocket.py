@@ -31,30 +31,7 @@ def write_xml(path, tracks):
         f.write('\t</tracks>\n</sync>\n')
 
 
-def py_sync_get_val(keys, row):
-    """track.c:32-60 restated: float key values, double interpolation"""
-    if not keys:
-        return 0.0
-    irow = math.floor(row)
-    idx = -1
-    for i, k in enumerate(keys):
-        if k[0] <= irow:
-            idx = i
-    if idx < 0:
-        return float(np.float32(keys[0][1]))
-    if idx > len(keys) - 2:
-        return float(np.float32(keys[-1][1]))
-    r0, v0, t0 = keys[idx]
-    r1, v1, _ = keys[idx + 1]
-    v0, v1 = np.float32(v0), np.float32(v1)
-    t = (row - r0) / (r1 - r0)
-    if t0 == 0:
-        return float(v0)
-    if t0 == 2:
-        t = t * t * (3 - 2 * t)
-    elif t0 == 3:
-        t = math.pow(t, 2.0)
-    return float(v0) + float(np.float32(v1 - v0)) * t
+from oracle.rocket import sync_get_val as py_sync_get_val  # noqa: E402  (track.c:32-60 restated: float key values, double interpolation)
 
 
 ROWS = [0.0, 0.5, 499.999, 500.0, 1047.9, 1048.0, 2060.25, 3600.0, 4500.5, 5700.0, 6808.3, 7080.0, 7144.75, 8900.0, 9407.0, 10296.0, 10999.0, 12000.0]

@@ -1,6 +1,7 @@
 """The plain-C restatement (oracle/ckd_oracle.c) is pinned against the committed golden fixtures, which are outputs of
 the reference itself (tests/golden/make_golden.py): every effect entry point and every post-chain case."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -86,3 +87,24 @@ def test_port_math_primitives(port):
     L.orc_cspan16(out.ctypes.data_as(C.c_void_p), 1, 8, 4, 0xFF102030, 0x00F0E0D0)
     assert [hex(v) for v in out[:4]] == ["0xff002000", "0xdf003800", "0xbf005008", "0x9f00681c"]
     assert L.orc_rsqrt(C.c_float(1.0)) == pytest.approx(float.fromhex("0x1.ffep-1"), abs=0)
+
+
+def test_port_compositor_matches_golden_frames(port):
+    """Demo_Draw restated on the plain-C primitives (oracle/port.py, code/demo.cpp:469-1023) against the compiled reference's
+    composed frames: every part and every optional layer of the timeline"""
+    import json
+    from conftest import GOLDEN
+    from oracle.rocket import Tracks
+    with open(os.path.join(GOLDEN, "golden_demo_720.json")) as f:
+        frames = json.load(f)["frames"]
+    T = Tracks.from_json(os.path.join(GOLDEN, "tracks.json"))
+    seed = (np.arange(1280 * 720, dtype=np.uint32) * np.uint32(2654435761)).reshape(720, 1280)
+    bad = []
+    for key, case in frames.items():
+        port.render_target0[:] = seed
+        frame = port.demo_draw(case["time"], T)
+        if frame is None:
+            frame = np.zeros((720, 1280), dtype=np.uint32)  # demo over: Demo_Draw returns false, the frame stays untouched
+        if sha256_u32(frame) != case["sha256"]:
+            bad.append(f"row {key} part {case['part']}")
+    assert not bad, bad
