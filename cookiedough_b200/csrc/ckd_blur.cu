@@ -125,6 +125,36 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 constexpr int kBlurWarps = 4;                   // warps per CTA: one per SM sub-partition (a 1-warp CTA always lands on sub-partition 0)
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: used where a CTA stages one long contiguous run
+//      (a whole line of the new blur).  The old blur's rings are filled 256 bytes per line and stage: there a TMA variant (eight
+//      bulk copies per stage from warp 0, one mbarrier per ring slot) measured 10-25 % slower than 128 threads x cp.async,
+//      see profiles/r01_notes.md. ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smemDst, const void *gmemSrc, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_u32(smemDst)), "l"(gmemSrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+	unsigned done;
+	do
+	{
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	}
+	while (0 == done);
+}
+
 template <bool B> struct BoolTag { static constexpr bool value = B; };
 
 // KM: the kernel median when it is < 8 and the blur runs in place (trailing edge from registers); 0: any width (from the ring)
@@ -878,7 +908,7 @@ __device__ __forceinline__ unsigned scale_fp22(float value)
 // accumulator in front of output k is
 //     iSum0 + P(iSpan + 1 + min(k, len - iSpan)) - P(iSpan + 1) - P(max(k - iSpan, 0)),
 // iSum0 = px[0] + ... + px[iSpan-1] + ((px[iSpan]*alpha16) >> 16) (boxblur.cpp:150-157).  One CTA owns one line: the line is
-// staged in shared memory with coalesced loads, every thread folds a chunk of consecutive E into a local prefix, a block
+// staged in shared memory by one TMA bulk copy (cp.async.bulk + mbarrier), every thread folds a chunk of consecutive E into a local prefix, a block
 // scan offsets the chunks, and the outputs -- two 16-byte prefix reads, the 10:22 scale, the pack -- go out coalesced.
 // Lines are contiguous (vertical passes run on a transposed copy, like the reference's own Transpose32 round trip,
 // boxblur.cpp:215-299), so the two elements the reference reads past the end of a line (boxblur.cpp:171,185) are simply the
@@ -888,32 +918,52 @@ constexpr int kNewBlurThreads = 256;
 __global__ void __launch_bounds__(kNewBlurThreads) new_blur_line_kernel(uint32_t *__restrict__ pDest, const uint32_t *__restrict__ pSrc, unsigned numLines, unsigned len, NewBlurSetup s)
 {
 	extern __shared__ __align__(16) uint8_t s_mem[];
-	// element m of either array lives at slot m + (m >> 4): a thread walks consecutive elements, neighbouring threads start a
-	// chunk apart, and the extra slot per 16 elements keeps their accesses on different banks
-	auto slot = [](unsigned m) -> unsigned { return m + (m >> 4); };
-	int4 *s_P = reinterpret_cast<int4 *>(s_mem);                          // P(0..len+1)
-	uint32_t *s_px = reinterpret_cast<uint32_t *>(s_P + slot(len + 2) + 1); // px[0..len+1]
+	uint32_t *s_px = reinterpret_cast<uint32_t *>(s_mem);                                   // px[0..len+1] (+2 of slack), contiguous: TMA destination
+	int4 *s_P = reinterpret_cast<int4 *>(s_mem + ((size_t(len) + 4)*4 + 15 & ~size_t(15))); // P(0..len+1)
 	__shared__ int4 s_warpTotals[kNewBlurThreads/32];
-	__shared__ int s_first[4];                                            // px[0] + ... + px[iSpan-1] per channel
+	__shared__ int s_first[4];                                                              // px[0] + ... + px[iSpan-1] per channel
+	__shared__ __align__(8) uint64_t s_bar;
 
 	const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const unsigned line = blockIdx.x;
 	const size_t total = size_t(numLines)*len, base = size_t(line)*len;
 
+	// the line and the two elements behind it: one TMA bulk copy when the run is 16-byte aligned and inside the buffer
+	const unsigned runElems = (len + 2 + 3) & ~3u;
+	const bool tma = 0 == ((reinterpret_cast<uintptr_t>(pSrc + base)) & 15) && base + runElems <= total;
 	if (tid < 4) s_first[tid] = 0;
-	for (unsigned i = tid; i < len + 2; i += kNewBlurThreads)
-		s_px[slot(i)] = (base + i < total) ? pSrc[base + i] : 0u;
-	__syncthreads();
+	if (tma)
+	{
+		if (0 == tid)
+		{
+			mbar_init(&s_bar, 1);
+			mbar_fence_init();
+		}
+		__syncthreads();
+		if (0 == tid)
+		{
+			mbar_arrive_expect_tx(&s_bar, runElems*4);
+			bulk_load(s_px, pSrc + base, runElems*4, &s_bar);
+		}
+		mbar_wait(&s_bar, 0);
+	}
+	else
+	{
+		for (unsigned i = tid; i < len + 2; i += kNewBlurThreads)
+			s_px[i] = (base + i < total) ? pSrc[base + i] : 0u;
+		__syncthreads();
+	}
 
-	// chunk of consecutive elements per thread: E(m) for m in [m0, m1), local exclusive prefix into s_P
-	const unsigned perThread = (len + 1 + kNewBlurThreads - 1)/kNewBlurThreads; // E(0..len) -> P(0..len+1)
+	// chunk of consecutive elements per thread: E(m) for m in [m0, m1), local exclusive prefix into s_P.  The chunk length is
+	// odd: neighbouring threads then start an odd number of words (px) / of 16-byte entries (P) apart: no bank conflicts
+	const unsigned perThread = ((len + 1 + kNewBlurThreads - 1)/kNewBlurThreads) | 1u; // E(0..len) -> P(0..len+1)
 	const unsigned m0 = min(tid*perThread, len + 1), m1 = min(m0 + perThread, len + 1);
 	int4 run = make_int4(0, 0, 0, 0), first = make_int4(0, 0, 0, 0);
-	uint32_t A = (m0 < m1) ? s_px[slot(m0)] : 0u;
+	uint32_t A = (m0 < m1) ? s_px[m0] : 0u;
 	for (unsigned m = m0; m < m1; ++m)
 	{
-		const uint32_t B = s_px[slot(m + 1)];
-		s_P[slot(m)] = run;
+		const uint32_t B = s_px[m + 1];
+		s_P[m] = run;
 		const int a0 = int(A & 0xff), a1 = int((A >> 8) & 0xff), a2 = int((A >> 16) & 0xff), a3 = int(A >> 24);
 		const int b0 = int(B & 0xff), b1 = int((B >> 8) & 0xff), b2 = int((B >> 16) & 0xff), b3 = int(B >> 24);
 		run.x += a0 + (((b0 - a0)*s.iAlpha) >> 16);
@@ -946,17 +996,17 @@ __global__ void __launch_bounds__(kNewBlurThreads) new_blur_line_kernel(uint32_t
 	}
 	for (unsigned m = m0; m < m1; ++m)
 	{
-		int4 v = s_P[slot(m)];
+		int4 v = s_P[m];
 		v.x += offset.x; v.y += offset.y; v.z += offset.z; v.w += offset.w;
-		s_P[slot(m)] = v;
+		s_P[m] = v;
 	}
 	if (m1 == len + 1 && m0 < m1) // the thread that owns the last E also provides P(len + 1)
-		s_P[slot(len + 1)] = make_int4(offset.x + run.x, offset.y + run.y, offset.z + run.z, offset.w + run.w);
+		s_P[len + 1] = make_int4(offset.x + run.x, offset.y + run.y, offset.z + run.z, offset.w + run.w);
 	__syncthreads();
 
 	// outputs
-	const uint32_t pivot = s_px[slot(s.iSpan)];
-	int4 sum0 = s_P[slot(s.iSpan + 1)]; // subtracted below
+	const uint32_t pivot = s_px[s.iSpan];
+	int4 sum0 = s_P[s.iSpan + 1]; // subtracted below
 	sum0.x = s_first[0] + ((int(pivot & 0xff)*s.iAlpha) >> 16) - sum0.x;
 	sum0.y = s_first[1] + ((int((pivot >> 8) & 0xff)*s.iAlpha) >> 16) - sum0.y;
 	sum0.z = s_first[2] + ((int((pivot >> 16) & 0xff)*s.iAlpha) >> 16) - sum0.z;
@@ -964,8 +1014,8 @@ __global__ void __launch_bounds__(kNewBlurThreads) new_blur_line_kernel(uint32_t
 
 	for (unsigned k = tid; k < len; k += kNewBlurThreads)
 	{
-		const int4 hi = s_P[slot(s.iSpan + 1 + min(k, len - s.iSpan))];
-		const int4 lo = s_P[slot((k > s.iSpan) ? k - s.iSpan : 0)];
+		const int4 hi = s_P[s.iSpan + 1 + min(k, len - s.iSpan)];
+		const int4 lo = s_P[(k > s.iSpan) ? k - s.iSpan : 0];
 		unsigned scale = s.iScale;
 		if (k < s.iSpan) scale = scale_fp22(s.halfScale + float(k)*s.dScale);                        // boxblur.cpp:160-174
 		else if (k >= len - s.iSpan) scale = scale_fp22(s.halfScale + float(len - 1 - k)*s.dScale);  // boxblur.cpp:196-207
@@ -1027,8 +1077,7 @@ static int NewBlurPasses(ckd_ctx *ctx, uint32_t *d_a, uint32_t *d_b, const uint3
 	s.halfScale = scale*0.5f;
 	s.dScale = s.halfScale/float(iSpan);
 
-	const size_t slots = size_t(lineLen + 2) + ((lineLen + 2) >> 4) + 2;
-	const size_t smem = slots*(sizeof(int4) + sizeof(uint32_t));
+	const size_t smem = ((size_t(lineLen) + 4)*4 + 15 & ~size_t(15)) + (size_t(lineLen) + 2)*sizeof(int4);
 	CKD_REQUIRE(smem <= 200*1024, "line too long for the blur's shared-memory staging");
 	if (!ctx->newBlurAttrSet)
 	{
