@@ -458,19 +458,22 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 	constexpr unsigned kStep = 4;
 	const unsigned laneBase = r*kPitchH + chan;
 
-	// the first 128 threads move the 64 steps starting at p0 between global memory and the rings: 16 bytes each along a row
-	// (horizontal), or 4 x 4 bytes, one image row each, 8 neighbouring columns per row (vertical)
+	// 128 work items move the 64 steps starting at p0 between global memory and the rings: 16 bytes each along a row
+	// (horizontal), or 4 x 4 bytes, one image row each, 8 neighbouring columns per row (vertical).  A CTA has 64 to 512
+	// threads: item w is handled by thread w, w - blockDim.x, ...
+	constexpr unsigned kThreads = 32u << LOG2P;
 	auto loadStage = [&](unsigned p0)
 	{
-		if (tid < 128)
+		#pragma unroll
+		for (unsigned w = tid; w < 128; w += kThreads)
 		{
 			if (VERT)
 			{
-				const unsigned col = tid & 7, line = line0 + col;
+				const unsigned col = w & 7, line = line0 + col;
 				#pragma unroll
 				for (unsigned k = 0; k < 4; ++k)
 				{
-					const unsigned pos = p0 + (tid >> 3) + k*16;
+					const unsigned pos = p0 + (w >> 3) + k*16;
 					const bool valid = pos < len && line < numLines;
 					const uint8_t *src = valid ? pDest + (size_t(pos)*pitch + line)*4 : pDest;
 					cp_async4(s_in + col*kPitchH + (pos & (kRing-1))*4, src, valid);
@@ -480,39 +483,40 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 			}
 			else
 			{
-				const unsigned pos = p0 + (tid & 15)*4, line = line0 + (tid >> 4);
+				const unsigned pos = p0 + (w & 15)*4, line = line0 + (w >> 4);
 				const bool valid = pos < len && line < numLines;
 				const uint8_t *src = valid ? pDest + (size_t(line)*pitch + pos)*4 : pDest;
-				cp_async16(s_in + (tid >> 4)*kPitchH + (pos & (kRing-1))*4, src, valid);
+				cp_async16(s_in + (w >> 4)*kPitchH + (pos & (kRing-1))*4, src, valid);
 				if ((pos & (kRing-1)) < kMirror)
-					cp_async16(s_in + (tid >> 4)*kPitchH + (kRing + (pos & (kRing-1)))*4, src, valid);
+					cp_async16(s_in + (w >> 4)*kPitchH + (kRing + (pos & (kRing-1)))*4, src, valid);
 			}
 		}
 	};
 	auto flushStage = [&](unsigned p0)
 	{
-		if (tid < 128)
+		#pragma unroll
+		for (unsigned w = tid; w < 128; w += kThreads)
 		{
 			if (VERT)
 			{
-				const unsigned col = tid & 7, line = line0 + col;
+				const unsigned col = w & 7, line = line0 + col;
 				uint32_t v[4];
 				#pragma unroll
 				for (unsigned k = 0; k < 4; ++k)
-					v[k] = *reinterpret_cast<const uint32_t *>(s_out + col*kPitchH + ((p0 + (tid >> 3) + k*16) & (kRing-1))*4);
+					v[k] = *reinterpret_cast<const uint32_t *>(s_out + col*kPitchH + ((p0 + (w >> 3) + k*16) & (kRing-1))*4);
 				#pragma unroll
 				for (unsigned k = 0; k < 4; ++k)
 				{
-					const unsigned pos = p0 + (tid >> 3) + k*16;
+					const unsigned pos = p0 + (w >> 3) + k*16;
 					if (pos < len && line < numLines)
 						*reinterpret_cast<uint32_t *>(pDest + (size_t(pos)*pitch + line)*4) = v[k];
 				}
 			}
 			else
 			{
-				const unsigned pos = p0 + (tid & 15)*4, line = line0 + (tid >> 4);
+				const unsigned pos = p0 + (w & 15)*4, line = line0 + (w >> 4);
 				if (pos < len && line < numLines)
-					*reinterpret_cast<uint4 *>(pDest + (size_t(line)*pitch + pos)*4) = *reinterpret_cast<const uint4 *>(s_out + (tid >> 4)*kPitchH + (pos & (kRing-1))*4);
+					*reinterpret_cast<uint4 *>(pDest + (size_t(line)*pitch + pos)*4) = *reinterpret_cast<const uint4 *>(s_out + (w >> 4)*kPitchH + (pos & (kRing-1))*4);
 			}
 		}
 	};
@@ -732,9 +736,10 @@ template <bool VERT, bool SUBEDGES>
 static cudaError_t LaunchBlocked(ckd_ctx *ctx, uint8_t *p, unsigned numLines, unsigned len, unsigned pitch, const OldBlurSetup &s)
 {
 	// Shape of a block: P = 1 << log2P lanes per line-channel, QT = ceil(kM/P) steps each.  Measured on B200 at 4K the fewest
-	// parts that keep QT <= 8 win: every extra scan round costs more than the warps it adds hide.
+	// parts that keep QT <= 8 win: every extra scan round costs more than the warps it adds hide (two parts up to a median of
+	// 13, four up to 32, ...).
 	const unsigned blocks = ckd_div_up(numLines, 8), kM = s.kernelMedian;
-	const unsigned log2P = (kM <= 32) ? 2 : (kM <= 64) ? 3 : 4;
+	const unsigned log2P = (kM <= 13) ? 1 : (kM <= 32) ? 2 : (kM <= 64) ? 3 : 4;
 	const int qt = int((kM + (1u << log2P) - 1) >> log2P); // every lane then owns qt or qt - 1 steps
 
 	const size_t smem = 2*kRingBytes;
@@ -743,6 +748,7 @@ static cudaError_t LaunchBlocked(ckd_ctx *ctx, uint8_t *p, unsigned numLines, un
 		case 5: CKD_BLOCKED(LOG2P, 5); break; case 6: CKD_BLOCKED(LOG2P, 6); break; case 7: CKD_BLOCKED(LOG2P, 7); break; default: CKD_BLOCKED(LOG2P, 8); break; }
 	switch (log2P)
 	{
+	case 1: CKD_BLOCKED_QT(1); break;
 	case 2: CKD_BLOCKED_QT(2); break;
 	case 3: CKD_BLOCKED_QT(3); break;
 	default: CKD_BLOCKED_QT(4); break;
