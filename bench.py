@@ -431,7 +431,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
             "config": {"workload": "effect-suite-4k", "res": [RES_X, RES_Y], "effects": [s[0] for s in SUITE], "rows": [s[4] for s in SUITE],
                        "streams": n_streams,
-                       "assets": "procedural stand-ins" if assets.synthetic else "reference art (oracle/_ref/assets.npz)",
+                       "assets": "procedural stand-ins" if assets.synthetic else "reference art (refdata/assets.npz)",
                        "l2": f"no explicit flush: one step streams ~{working_set_mb:.0f} MB (frames, render targets, polar maps, textures) through the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                     "api": "X_Draw(uint32_t *pDest, float time, float delta) of include/ckd_host.h, pinned host pDest, synchronous (drop-in semantics)",
@@ -566,7 +566,7 @@ def run_timeline(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
             "config": {"workload": "timeline-4k", "frames": args.frames, "res": [RES_X, RES_Y], "api": "Demo_Draw (effect + the part's layers, composed on the device)",
                        "sharding": "frame i -> rank i mod N, no data-path collective",
-                       "assets": "procedural stand-ins" if assets.synthetic else "reference art (oracle/_ref/assets.npz), layers nearest-upscaled x3"},
+                       "assets": "procedural stand-ins" if assets.synthetic else "reference art (refdata/assets.npz), layers nearest-upscaled x3"},
             "e2e": {"value": px / e2e_s / 1e6, "unit": "Mpixel/s", "fps": args.frames / e2e_s, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": args.frames * frame_bytes, "pipelined_value": px / e2e_pipe_s / 1e6, "pipelined_fps": args.frames / e2e_pipe_s},
             "gpu_launches": int(launches), "frame_checksums_crc32": {str(i): c for i, c in enumerate(sums) if c}}))

@@ -3,7 +3,7 @@
 The reference decodes its art with DevIL (code/image.cpp:31-73: 32-bit BGRA or 8-bit luminance, upper-left
 origin).  Decoding is outside the hot path, so the harness works on pre-decoded arrays:
 
-* ``oracle/_ref/assets.npz`` (written by ``oracle/build_ref.py`` from the reference's ``target/assets``) when present,
+* ``refdata/assets.npz`` (written by ``oracle/build_ref.py`` from the reference's ``target/assets``) when present,
 * deterministic procedural stand-ins of the same shapes otherwise (so tests can run from a bare checkout).
 
 Resolution rules for builds other than 1280x720: output-sized art is
@@ -95,7 +95,7 @@ SPEC.update(DEMO_SPEC)
 
 
 def default_npz_path():
-    return os.environ.get("CKD_ASSETS", os.path.join(_REPO, "oracle", "_ref", "assets.npz"))
+    return os.environ.get("CKD_ASSETS", os.path.join(_REPO, "refdata", "assets.npz"))
 
 
 def _nearest_resize(arr, new_h, new_w):

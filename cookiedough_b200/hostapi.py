@@ -41,9 +41,9 @@ def _lib():
 
 
 def default_rocket_source():
-    """the demo's Rocket project: the XML shipped with the reference when oracle/_ref/data holds a copy"""
+    """the demo's Rocket project: the XML shipped with the reference when refdata/ holds a copy (oracle/build_ref.py)"""
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    return os.environ.get("CKD_ROCKET", os.path.join(here, "oracle", "_ref", "data", "directors-cut.rocket"))
+    return os.environ.get("CKD_ROCKET", os.path.join(here, "refdata", "directors-cut.rocket"))
 
 
 class RocketOnly:

@@ -7,11 +7,12 @@ Compiles the reference's own hot-path translation units from where they lie unde
     oracle/_ref/libckd_ref_720.so     (kResX x kResY = 1280 x 720, the reference as shipped)
     oracle/_ref/libckd_ref_2160.so    (3840 x 2160, resolution constants patched)
 
-and prepares the shared input data next to them (git-ignored, but shipped to the GPU box):
+and prepares the reference's input data in refdata/ at the repository root (git-ignored, but shipped to the GPU box; these
+are inputs -- timeline and art -- that the product reads as well, so they do not live under oracle/):
 
-    oracle/_ref/data/sync/*.track           binary GNU Rocket tracks (target/sync)
-    oracle/_ref/data/directors-cut.rocket   the XML Rocket project (target/directors-cut.rocket)
-    oracle/_ref/assets.npz                  art/maps decoded once with Pillow (BGRA / L8), shared by both sides
+    refdata/sync/*.track            binary GNU Rocket tracks (target/sync)
+    refdata/directors-cut.rocket    the XML Rocket project (target/directors-cut.rocket)
+    refdata/assets.npz              art/maps decoded once with Pillow (BGRA / L8), shared by both sides
 
 Patch list (applied on the fly to a throw-away symlink tree in a temp dir):
     P1  fx-blitter.cpp:48-49   _mm_load_si128 on a 4-byte aligned address -> _mm_loadu_si128 (x86 #GP)
@@ -34,6 +35,7 @@ from concurrent.futures import ThreadPoolExecutor
 REF = os.environ.get("CKD_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
+DATA = os.path.join(os.path.dirname(HERE), "refdata")   # decoded inputs of the reference: used by the product too, so not under oracle/
 
 CPP_UNITS = [
     "shadertoy.cpp", "landscape.cpp", "tunnelscape.cpp", "ball.cpp", "torus-twister.cpp",
@@ -133,7 +135,7 @@ def build_lib(res_x, res_y):
 
 
 def prepare_data():
-    data = os.path.join(OUT, "data")
+    data = DATA
     sync = os.path.join(data, "sync")
     os.makedirs(sync, exist_ok=True)
     src_sync = os.path.join(REF, "target", "sync")
@@ -157,7 +159,8 @@ def prepare_assets():
             arr = np.ascontiguousarray(rgba[..., [2, 1, 0, 3]])  # -> B,G,R,A bytes == little-endian 0xAARRGGBB (code/image.cpp:53-54)
             arr = arr.view(np.uint32).reshape(arr.shape[0], arr.shape[1])
         arrays[path] = arr
-    np.savez_compressed(os.path.join(OUT, "assets.npz"), **arrays)
+    os.makedirs(DATA, exist_ok=True)
+    np.savez_compressed(os.path.join(DATA, "assets.npz"), **arrays)
 
 
 def main():

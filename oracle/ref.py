@@ -11,7 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
-DATA_DIR = os.path.join(REF_DIR, "data")
+DATA_DIR = os.path.join(os.path.dirname(HERE), "refdata")   # sync/*.track, directors-cut.rocket, assets.npz (oracle/build_ref.py)
 
 ROW_RATE = (170.0 / (60.0 * (170.0 / 174.0))) * 16.0  # code/audio.cpp:18 (= 46.4 rows/s)
 

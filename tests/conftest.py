@@ -73,7 +73,7 @@ def ctx_synth(synth_assets, golden_rsqrt):
 
 
 def _live(res_y):
-    """(Reference, Context) pair sharing the same assets (the reference's art when oracle/_ref/assets.npz exists) and the
+    """(Reference, Context) pair sharing the same assets (the reference's art when refdata/assets.npz exists) and the
     host CPU's own RSQRTPS table, or None when the compiled reference is not available"""
     from oracle import ref as oref
     if not oref.available(res_y):

@@ -114,7 +114,7 @@ def test_demo_draw_4k_child_process():
     if not oref.available(2160):
         pytest.skip("oracle/_ref not built")
     rows = "450,1500,2364,4246,5700,6684,7882,9410,9980"
-    r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "demo_parity.py"), "--res", "2160", "--rows", rows],
+    r = subprocess.run([sys.executable, os.path.join(REPO, "tests", "tools", "demo_parity.py"), "--res", "2160", "--rows", rows],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:]
     worst = [line for line in r.stdout.splitlines() if line.startswith("worst exact %")]

@@ -2,8 +2,9 @@
 """micro-benchmark + parity of the box blurs against the compiled reference (needs a GPU and oracle/_ref)"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
 from cookiedough_b200 import capi
 from cookiedough_b200.assets import Assets
 from oracle import ref as oref

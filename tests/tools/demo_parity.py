@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
 """Demo_Draw parity: the composed frame of every part (CUDA host layer) against the compiled reference's Demo_Draw.
 
-    python tools/demo_parity.py [--res 720|2160] [--rows r0,r1,...] [--frames N]
+    python tests/tools/demo_parity.py [--res 720|2160] [--rows r0,r1,...] [--frames N]
 """
 import argparse, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, REPO)
 from cookiedough_b200 import hostapi
 from cookiedough_b200.assets import Assets
 from oracle import ref as oref

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Parity + timing report: every effect and post op, CUDA path (C ABI) vs the compiled reference (oracle/_ref).
 
-    python tools/parity_report.py [--res 720|2160|both] [--json out.json]
+    python tests/tools/parity_report.py [--res 720|2160|both] [--json out.json]
 
 Needs a B200 (CUDA side) and oracle/_ref (reference side).  Prints one line per case:
 exact-pixel %, max channel delta, % within 1/2 LSB, GPU ms (CUDA events, median of 5) and CPU ms.
@@ -14,7 +14,8 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, REPO)
 
 from cookiedough_b200 import capi  # noqa: E402
 from cookiedough_b200.assets import Assets  # noqa: E402
