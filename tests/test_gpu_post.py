@@ -151,3 +151,27 @@ def test_blend_chain_equals_sequential_blends(ctx_synth):
         b = ctx.download(d_chain, (n + 3,))
         assert np.array_equal(a, b), f"trial {trial}: {[s[0] for s in steps]}"
         assert np.array_equal(b[n:], start[n:]), "wrote past num_pixels"
+
+
+@pytest.mark.parametrize("kind", ["h", "v"])
+def test_old_blur_every_kernel_size_in_place(live720, kind):
+    """every kernel width 1..255 (each one picks its own kernel: register trailing edge, serial walk, or a scan shape P x QT)
+    against the live reference, in place, on images whose lines are just long enough for the widest kernel"""
+    from oracle.ref import aligned_u32
+    R, ctx = live720
+    w, h = (704, 40) if kind == "h" else (64, 520)
+    n = w * h
+    src = pc.seeded(n, "noise") | np.uint32(0x40404040)   # bright enough to reach the 16-bit saturation for wide kernels
+    d = ctx.to_device(src, pad_elems=4 * w)
+    bad = []
+    for span in range(1, 256):
+        strength = span / 255.0
+        ref = aligned_u32(n, pad=4 * w)
+        ref[:] = src
+        R.old_blur(kind, ref, ref, w, h, strength)
+        ctx.upload(d, src)
+        ctx.old_blur(kind, d, d, w, h, strength)
+        if not np.array_equal(ctx.download(d, (n,)), ref):
+            bad.append(span)
+    ctx.free(d)
+    assert not bad, f"old_blur_{kind} in place differs for kernel spans {bad}"
