@@ -144,3 +144,35 @@ def test_render_demo_stream_matches_demo_draw(tmp_path):
             assert np.array_equal(sink.read_frame(path, i), out), f"frame {i}"
     finally:
         host.close()
+
+
+def test_demo_draw_unknown_part_draws_the_test_pattern(tmp_path):
+    """demo:Effect outside 1..13 -> FxBlitter_DrawTestPattern (code/demo.cpp:1000-1001, fx-blitter.cpp:77-98) + the post fade;
+    driven through a hand-written Rocket project, so this also covers Demo_Create on a caller-supplied .rocket file"""
+    import json
+    from test_host_rocket import write_xml
+    from cookiedough_b200 import hostapi
+    from cookiedough_b200.assets import Assets
+    with open(os.path.join(GOLDEN, "tracks.json")) as f:
+        tracks = json.load(f)["tracks"]
+    tracks["demo:Effect"] = [[0, 0.0, 0]]
+    tracks["demo:FadeToBlack"] = [[0, 0.25, 0]]
+    tracks["demo:FadeToWhite"] = [[0, 0.0, 0]]
+    xml = tmp_path / "pattern.rocket"
+    write_xml(xml, tracks)
+    host = hostapi.Host(1280, 720, 0, Assets(1280, 720, force_synthetic=True), rocket_source=xml, demo=True)
+    try:
+        ctx = host.context()
+        out = np.zeros((720, 1280), dtype=np.uint32)
+        assert host.demo_draw(out, 1.0)
+        fx_y, fx_x = 720 // 2 + 4, 1280 // 2 + 4
+        iy, ix = np.mgrid[0:fx_y, 0:fx_x]
+        pattern = np.where(iy < fx_y // 2, np.where(iy & 1, 0xFFFFFFFF, 0), np.where(ix & 1, 0xFFFFFFFF, 0)).astype(np.uint32)
+        d_fx = ctx.to_device(pattern, pad_elems=4 * 1280)
+        ctx.fx_blit_2x2(ctx.frame(), d_fx)
+        ctx.blend("Fade32", ctx.frame(), ctx.frame(), 1280 * 720, 0.0, (int(np.float32(0.25) * np.float32(255.0)) << 24))
+        assert np.array_equal(out, ctx.read_frame())
+        assert out.any() and not (out == out.flat[0]).all()
+        ctx.free(d_fx)
+    finally:
+        host.close()
