@@ -174,10 +174,24 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """The reference parallelises with OpenMP.  torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the reference
+    on one core: give it every core this process may run on (omp_set_num_threads on the already loaded runtime)."""
+    n = cpu_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    use_all_host_threads()
     R, step = reference_suite_runner()
     base = {"impl": "reference", "metric": "Mpixel/s", "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
@@ -409,6 +423,7 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference itself on the host cores ---------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        use_all_host_threads()
         R, ref_step = reference_suite_runner()
         if ref_step is not None:
             ref_step()
@@ -461,6 +476,7 @@ def timeline_reference(args):
         base["unavailable"] = "oracle/_ref (compiled reference) is not present in this checkout"
         print(json.dumps(base))
         return 0
+    use_all_host_threads()
     R = oref.Reference.get(RES_Y, Assets(RES_X, RES_Y), demo=True)
     times = sharding.timeline_times(args.frames)
     stride = max(1, args.frames // 40)
