@@ -132,6 +132,31 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(local):
+    """one process per GPU: keep the process (and with it the pinned frame buffers it allocates and the copies it drives) on the
+    CPU cores of the GPU's own NUMA node.  Returns the number of cores bound to, or None when the topology is not exposed."""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(local)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def dist_setup(n_gpus):
     # rank 0 must print exactly one JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -143,6 +168,7 @@ def dist_setup(n_gpus):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        bind_to_gpu_numa(local)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
         return rank, world, local, dist
     return rank, world, local, None
