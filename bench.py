@@ -47,11 +47,15 @@ SUITE = [
 ]
 PIXELS_PER_STEP = len(SUITE) * RES_X * RES_Y
 
-# mean FP32 operations per FX-map pixel at the pinned rows (instrumented-oracle estimate; 1 op = one
-# FP add/mul/cvt/cmp, no FMA contraction) -- denominators for the raymarch kernels' FP32 roofline
+# FP operations per FX-map pixel at the pinned rows (SURVEY.md 8d asks for the measured mean, not the <= bound): MEASURED on
+# the B200 as executed thread-level FP instructions of one 4K launch of each kernel (tools/count_fp_ops.py ->
+# profiles/r01_fp_ops.json).  The kernels execute the reference's float operations one for one (no FMA contraction), so this
+# is the algorithmic count; 1 op = one FP add / mul / compare / min-max / MUFU / conversion, FP64 ops of powf/expf likewise.
+# FFMA instructions are NOT counted (they only occur in the IEEE division / sqrt refinement sequences that stand for one
+# divss / sqrtss of the reference, whose MUFU seed is the one op counted), which makes the fractions conservative.
 FLOP_PER_FX_PIXEL = {
-    "raymarch_plasma": 1.7e3, "raymarch_nautilus": 2.2e3, "raymarch_spikey_close": 1.7e3, "raymarch_spikey_distant": 1.8e3,
-    "raymarch_spikey_spec": 1.9e3, "raymarch_sinuses": 2.7e3, "raymarch_laura": 1.7e3, "raymarch_tunnel": 0.25e3,
+    "raymarch_plasma": 1461.0, "raymarch_nautilus": 1814.0, "raymarch_spikey_close": 1673.0, "raymarch_spikey_distant": 1688.0,
+    "raymarch_sinuses": 2490.0, "raymarch_laura": 1494.0, "raymarch_tunnel": 268.0,
 }
 
 
