@@ -152,7 +152,7 @@ def load():
         "ckd_set_polar_maps": ([VP, VP, VP], _I), "ckd_get_polar_maps": ([VP, VP, VP], _I),
         "ckd_set_image": ([VP, _I, VP, _I, _I, _I], _I), "ckd_get_image": ([VP, _I], VP),
         "ckd_fx_blit_2x2": ([VP, VP, VP], _I),
-        "ckd_polar_blit": ([VP, VP, VP, _I], _I), "ckd_polar_blit_a": ([VP, VP, VP, _I], _I),
+        "ckd_polar_blit": ([VP, VP, VP, _I], _I), "ckd_polar_blit_a": ([VP, VP, VP, _I], _I), "ckd_polar_blit_2x2": ([VP, VP, VP, _I], _I),
         "ckd_old_blur_h": ([VP, VP, VP, U, U, F], _I), "ckd_old_blur_v": ([VP, VP, VP, U, U, F], _I), "ckd_old_blur": ([VP, VP, VP, U, U, F], _I),
         "ckd_box_blur_scale": ([F], F),
         "ckd_new_blur_h": ([VP, VP, VP, U, U, F, F, U], _I), "ckd_new_blur_v": ([VP, VP, VP, U, U, F, F, U], _I), "ckd_new_blur": ([VP, VP, VP, U, U, F, F, U], _I),
@@ -330,6 +330,9 @@ class Context:
     def polar_blit(self, d_dest, d_src, inverse=False, alpha=False):
         fn = self.L.ckd_polar_blit_a if alpha else self.L.ckd_polar_blit
         self._check(fn(self.h, C.c_void_p(d_dest), C.c_void_p(d_src), int(inverse)))
+
+    def polar_blit_2x2(self, d_dest, d_src, inverse=False):
+        self._check(self.L.ckd_polar_blit_2x2(self.h, C.c_void_p(d_dest), C.c_void_p(d_src), int(inverse)))
 
     def blend_chain(self, d_dest, steps, n):
         """steps: [(op name, d_src or None, f_param, u_param)] applied per pixel in one pass (ckd_blend_chain)"""

@@ -194,6 +194,26 @@ extern "C" int ckd_get_polar_maps(ckd_ctx *ctx, int32_t *out_map, int32_t *out_i
 	return CKD_OK;
 }
 
+// s_pMap2x2 / s_pInvMap2x2 (polar.cpp:15-16,69): only Polar_Blit_2x2 reads them and the demo never calls it, so they are
+// built on first use instead of in ckd_create (2 x 16.7 MB at 3840x2160)
+int ckd_ensure_polar_maps_2x2(ckd_ctx *ctx)
+{
+	if (ctx->d_polarMap2x2)
+		return CKD_OK;
+	const size_t fxPixels = size_t(ctx->fxX)*ctx->fxY;
+	const size_t bytes = fxPixels*2*sizeof(int32_t);
+	std::vector<int32_t> map(fxPixels*2), invMap(fxPixels*2);
+	BuildPolarMaps(map.data(), invMap.data(), ctx->fxX, ctx->fxY, ctx->fxX, ctx->fxY); // polar.cpp:69
+	int32_t *d_maps = nullptr;
+	CKD_CUDA(cudaMalloc(&d_maps, 2*bytes));
+	cudaError_t err = cudaMemcpy(d_maps, map.data(), bytes, cudaMemcpyHostToDevice);
+	if (cudaSuccess == err) err = cudaMemcpy(d_maps + fxPixels*2, invMap.data(), bytes, cudaMemcpyHostToDevice);
+	if (cudaSuccess != err) { cudaFree(d_maps); return ckd_cuda_fail(err, "cudaMemcpy(polar maps 2x2)", __FILE__, __LINE__); }
+	ctx->d_polarMap2x2 = d_maps;
+	ctx->d_polarInvMap2x2 = d_maps + fxPixels*2;
+	return CKD_OK;
+}
+
 extern "C" int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device)
 {
 	CKD_REQUIRE(out_ctx, "null out_ctx");
@@ -310,6 +330,7 @@ extern "C" void ckd_destroy(ckd_ctx *ctx)
 	for (auto &slot : ctx->images)
 		if (slot.d_pixels) cudaFree(slot.d_pixels);
 	if (ctx->d_rsqrtTab) cudaFree(ctx->d_rsqrtTab);
+	if (ctx->d_polarMap2x2) cudaFree(ctx->d_polarMap2x2);
 	free(ctx->h_rsqrtTab);
 	for (auto &e : ctx->profEntries) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
 	for (int i = 0; i < 2; ++i)

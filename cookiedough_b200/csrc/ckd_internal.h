@@ -51,6 +51,7 @@ struct ckd_ctx {
 	int rsqrtLog2Bin = 13;
 	size_t rsqrtEntries = 0;
 	int32_t *d_polarMap = nullptr, *d_polarInvMap = nullptr; // 2 ints per pixel
+	int32_t *d_polarMap2x2 = nullptr, *d_polarInvMap2x2 = nullptr; // FX-map sized twins (s_pMap2x2/s_pInvMap2x2, polar.cpp:15-16), built on first use
 	int *d_voxelTables = nullptr;     // per-frame projection / lighting tables for ball & twister
 	float *d_rayParams = nullptr;     // per-ray host-computed parameters (ball fan deltas, twister origins)
 	unsigned *d_tileCounters = nullptr; // two alternating work-queue counters of the raymarch kernels
@@ -69,6 +70,8 @@ struct ckd_ctx {
 // brackets the next kernel launch with CUDA events when profiling is on; algoBytes = algorithmic bytes of that launch
 void ckd_prof_begin(ckd_ctx *ctx, const char *name, double algoBytes);
 void ckd_prof_end(ckd_ctx *ctx);
+
+int ckd_ensure_polar_maps_2x2(ckd_ctx *ctx); // builds and uploads the FX-map sized polar maps once
 
 void ckd_set_error(const std::string &message);
 int ckd_cuda_fail(cudaError_t err, const char *what, const char *file, int line);

@@ -563,6 +563,21 @@ static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, in
 extern "C" int ckd_polar_blit(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse) { return LaunchPolar(ctx, d_dest, d_src, inverse, false); }
 extern "C" int ckd_polar_blit_a(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse) { return LaunchPolar(ctx, d_dest, d_src, inverse, true); }
 
+// Polar_Blit_2x2, polar.cpp:200-218: the same remap on FX-map sized buffers (row stride fxResX) through the FX-map sized maps
+extern "C" int ckd_polar_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse)
+{
+	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
+	CKD_REQUIRE(d_dest != d_src, "polar blit cannot run in place");
+	CKD_REQUIRE(0 == (reinterpret_cast<uintptr_t>(d_dest) & 15), "destination must be 16-byte aligned");
+	CKD_TRY(ckd_ensure_polar_maps_2x2(ctx));
+	const unsigned numQuads = unsigned(size_t(ctx->fxX)*ctx->fxY/4); // fxResX is a multiple of 4 (fx-blitter.h:18)
+	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap2x2 : ctx->d_polarMap2x2);
+	ckd_prof_begin(ctx, "polar_blit_2x2", 16.0*ctx->fxX*ctx->fxY);
+	polar_blit_kernel<false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->fxX));
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // TapeWarp32 -- util.cpp:552-603
 // ---------------------------------------------------------------------------------------------------------------

@@ -680,6 +680,8 @@ static SyncTrack trackBallBlur, trackBallRadius, trackBallRayLength, trackBallSp
 static SyncTrack trackBallBeamAtten, trackBallBeamAlphaMin, trackBallRotateOffsX, trackBallRotateOffsY, trackBallBeams1, trackBallBeams2, trackBallBeams3, trackBallLowBeams;
 
 // ball.cpp:367-450
+static std::vector<uint32_t> s_ballBackground; // s_pBackgrounds[0] for Ball_GetBackground (ball.cpp:412,516)
+
 bool Ball_Create()
 {
 	static const char *kHeightMapPaths[5] = { "assets/ball/hmap_1_1k.jpg", "assets/ball/hmap_4_1k.jpg", "assets/ball/hmap_2_1k.jpg", "assets/ball/hmap_3_1k.jpg", "assets/ball/hmap_5_1k.jpg" };
@@ -698,6 +700,11 @@ bool Ball_Create()
 		return false;
 	if (!LoadImage("assets/ball/halo.png", CKD_IMG_BALL_HALO, 4))
 		return false;
+	{
+		const HostImage &bg = s_images["assets/ball/nytrik-background_1280x720.png"];
+		const uint32_t *px = reinterpret_cast<const uint32_t *>(bg.pixels.data());
+		s_ballBackground.assign(px, px + size_t(bg.width)*bg.height);
+	}
 
 	trackBallBlur = Rocket::AddTrack("ball:Blur");
 	trackBallRadius = Rocket::AddTrack("ball:Radius");
@@ -717,7 +724,10 @@ bool Ball_Create()
 	return true;
 }
 
-void Ball_Destroy() {}
+void Ball_Destroy() { s_ballBackground.clear(); s_ballBackground.shrink_to_fit(); }
+
+// ball.cpp:516-520
+uint32_t *Ball_GetBackground() { return s_ballBackground.empty() ? nullptr : s_ballBackground.data(); }
 
 // ball.cpp:452-514
 void Ball_Draw(uint32_t *pDest, float time, float delta)
@@ -840,6 +850,30 @@ void Polar_BlitA(uint32_t *pDest, const uint32_t *pSrc, bool inverse)
 	if (s.ok) s.Finish(ckd_polar_blit_a(s_ctx, s.d_dest, s.d_src, inverse), "Polar_BlitA");
 }
 
+void Polar_Blit_2x2(uint32_t *pDest, const uint32_t *pSrc, bool inverse)
+{
+	Staged s(pDest, FxPixels(), pSrc, FxPixels(), false);
+	if (s.ok) s.Finish(ckd_polar_blit_2x2(s_ctx, s.d_dest, s.d_src, inverse), "Polar_Blit_2x2");
+}
+
+// fx-blitter.cpp:77-98: stripes into g_pFxMap[0] (the device twin), then Fx_Blit_2x2
+void FxBlitter_DrawTestPattern(uint32_t *pDest)
+{
+	if (nullptr == s_ctx) { SetLastError("CkdHost_Create() has not been called"); return; }
+	const unsigned fxX = unsigned(ckd_fxmap_res_x(s_ctx)), fxY = unsigned(ckd_fxmap_res_y(s_ctx));
+	std::vector<uint32_t> pattern(size_t(fxX)*fxY);
+	for (unsigned iY = 0; iY < fxY; ++iY)
+		for (unsigned iX = 0; iX < fxX; ++iX)
+			pattern[size_t(iY)*fxX + iX] = (iY < fxY/2) ? ((iY & 1) ? 0xffffffffu : 0u) : ((iX & 1) ? 0xffffffffu : 0u);
+	if (nullptr != g_pFxMap[0])
+		memcpy(g_pFxMap[0], pattern.data(), pattern.size()*4); // the reference leaves the pattern in g_pFxMap[0]
+	uint32_t *d_fx = ckd_fxmap(s_ctx, 0), *d_dest = ckd_render_target(s_ctx, 2);
+	if (Check(ckd_upload(s_ctx, d_fx, pattern.data(), pattern.size()*4), "FxBlitter_DrawTestPattern")
+		&& Check(ckd_fx_blit_2x2(s_ctx, d_dest, d_fx), "FxBlitter_DrawTestPattern")
+		&& Check(ckd_download(s_ctx, pDest, d_dest, OutPixels()*4), "FxBlitter_DrawTestPattern"))
+		Check(ckd_sync(s_ctx), "FxBlitter_DrawTestPattern"); // also keeps `pattern` alive until the upload has run
+}
+
 void Fx_Blit_2x2(uint32_t *pDest, const uint32_t *pSrc)
 {
 	Staged s(pDest, OutPixels(), pSrc, FxPixels(), false);
@@ -899,6 +933,166 @@ void MulSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels) { B
 void MulSrc32A(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels) { Blend(CKD_MULSRC32A, pDest, pSrc, numPixels, 0.f, 0, "MulSrc32A"); }
 void MixSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels) { Blend(CKD_MIXSRC32, pDest, pSrc, numPixels, 0.f, 0, "MixSrc32"); }
 void Fade32(uint32_t *pDest, unsigned int numPixels, uint32_t RGB, uint8_t alpha) { Blend(CKD_FADE32, pDest, nullptr, numPixels, 0.f, (unsigned(alpha) << 24) | (RGB & 0xffffff), "Fade32"); }
+
+// rectangular blits (util.cpp:636-796): pDest usually points INTO a frame (demo.cpp:886 `pDest + xOffs + yOffs*kResX`), so
+// the staged extent is the run from the first to the last pixel the op touches; sources may be larger than a frame
+// (the 2160-pixel wide ribbons of MixSrc32S, demo.cpp:682) and then get a device buffer of their own.
+namespace {
+
+struct StagedRect
+{
+	uint32_t *d_dest = nullptr, *d_src = nullptr, *d_ownSrc = nullptr;
+	uint32_t *pDest;
+	size_t destBytes;
+	bool ok = false;
+
+	StagedRect(uint32_t *pDest_, size_t destPixels, const uint32_t *pSrc, size_t srcPixels) : pDest(pDest_), destBytes(destPixels*4)
+	{
+		if (nullptr == s_ctx) { SetLastError("CkdHost_Create() has not been called"); return; }
+		if (0 == destPixels || 0 == srcPixels) return;
+		if (destPixels > OutPixels()) { SetLastError("buffer larger than the output resolution"); return; }
+		d_dest = ckd_render_target(s_ctx, 2);
+		if (!Check(ckd_upload(s_ctx, d_dest, pDest, destBytes), "upload")) return;
+		if (srcPixels <= OutPixels())
+			d_src = ckd_render_target(s_ctx, 3);
+		else
+		{
+			void *p = nullptr;
+			if (!Check(ckd_malloc(s_ctx, &p, srcPixels*4), "ckd_malloc")) return;
+			d_src = d_ownSrc = static_cast<uint32_t *>(p);
+		}
+		ok = Check(ckd_upload(s_ctx, d_src, pSrc, srcPixels*4), "upload");
+	}
+
+	void Finish(int rc, const char *what)
+	{
+		if (ok && Check(rc, what) && Check(ckd_download(s_ctx, pDest, d_dest, destBytes), what))
+			Check(ckd_sync(s_ctx), what);
+	}
+
+	~StagedRect()
+	{
+		if (d_ownSrc) { ckd_sync(s_ctx); ckd_free(s_ctx, d_ownSrc); }
+	}
+};
+
+void Blit(ckd_blit_op op, uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned srcResX, unsigned yRes, float alpha, const char *what)
+{
+	if (0 == yRes || 0 == srcResX) return;
+	StagedRect s(pDest, size_t(yRes-1)*destResX + srcResX, pSrc, size_t(srcResX)*yRes);
+	if (s.ok) s.Finish(ckd_blit(s_ctx, op, s.d_dest, s.d_src, destResX, srcResX, yRes, alpha), what);
+}
+
+} // namespace
+
+void MixSrc32S(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned destResY, unsigned srcStride)
+{
+	if (0 == destResX || 0 == destResY) return;
+	StagedRect s(pDest, size_t(destResX)*destResY, pSrc, size_t(destResY-1)*srcStride + destResX);
+	if (s.ok) s.Finish(ckd_mix_src_s(s_ctx, s.d_dest, s.d_src, destResX, destResY, srcStride), "MixSrc32S");
+}
+
+void BlitSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned srcResX, unsigned yRes) { Blit(CKD_BLITSRC32, pDest, pSrc, destResX, srcResX, yRes, 0.f, "BlitSrc32"); }
+void BlitSrc32A(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned srcResX, unsigned yRes, float alpha) { Blit(CKD_BLITSRC32A, pDest, pSrc, destResX, srcResX, yRes, alpha, "BlitSrc32A"); }
+void BlitAdd32(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned srcResX, unsigned yRes) { Blit(CKD_BLITADD32, pDest, pSrc, destResX, srcResX, yRes, 0.f, "BlitAdd32"); }
+void BlitAdd32A(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned srcResX, unsigned yRes, float alpha) { Blit(CKD_BLITADD32A, pDest, pSrc, destResX, srcResX, yRes, alpha, "BlitAdd32A"); }
+
+// util.h:57-67
+void memset32(void *pDest, int value, size_t numInts)
+{
+	if (nullptr == s_ctx) { SetLastError("CkdHost_Create() has not been called"); return; }
+	uint32_t *d_dest = ckd_render_target(s_ctx, 2);
+	for (size_t done = 0; done < numInts; ) // buffers larger than a frame go in frame-sized pieces
+	{
+		const size_t n = numInts - done < OutPixels() ? numInts - done : OutPixels();
+		if (!Check(ckd_memset32(s_ctx, d_dest, uint32_t(value), n), "memset32")
+			|| !Check(ckd_download(s_ctx, static_cast<uint32_t *>(pDest) + done, d_dest, n*4), "memset32") || !Check(ckd_sync(s_ctx), "memset32"))
+			return;
+		done += n;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// module set-up: polar.cpp:61-80, boxblur.cpp:23-36, fx-blitter.cpp:10-25, shared-resources.cpp:14-43
+// ---------------------------------------------------------------------------------------------------------------
+
+uint32_t *g_pFxMap[kNumFxMaps] = { nullptr };
+uint32_t *g_renderTarget[kNumRenderTargets] = { nullptr };
+uint32_t *g_pNytrikTPB = nullptr;
+uint32_t *g_pXboxLogoTPB = nullptr;
+ckd_unp16 g_gradientUnp16[kNumGradients];
+
+static std::vector<uint32_t> s_nytrikTPB, s_xboxLogoTPB;
+
+static bool HaveContext(const char *what)
+{
+	if (nullptr != s_ctx) return true;
+	SetLastError(std::string(what) + ": CkdHost_Create() has not been called");
+	return false;
+}
+
+static bool AllocHostImages(uint32_t **images, unsigned count, size_t pixels, const char *what)
+{
+	for (unsigned i = 0; i < count; ++i)
+	{
+		if (nullptr != images[i]) continue;
+		void *p = nullptr;
+		if (!Check(ckd_malloc_host(&p, pixels*sizeof(uint32_t)), what)) return false;
+		memset(p, 0, pixels*sizeof(uint32_t));
+		images[i] = static_cast<uint32_t *>(p);
+	}
+	return true;
+}
+
+static void FreeHostImages(uint32_t **images, unsigned count)
+{
+	for (unsigned i = 0; i < count; ++i)
+	{
+		if (images[i]) ckd_free_host(images[i]);
+		images[i] = nullptr;
+	}
+}
+
+// the polar maps and the blur scratch belong to the context (ckd_create builds s_pMap/s_pInvMap, the 2x2 maps on first use)
+bool Polar_Create() { return HaveContext("Polar_Create"); }
+void Polar_Destroy() {}
+bool BoxBlur_Create() { return HaveContext("BoxBlur_Create"); }
+void BoxBlur_Destroy() {}
+
+bool FxBlitter_Create() { return HaveContext("FxBlitter_Create") && AllocHostImages(g_pFxMap, kNumFxMaps, FxPixels(), "FxBlitter_Create"); }
+void FxBlitter_Destroy() { FreeHostImages(g_pFxMap, kNumFxMaps); }
+
+static bool CopyImage32(const char *path, std::vector<uint32_t> &out)
+{
+	auto it = s_images.find(path);
+	if (it == s_images.end() || 4 != it->second.bpp)
+	{
+		SetLastError(std::string("Can not load image: ") + path); // image.cpp:40
+		return false;
+	}
+	const uint32_t *px = reinterpret_cast<const uint32_t *>(it->second.pixels.data());
+	out.assign(px, px + size_t(it->second.width)*it->second.height);
+	return true;
+}
+
+bool Shared_Create()
+{
+	if (!HaveContext("Shared_Create")) return false;
+	for (unsigned i = 0; i < kNumGradients; ++i) // c2vISSE16(i*0x01010101): bytes unpacked into the low four 16-bit lanes
+		g_gradientUnp16[i] = { { uint16_t(i), uint16_t(i), uint16_t(i), uint16_t(i), 0, 0, 0, 0 } };
+	if (!AllocHostImages(g_renderTarget, kNumRenderTargets, OutPixels(), "Shared_Create")) return false;
+	if (!CopyImage32("assets/demo/TPB-logo.png", s_nytrikTPB) || !CopyImage32("assets/demo/tpb_xbox_tp-263x243.png", s_xboxLogoTPB)) return false;
+	g_pNytrikTPB = s_nytrikTPB.data();
+	g_pXboxLogoTPB = s_xboxLogoTPB.data();
+	return true;
+}
+
+void Shared_Destroy()
+{
+	FreeHostImages(g_renderTarget, kNumRenderTargets);
+	g_pNytrikTPB = g_pXboxLogoTPB = nullptr;
+	s_nytrikTPB.clear(); s_xboxLogoTPB.clear();
+}
 
 void TapeWarp32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float speed)
 {
@@ -1020,9 +1214,48 @@ int ckdhost_post(int op, uint32_t *pDest, const uint32_t *pSrc, unsigned a, unsi
 	case 7: MixSrc32(pDest, pSrc, a); break;
 	case 8: SoftLight32(pDest, pSrc, a); break;
 	case 9: TapeWarp32(pDest, pSrc, a, b, f0, f1); break;
+	case 10: Polar_Blit_2x2(pDest, pSrc, 0 != u); break;
+	case 11: FxBlitter_DrawTestPattern(pDest); break;
+	case 12: BlitSrc32(pDest, pSrc, a, b, u); break;       // a = destResX, b = srcResX, u = yRes
+	case 13: BlitSrc32A(pDest, pSrc, a, b, u, f0); break;
+	case 14: BlitAdd32(pDest, pSrc, a, b, u); break;
+	case 15: BlitAdd32A(pDest, pSrc, a, b, u, f0); break;
+	case 16: MixSrc32S(pDest, pSrc, a, b, u); break;       // a = destResX, b = destResY, u = srcStride
+	case 17: memset32(pDest, int(u), size_t(a)); break;
 	default: return -1;
 	}
 	return s_lastError.empty() ? 0 : -2;
+}
+
+// module set-up names: 0 Polar, 1 BoxBlur, 2 FxBlitter, 3 Shared; create != 0 calls X_Create, else X_Destroy
+int ckdhost_module(int module, int create)
+{
+	s_lastError.clear();
+	bool ok = true;
+	switch (module)
+	{
+	case 0: if (create) ok = Polar_Create(); else Polar_Destroy(); break;
+	case 1: if (create) ok = BoxBlur_Create(); else BoxBlur_Destroy(); break;
+	case 2: if (create) ok = FxBlitter_Create(); else FxBlitter_Destroy(); break;
+	case 3: if (create) ok = Shared_Create(); else Shared_Destroy(); break;
+	default: return -1;
+	}
+	return ok ? 0 : -2;
+}
+
+// which: 0-3 g_pFxMap[i], 4-7 g_renderTarget[i], 8 g_pNytrikTPB, 9 g_pXboxLogoTPB, 10 g_gradientUnp16, 11 Ball_GetBackground()
+void *ckdhost_global(int which)
+{
+	if (which >= 0 && which < 4) return g_pFxMap[which];
+	if (which >= 4 && which < 8) return g_renderTarget[which-4];
+	switch (which)
+	{
+	case 8: return g_pNytrikTPB;
+	case 9: return g_pXboxLogoTPB;
+	case 10: return g_gradientUnp16;
+	case 11: return Ball_GetBackground();
+	}
+	return nullptr;
 }
 
 } // extern "C"

@@ -12,7 +12,10 @@ ROW_RATE = (170.0 / (60.0 * (170.0 / 174.0))) * 16.0  # code/audio.cpp:18
 EFFECT_IDS = {"plasma": 0, "nautilus": 1, "spikey_close": 2, "spikey_distant": 3, "tunnel": 4, "sinuses": 5, "laura": 6,
               "landscape": 7, "tunnelscape": 8, "ball": 9, "twister": 10}
 POST_IDS = {"Fx_Blit_2x2": 0, "Polar_Blit": 1, "Polar_BlitA": 2, "HorizontalBoxBlur32": 3, "VerticalBoxBlur32": 4, "BoxBlur32": 5,
-            "BoxBlur_32": 6, "MixSrc32": 7, "SoftLight32": 8, "TapeWarp32": 9}
+            "BoxBlur_32": 6, "MixSrc32": 7, "SoftLight32": 8, "TapeWarp32": 9, "Polar_Blit_2x2": 10, "FxBlitter_DrawTestPattern": 11,
+            "BlitSrc32": 12, "BlitSrc32A": 13, "BlitAdd32": 14, "BlitAdd32A": 15, "MixSrc32S": 16, "memset32": 17}
+MODULE_IDS = {"Polar": 0, "BoxBlur": 1, "FxBlitter": 2, "Shared": 3}
+GLOBAL_IDS = {"g_pFxMap": 0, "g_renderTarget": 4, "g_pNytrikTPB": 8, "g_pXboxLogoTPB": 9, "g_gradientUnp16": 10, "Ball_GetBackground": 11}
 
 _U32P = C.POINTER(C.c_uint32)
 
@@ -33,6 +36,9 @@ def _lib():
     L.ckdhost_track_i.argtypes = [C.c_char_p]
     L.ckdhost_draw.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_float]
     L.ckdhost_post.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_uint]
+    L.ckdhost_module.argtypes = [C.c_int, C.c_int]
+    L.ckdhost_global.argtypes = [C.c_int]
+    L.ckdhost_global.restype = C.c_void_p
     L.ckdhost_demo_create.argtypes = []
     L.ckdhost_demo_draw.argtypes = [C.c_void_p, C.c_double, C.c_float]
     L.ckdhost_demo_destroy.argtypes = []
@@ -92,6 +98,11 @@ class Host:
         self.ctx_handle = self.L.ckdhost_context()
         self.time = 0.0
 
+    def register_image(self, path, arr):
+        """CkdHost_RegisterImage: pre-decoded pixels (uint32 BGRA or uint8 L8, HxW) under the path the reference loads them by"""
+        arr = np.ascontiguousarray(arr)
+        self.L.ckdhost_register_image(path.encode(), arr.ctypes.data, arr.shape[1], arr.shape[0], 1 if arr.dtype == np.uint8 else 4)
+
     def context(self):
         """a capi.Context view of the host layer's ckd_ctx (not owning)"""
         ctx = capi.Context.__new__(capi.Context)
@@ -136,6 +147,19 @@ class Host:
         rc = self.L.ckdhost_post(POST_IDS[op], dst.ctypes.data, src.ctypes.data if src is not None else None, a, b, C.c_float(f0), C.c_float(f1), u)
         if rc != 0:
             raise capi.CkdError(f"{op}: {self.L.ckdhost_last_error().decode()}")
+
+    def module(self, name, create=True):
+        """Polar/BoxBlur/FxBlitter/Shared _Create (-> bool) or _Destroy"""
+        return self.L.ckdhost_module(MODULE_IDS[name], int(bool(create))) == 0
+
+    def global_array(self, name, index=0, shape=None, dtype=np.uint32):
+        """numpy view of one of the reference's globals (g_pFxMap[i], g_renderTarget[i], ...); None while it is null"""
+        addr = self.L.ckdhost_global(GLOBAL_IDS[name] + index)
+        if not addr:
+            return None
+        n = int(np.prod(shape))
+        buf = (C.c_uint8*(n*np.dtype(dtype).itemsize)).from_address(addr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def pin(self, out):
         """CkdHost_PinFrameBuffer: page-lock a caller-owned numpy frame in place"""

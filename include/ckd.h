@@ -134,6 +134,10 @@ int ckd_fx_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src);
 /* Polar_Blit / Polar_BlitA (polar.cpp:135-154, 180-198) */
 int ckd_polar_blit(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse);
 int ckd_polar_blit_a(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse);
+/* Polar_Blit_2x2 (polar.cpp:200-218): FX-map sized source and destination (fxResX x fxResY), FX-map sized maps built on
+ * first use.  The reference's 64/32-pixel tiles do not divide the FX map and run past the end of its buffers; this
+ * entry writes exactly fxResX*fxResY pixels (the in-bounds part of the reference's result). */
+int ckd_polar_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse);
 
 /* 2007 box blur (deprecated/boxblur.cpp:44-231); d_dest may equal d_src (the reference's in-place semantics are kept) */
 int ckd_old_blur_h(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, unsigned x_res, unsigned y_res, float strength);

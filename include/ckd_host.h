@@ -101,6 +101,7 @@ void Tunnelscape_Draw(uint32_t *pDest, float time, float delta);
 bool Ball_Create();
 void Ball_Destroy();
 void Ball_Draw(uint32_t *pDest, float time, float delta);
+uint32_t *Ball_GetBackground(); // ball.cpp:516-520: host pixels of the first background (valid until Ball_Destroy)
 bool Ball_HasBeams();
 
 bool Twister_Create();
@@ -119,9 +120,40 @@ bool Demo_Draw(uint32_t *pDest, float time, float delta);
 // ---- 2D post chain on HOST buffers (polar.h:7-17, deprecated/boxblur.h:21-41, boxblur.h:7-20, fx-blitter.h:26-33,
 //      util.h:57-122).  pDest/pSrc may alias where the reference allows it. ---------------------------------------------
 
+// module set-up of the reference (polar.h:7-8, boxblur.h:7-8, fx-blitter.h:28-29, shared-resources.h:27-28).  The scratch
+// images and maps these allocate in the reference live in the device context (CkdHost_Create), so here they check that the
+// context exists and provide the caller-visible globals: FxBlitter_Create allocates g_pFxMap[0..3] and Shared_Create
+// g_renderTarget[0..3] as page-locked HOST buffers of the reference's sizes (kFxMapBytes / kTargetBytes) for callers that
+// use them as scratch between post ops (demo.cpp does); the effects' own intermediate images never leave the device
+// (ckd_fxmap / ckd_render_target).  Shared_Create also needs the two TPB logos registered (shared-resources.cpp:27-34).
+bool Polar_Create();
+void Polar_Destroy();
+bool BoxBlur_Create();
+void BoxBlur_Destroy();
+bool FxBlitter_Create();
+void FxBlitter_Destroy();
+bool Shared_Create();
+void Shared_Destroy();
+
+constexpr unsigned kNumFxMaps = 4;        // fx-blitter.h:14
+constexpr unsigned kNumRenderTargets = 4; // shared-resources.h:11
+constexpr unsigned kNumGradients = 256;   // shared-resources.h:7
+extern uint32_t *g_pFxMap[kNumFxMaps];
+extern uint32_t *g_renderTarget[kNumRenderTargets];
+extern uint32_t *g_pNytrikTPB;
+extern uint32_t *g_pXboxLogoTPB;
+// g_gradientUnp16[i] = c2vISSE16(i*0x01010101) (shared-resources.cpp:17-20): eight 16-bit lanes, the low four = i.
+// Same 16-byte layout as the reference's __m128i array; filled by Shared_Create.
+struct alignas(16) ckd_unp16 { uint16_t lane[8]; };
+extern ckd_unp16 g_gradientUnp16[kNumGradients];
+
 void Polar_Blit(uint32_t *pDest, const uint32_t *pSrc, bool inverse = false);
 void Polar_BlitA(uint32_t *pDest, const uint32_t *pSrc, bool inverse = false);
+// FX-map sized buffers (kFxMapResX x kFxMapResY).  The reference's tiles run past the end of the FX map (64 and 32 do not
+// divide 644 x 364); this writes exactly kFxMapSize pixels -- what the reference writes in bounds.
+void Polar_Blit_2x2(uint32_t *pDest, const uint32_t *pSrc, bool inverse = false);
 void Fx_Blit_2x2(uint32_t *pDest, const uint32_t *pSrc);
+void FxBlitter_DrawTestPattern(uint32_t *pDest); // fx-blitter.cpp:77-98
 
 void HorizontalBoxBlur32(uint32_t *pDest, const uint32_t *pSrc, unsigned int xRes, unsigned int yRes, float strength);
 void VerticalBoxBlur32(uint32_t *pDest, const uint32_t *pSrc, unsigned int xRes, unsigned int yRes, float strength);
@@ -146,5 +178,11 @@ void Darken32_50(uint32_t *pDest, const uint32_t *pSrc, unsigned numPixels);
 void MulSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels);
 void MulSrc32A(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels);
 void MixSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned int numPixels);
+void MixSrc32S(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned destResY, unsigned srcStride);
+void BlitSrc32(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned srcResX, unsigned yRes);
+void BlitSrc32A(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned srcResX, unsigned yRes, float alpha);
+void BlitAdd32(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned srcResX, unsigned yRes);
+void BlitAdd32A(uint32_t *pDest, const uint32_t *pSrc, unsigned destResX, unsigned srcResX, unsigned yRes, float alpha);
 void Fade32(uint32_t *pDest, unsigned int numPixels, uint32_t RGB, uint8_t alpha);
+void memset32(void *pDest, int value, size_t numInts); // util.h:57-67 (numInts a multiple of 4, pDest 8-byte aligned)
 void TapeWarp32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float speed);

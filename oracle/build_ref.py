@@ -16,7 +16,8 @@ are inputs -- timeline and art -- that the product reads as well, so they do not
 
 Patch list (applied on the fly to a throw-away symlink tree in a temp dir):
     P1  fx-blitter.cpp:48-49   _mm_load_si128 on a 4-byte aligned address -> _mm_loadu_si128 (x86 #GP)
-    P2  polar.cpp:113,161      clamp tile rows to kResY (720 % 32 != 0 -> heap overflow)
+    P2  polar.cpp:113,161      clamp tile rows to kResY (720 % 32 != 0 -> heap overflow); kFxMapResY for the FX-map instantiation
+    P2b polar.cpp:118          Polar_Blit_Tile: clamp tile columns to xRes (Polar_Blit_2x2: 644 % 64 != 0; no-op at full size)
     P3a boxblur.cpp:18         kMaxRes 2048 -> 4096 (4K scratch)
     P3b shadertoy.cpp:185      blur-map scratch (1280*720)/2 px -> kFxMapBytes
     P3c main.h:37-38           kResX/kResY (4K build only)
@@ -88,8 +89,16 @@ def make_tree(tmp, res_x, res_y):
     rewrite("fx-blitter.cpp", lambda t: _patch(
         t, r"_mm_load_si128\(reinterpret_cast<const __m128i\*>\(&pSrc\[", "_mm_loadu_si128(reinterpret_cast<const __m128i*>(&pSrc[", 2, "P1"))
     # P2
-    rewrite("polar.cpp", lambda t: _patch(
-        t, r"for \(unsigned iY = tY; iY < tY \+ tileSize; \+\+iY\)", "for (unsigned iY = tY; iY < tY + tileSize && iY < kResY; ++iY)", 2, "P2"))
+    def p2(t):
+        # first row loop = Polar_Blit_Tile<xRes> (also instantiated for the FX map by Polar_Blit_2x2), second = Polar_Blit_TileA
+        row_loop = "for (unsigned iY = tY; iY < tY + tileSize; ++iY)"
+        if t.count(row_loop) != 2:
+            raise RuntimeError("patch 'P2': expected 2 tile row loops")
+        t = t.replace(row_loop, "for (unsigned iY = tY; iY < tY + tileSize && iY < (xRes == kFxMapResX ? kFxMapResY : kResY); ++iY)", 1)
+        t = t.replace(row_loop, "for (unsigned iY = tY; iY < tY + tileSize && iY < kResY; ++iY)", 1)
+        # P2b: only Polar_Blit_Tile<xRes> steps its columns by 4
+        return _patch(t, r"for \(unsigned iX = 0; iX < tileSize; iX \+= 4\)", "for (unsigned iX = 0; iX < tileSize && tX + iX < xRes; iX += 4)", 1, "P2b")
+    rewrite("polar.cpp", p2)
     # P3a, P3b (harmless at 720p; applied to both builds so the two oracles share one code base)
     rewrite("boxblur.cpp", lambda t: _patch(t, r"constexpr size_t kMaxRes = 2048;", "constexpr size_t kMaxRes = 4096;", 1, "P3a"))
     rewrite("shadertoy.cpp", lambda t: _patch(

@@ -305,10 +305,9 @@ static texc prep_uvs(int U, int V, unsigned mapAnd, unsigned mapShift) /* bsamp_
  * polar remap -- polar.cpp:18-198
  * ---------------------------------------------------------------------------------------------------------------- */
 
-void orc_polar_maps(int32_t *pDest, int32_t *pInvDest) /* CalculateMaps, polar.cpp:18-59 with src == dest resolution */
+static void polar_maps(int32_t *pDest, int32_t *pInvDest, unsigned srcResX, unsigned srcResY) /* CalculateMaps, polar.cpp:18-59 with src == dest resolution */
 {
-	const unsigned srcResX = (unsigned)s_resX, srcResY = (unsigned)s_resY;
-	const float halfResX = s_resX/2.f, halfResY = s_resY/2.f;
+	const float halfResX = srcResX/2.f, halfResY = srcResY/2.f;
 	size_t iPixel = 0;
 	const float maxDist = sqrtf(halfResX*halfResX + halfResY*halfResY);
 	for (float Y = -halfResY; Y < halfResY; Y += 1.f)
@@ -326,16 +325,31 @@ void orc_polar_maps(int32_t *pDest, int32_t *pInvDest) /* CalculateMaps, polar.c
 		}
 }
 
-void orc_polar_blit(uint32_t *pDest, const uint32_t *pSrc, const int32_t *pMap, int alpha) /* Polar_Blit / Polar_BlitA */
+void orc_polar_maps(int32_t *pDest, int32_t *pInvDest) { polar_maps(pDest, pInvDest, (unsigned)s_resX, (unsigned)s_resY); }      /* polar.cpp:68 */
+void orc_polar_maps_2x2(int32_t *pDest, int32_t *pInvDest) { polar_maps(pDest, pInvDest, (unsigned)s_fxX, (unsigned)s_fxY); }  /* polar.cpp:69 */
+
+static void polar_blit(uint32_t *pDest, const uint32_t *pSrc, const int32_t *pMap, int alpha, unsigned resX, unsigned resY)
 {
-	const size_t n = (size_t)s_resX*s_resY;
+	const size_t n = (size_t)resX*resY;
 	for (size_t i = 0; i < n; ++i)
 	{
 		const int U = pMap[i*2], V = pMap[i*2+1];
-		const unsigned U0 = (unsigned)(U >> 8), V0 = (unsigned)(V >> 8)*(unsigned)s_resX;
-		const uint32_t s = bsamp32(pSrc, U0+V0, U0+1+V0, U0+V0+s_resX, U0+1+V0+s_resX, U & 0xff, V & 0xff);
+		const unsigned U0 = (unsigned)(U >> 8), V0 = (unsigned)(V >> 8)*resX;
+		const uint32_t s = bsamp32(pSrc, U0+V0, U0+1+V0, U0+V0+resX, U0+1+V0+resX, U & 0xff, V & 0xff);
 		pDest[i] = alpha ? lerp_argb(pDest[i], s, s >> 24) : s; /* polar.cpp:169-174 */
 	}
+}
+
+void orc_polar_blit(uint32_t *pDest, const uint32_t *pSrc, const int32_t *pMap, int alpha) /* Polar_Blit / Polar_BlitA, polar.cpp:135-198 */
+{
+	polar_blit(pDest, pSrc, pMap, alpha, (unsigned)s_resX, (unsigned)s_resY);
+}
+
+/* Polar_Blit_2x2, polar.cpp:200-218: the tile walk restated as what it writes inside the FX map (the tiles' overrun past
+ * the last row and the right edge is the reference's defect; the oracle build clamps it: P2/P2b) */
+void orc_polar_blit_2x2(uint32_t *pDest, const uint32_t *pSrc, const int32_t *pMap)
+{
+	polar_blit(pDest, pSrc, pMap, 0, (unsigned)s_fxX, (unsigned)s_fxY);
 }
 
 /* ------------------------------------------------------------------------------------------------------------------

@@ -61,6 +61,8 @@ class Port:
         L.orc_fx_blit_2x2.argtypes = [VP, VP]
         L.orc_polar_maps.argtypes = [VP, VP]
         L.orc_polar_blit.argtypes = [VP, VP, VP, I]
+        L.orc_polar_maps_2x2.argtypes = [VP, VP]
+        L.orc_polar_blit_2x2.argtypes = [VP, VP, VP]
         for n in ("orc_old_blur_h", "orc_old_blur_v", "orc_old_blur"):
             getattr(L, n).argtypes = [VP, VP, U, U, F]
         L.orc_new_blur.argtypes = [I, VP, VP, C.c_size_t, U, U, F, F, U]
@@ -107,6 +109,14 @@ class Port:
     def polar_blit(self, dst, src, inverse=False, alpha=False):
         m, inv = self.polar_maps()
         self.L.orc_polar_blit(_p(dst), _p(src), _p(inv if inverse else m), int(alpha))
+
+    def polar_blit_2x2(self, dst, src, inverse=False):
+        if getattr(self, "_maps2x2", None) is None:
+            m = np.zeros((self.fx_y, self.fx_x, 2), dtype=np.int32)
+            inv = np.zeros_like(m)
+            self.L.orc_polar_maps_2x2(_p(m), _p(inv))
+            self._maps2x2 = (m, inv)
+        self.L.orc_polar_blit_2x2(_p(dst), _p(src), _p(self._maps2x2[1 if inverse else 0]))
 
     def old_blur(self, kind, dst, src, w, h, strength):
         fn = {"h": self.L.orc_old_blur_h, "v": self.L.orc_old_blur_v, "hv": self.L.orc_old_blur}[kind]

@@ -93,6 +93,9 @@ class Reference:
         L.ref_fx_blit_2x2.argtypes = [_U32P, _U32P]
         L.ref_polar_blit.argtypes = [_U32P, _U32P, C.c_int]
         L.ref_polar_blit_a.argtypes = [_U32P, _U32P, C.c_int]
+        L.ref_polar_blit_2x2.argtypes = [_U32P, _U32P, C.c_int]
+        L.ref_fx_test_pattern.argtypes = [_U32P]
+        L.ref_ball_background.restype = C.c_void_p
         for name in ("ref_old_blur_h", "ref_old_blur_v", "ref_old_blur"):
             getattr(L, name).argtypes = [_U32P, _U32P, C.c_uint, C.c_uint, C.c_float]
         for name in ("ref_new_blur_h", "ref_new_blur_v", "ref_new_blur"):
@@ -192,6 +195,18 @@ class Reference:
 
     def polar_blit(self, dst, src, inverse=False, alpha=False):
         (self.lib.ref_polar_blit_a if alpha else self.lib.ref_polar_blit)(_p32(dst), _p32(src), int(inverse))
+
+    def polar_blit_2x2(self, dst, src, inverse=False):
+        """Polar_Blit_2x2 on FX-map sized buffers (oracle patched to stay inside them, build_ref.py P2/P2b)"""
+        self.lib.ref_polar_blit_2x2(_p32(dst), _p32(src), int(inverse))
+
+    def fx_test_pattern(self, dst):
+        self.lib.ref_fx_test_pattern(_p32(dst))
+
+    def ball_background(self):
+        addr = self.lib.ref_ball_background()
+        n = self.res_x * self.res_y
+        return np.frombuffer((C.c_uint32 * n).from_address(addr), dtype=np.uint32).copy()
 
     def old_blur(self, kind, dst, src, w, h, strength):
         fn = {"h": self.lib.ref_old_blur_h, "v": self.lib.ref_old_blur_v, "hv": self.lib.ref_old_blur}[kind]

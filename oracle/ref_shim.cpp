@@ -223,6 +223,9 @@ const double *ref_fast_cos_tab() { return g_fastCosTab; }
 void ref_fx_blit_2x2(uint32_t *pDest, const uint32_t *pSrc) { Fx_Blit_2x2(pDest, pSrc); }
 void ref_polar_blit(uint32_t *pDest, const uint32_t *pSrc, int inverse) { Polar_Blit(pDest, pSrc, 0 != inverse); }
 void ref_polar_blit_a(uint32_t *pDest, const uint32_t *pSrc, int inverse) { Polar_BlitA(pDest, pSrc, 0 != inverse); }
+void ref_polar_blit_2x2(uint32_t *pDest, const uint32_t *pSrc, int inverse) { Polar_Blit_2x2(pDest, pSrc, 0 != inverse); } // needs P2/P2b (build_ref.py)
+void ref_fx_test_pattern(uint32_t *pDest) { FxBlitter_DrawTestPattern(pDest); }
+uint32_t *ref_ball_background() { return Ball_GetBackground(); }
 
 void ref_old_blur_h(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength) { HorizontalBoxBlur32(pDest, pSrc, xRes, yRes, strength); }
 void ref_old_blur_v(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength) { VerticalBoxBlur32(pDest, pSrc, xRes, yRes, strength); }

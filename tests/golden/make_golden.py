@@ -261,6 +261,23 @@ def main():
     if sys.argv[1:3] == ["--only", "demo"]:
         return
 
+    if sys.argv[1:3] == ["--only", "post"]:   # refresh the post-chain pins alone (new cases); existing pins may not move
+        with tempfile.TemporaryDirectory() as tmp:
+            part = os.path.join(tmp, "post.json")
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "--child", "post", part])
+            with open(part) as f:
+                new = json.load(f)
+        path = os.path.join(HERE, "golden_post_720.json")
+        with open(path) as f:
+            golden = json.load(f)
+        moved = [k for k, v in golden["cases"].items() if new.get(k) != v]
+        if moved:
+            sys.exit(f"existing pins changed: {moved}")
+        golden["cases"] = new
+        with open(path, "w") as f:
+            json.dump(golden, f, indent=1)
+        return
+
     with tempfile.TemporaryDirectory() as tmp:
         parts = {}
         for mode in ("timeline", "scenario", "post"):

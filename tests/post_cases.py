@@ -55,6 +55,9 @@ _add(label="fx_blit_2x2/mul", op="fx_blit", src="mul")
 for inv in (0, 1):
     for alpha in (0, 1):
         _add(label=f"polar_blit/inv{inv}/alpha{alpha}", op="polar", inverse=inv, alpha=alpha, src="noise", dst="mix")
+for inv in (0, 1):
+    _add(label=f"polar_blit_2x2/inv{inv}", op="polar_2x2", inverse=inv, src="noise", dst="mix")
+_add(label="fx_test_pattern", op="test_pattern", dst="mix")
 
 for kind in ("h", "v", "hv"):
     for strength in (0.01, 0.05, 0.11, 0.33, 1.0):
@@ -101,6 +104,13 @@ _add(label="mix_src_s/ribbons", op="mix_src_s", dest_res_x=RES_X, dest_res_y=300
 _add(label="memset32", op="memset32", value=0x80c0ffee, n=RES_X * 100, dst="mix")
 
 
+def test_pattern():
+    """what FxBlitter_DrawTestPattern writes into g_pFxMap[0] (fx-blitter.cpp:77-95): line stripes above, column stripes below"""
+    y, x = np.mgrid[0:FX_Y, 0:FX_X]
+    on = np.where(y < FX_Y // 2, y & 1, x & 1).astype(bool)
+    return np.where(on, np.uint32(0xffffffff), np.uint32(0)).astype(np.uint32).ravel()
+
+
 def _sizes(case):
     """(dst elements, src elements) each case needs"""
     op = case["op"]
@@ -109,6 +119,10 @@ def _sizes(case):
         return full, FX_X * FX_Y
     if op in ("polar", "tape_warp"):
         return full, full
+    if op == "polar_2x2":
+        return FX_X * FX_Y, FX_X * FX_Y
+    if op == "test_pattern":
+        return full, 1
     if op in ("old_blur", "new_blur"):
         return case["w"] * case["h"], case["w"] * case["h"]
     if op == "blend":
@@ -143,6 +157,10 @@ def run_reference(R, case):
         R.fx_blit_2x2(dst, src)
     elif op == "polar":
         R.polar_blit(dst, src, bool(case["inverse"]), alpha=bool(case["alpha"]))
+    elif op == "polar_2x2":
+        R.polar_blit_2x2(dst, src, bool(case["inverse"]))
+    elif op == "test_pattern":
+        R.fx_test_pattern(dst)
     elif op == "old_blur":
         s = dst if case["inplace"] else src
         if case["inplace"]:
@@ -187,6 +205,11 @@ def run_cuda(ctx, case):
             ctx.fx_blit_2x2(d_dst, d_src)
         elif op == "polar":
             ctx.polar_blit(d_dst, d_src, bool(case["inverse"]), alpha=bool(case["alpha"]))
+        elif op == "polar_2x2":
+            ctx.polar_blit_2x2(d_dst, d_src, bool(case["inverse"]))
+        elif op == "test_pattern":
+            ctx.upload(ctx.fxmap(0), test_pattern())
+            ctx.fx_blit_2x2(d_dst, ctx.fxmap(0))
         elif op == "old_blur":
             ctx.old_blur(case["kind"], d_dst, d_dst if case["inplace"] else d_src, case["w"], case["h"], case["strength"])
         elif op == "new_blur":

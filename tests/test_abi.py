@@ -91,9 +91,27 @@ def test_host_layer_exports_the_reference_entry_points():
     assert not missing, f"include/ckd_host.h declares functions the library does not export: {missing}"
 
 
+def test_host_layer_covers_the_survey_signature_list():
+    """SURVEY 8(b) 'signatures to preserve': every function and global of that list is exported by the library"""
+    from cookiedough_b200 import capi
+    functions = """Shadertoy_Create Shadertoy_Destroy Nautilus_Draw Sinuses_Draw Laura_Draw Plasma_Draw Tunnel_Draw Spikey_Draw
+        Landscape_Create Landscape_Destroy Landscape_Draw Tunnelscape_Create Tunnelscape_Destroy Tunnelscape_Draw
+        Twister_Create Twister_Destroy Twister_Draw Ball_Create Ball_Destroy Ball_Draw Ball_GetBackground Ball_HasBeams
+        Polar_Create Polar_Destroy Polar_Blit Polar_BlitA Polar_Blit_2x2 BoxBlur_Create BoxBlur_Destroy BoxBlur_Horz32 BoxBlur_Vert32 BoxBlur_32
+        HorizontalBoxBlur32 VerticalBoxBlur32 BoxBlur32 BoxBlurScale FxBlitter_Create FxBlitter_Destroy Fx_Blit_2x2 FxBlitter_DrawTestPattern
+        Shared_Create Shared_Destroy memset32 Mix32 MixOver32 Add32 Sub32 Excl32 SoftLight32 SoftLight32A SoftLight32AA TapeWarp32 Overlay32
+        Overlay32A Darken32_50 MulSrc32 MulSrc32A MixSrc32 MixSrc32S BlitSrc32 BlitSrc32A BlitAdd32 BlitAdd32A Fade32
+        Demo_Create Demo_Destroy Demo_Draw""".split()
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", "-C", capi.LIB_PATH], text=True)
+    exported = set(re.findall(r" T ([A-Za-z_][A-Za-z0-9_]*)\(", syms))
+    assert not sorted(set(functions) - exported)
+    data = set(re.findall(r" [BD] ([A-Za-z_][A-Za-z0-9_]*)$", syms, flags=re.M))
+    assert {"g_pFxMap", "g_renderTarget", "g_gradientUnp16", "g_pNytrikTPB", "g_pXboxLogoTPB"} <= data
+
+
 def test_host_hooks_for_bindings_are_exported():
     from cookiedough_b200 import capi
     lib = ctypes.CDLL(capi.LIB_PATH)
     for name in ("ckdhost_create", "ckdhost_launch", "ckdhost_draw", "ckdhost_post", "ckdhost_demo_create", "ckdhost_demo_draw", "ckdhost_demo_destroy",
-                 "ckdhost_set_pipelined", "ckdhost_flush", "ckdsink_open", "ckdsink_acquire", "ckdsink_commit", "ckdsink_close"):
+                 "ckdhost_set_pipelined", "ckdhost_flush", "ckdhost_module", "ckdhost_global", "ckdsink_open", "ckdsink_acquire", "ckdsink_commit", "ckdsink_close"):
         assert hasattr(lib, name), name

@@ -67,6 +67,91 @@ def test_host_post_ops_on_host_buffers(host_and_ref):
     a, b = pair(); R.fx_blit_2x2(a, fx); host.post("Fx_Blit_2x2", b, fx); assert_bit_exact(b, a, "Fx_Blit_2x2")
 
 
+def test_host_rect_blits_into_a_frame(host_and_ref):
+    """BlitSrc32/A, BlitAdd32/A with pDest pointing INTO a frame (demo.cpp:886), MixSrc32S with a source wider than a frame
+    (the 2160-pixel ribbons, demo.cpp:682), memset32, Polar_Blit_2x2 and FxBlitter_DrawTestPattern on host buffers"""
+    host, R = host_and_ref
+    import post_cases as pc
+    from oracle.ref import aligned_u32
+    n = R.res_x * R.res_y
+    sprite_w, sprite_h = 263, 243
+    sprite = aligned_u32(sprite_w * sprite_h, pad=64); sprite[:] = pc.seeded(sprite.size, "noise")
+    offs = 101 + 57 * R.res_x
+
+    def pair():
+        a = aligned_u32(n, pad=4 * R.res_x); a[:] = pc.seeded(n, "mix")
+        b = aligned_u32(n, pad=4 * R.res_x); b[:] = a
+        return a, b
+
+    for op, alpha in (("BlitSrc32", 0.0), ("BlitSrc32A", 0.6), ("BlitAdd32", 0.0), ("BlitAdd32A", 0.35)):
+        a, b = pair()
+        R.blit(op, a[offs:], sprite, R.res_x, sprite_w, sprite_h, alpha)
+        host.post(op, b[offs:], sprite, R.res_x, sprite_w, sprite_h, f0=alpha)
+        assert_bit_exact(b, a, op)
+
+    ribbons = aligned_u32(2160 * (R.res_y - 1) + R.res_x, pad=64); ribbons[:] = pc.seeded(ribbons.size, "noise2")
+    a, b = pair()
+    R.mix_src_s(a, ribbons[77:], R.res_x, R.res_y - 1, 2160)
+    host.post("MixSrc32S", b, ribbons[77:], R.res_x, R.res_y - 1, u=2160)
+    assert_bit_exact(b, a, "MixSrc32S")
+
+    a, b = pair()
+    R.memset32(a, 0x00c0ffee, n - 8)
+    host.post("memset32", b, None, a=n - 8, u=0x00c0ffee)
+    assert_bit_exact(b, a, "memset32")
+
+    nfx = R.fx_x * R.fx_y
+    fx_src = aligned_u32(nfx, pad=4 * R.res_x); fx_src[:] = pc.seeded(nfx, "noise")
+    for inverse in (False, True):
+        a = aligned_u32(nfx, pad=4 * R.res_x); a[:] = 0x11223344
+        b = aligned_u32(nfx, pad=4 * R.res_x); b[:] = 0x11223344
+        R.polar_blit_2x2(a, fx_src, inverse)
+        host.post("Polar_Blit_2x2", b, fx_src, u=int(inverse))
+        assert_bit_exact(b, a, f"Polar_Blit_2x2 inverse={inverse}")
+
+    a, b = pair()
+    R.fx_test_pattern(a)
+    host.post("FxBlitter_DrawTestPattern", b, None)
+    assert_bit_exact(b, a, "FxBlitter_DrawTestPattern")
+
+
+def test_host_module_setup_and_globals(host_and_ref):
+    """Polar/BoxBlur/FxBlitter/Shared _Create/_Destroy and the globals they own: g_pFxMap, g_renderTarget as caller scratch
+    for a demo.cpp-style chain on host buffers, g_gradientUnp16, Ball_GetBackground"""
+    host, R = host_and_ref
+    import post_cases as pc
+    assert host.module("Polar") and host.module("BoxBlur") and host.module("FxBlitter")
+    # Shared_Create loads the two TPB logos (shared-resources.cpp:27-34): the bare-effects host has not registered them
+    logos = {"assets/demo/TPB-logo.png": (R.res_x, R.res_y), "assets/demo/tpb_xbox_tp-263x243.png": (263, 243)}
+    for path, (w, h) in logos.items():
+        host.register_image(path, pc.seeded(w * h, "noise2").reshape(h, w))
+    assert host.module("Shared")
+    try:
+        n, nfx = R.res_x * R.res_y, R.fx_x * R.fx_y
+        fx0 = host.global_array("g_pFxMap", 0, (nfx,))
+        rt0 = host.global_array("g_renderTarget", 0, (n,))
+        rt3 = host.global_array("g_renderTarget", 3, (n,))
+        assert fx0 is not None and rt0 is not None and rt3 is not None
+        assert np.array_equal(host.global_array("g_pXboxLogoTPB", 0, (263 * 243,)), pc.seeded(263 * 243, "noise2"))
+        grad = host.global_array("g_gradientUnp16", 0, (256, 8), dtype=np.uint16)
+        assert np.array_equal(grad[:, :4], np.repeat(np.arange(256, dtype=np.uint16)[:, None], 4, axis=1)) and not grad[:, 4:].any()
+        assert np.array_equal(host.global_array("Ball_GetBackground", 0, (n,)), R.ball_background())
+
+        # FX map -> frame -> inverse polar -> blurred in place, through the globals, against the reference on its own globals
+        fx0[:] = pc.seeded(nfx, "noise")
+        R.fxmap(0).ravel()[:nfx] = fx0
+        host.post("Fx_Blit_2x2", rt0, fx0)
+        host.post("Polar_Blit", rt3, rt0, u=1)
+        host.post("BoxBlur32", rt3, rt3, R.res_x, R.res_y, 0.11)
+        r0, r3 = R.render_target(0), R.render_target(3)
+        R.fx_blit_2x2(r0, R.fxmap(0)); R.polar_blit(r3, r0, True); R.old_blur("hv", r3, r3, R.res_x, R.res_y, 0.11)
+        assert_bit_exact(rt3, np.asarray(r3).ravel()[:n], "chain on g_renderTarget")
+    finally:
+        for name in ("Shared", "FxBlitter", "BoxBlur", "Polar"):
+            host.module(name, create=False)
+    assert host.global_array("g_renderTarget", 0, (4,)) is None and host.global_array("g_pFxMap", 0, (4,)) is None
+
+
 def test_pinning_the_callers_frame_buffer(host_and_ref):
     """CkdHost_PinFrameBuffer: same frame, faster copy-back into a caller-owned (malloc'ed) buffer"""
     import time

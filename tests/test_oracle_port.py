@@ -26,6 +26,11 @@ def _run_post(port, case):
         port.fx_blit_2x2(dst, src)
     elif op == "polar":
         port.polar_blit(dst, src, bool(case["inverse"]), alpha=bool(case["alpha"]))
+    elif op == "polar_2x2":
+        port.polar_blit_2x2(dst, src, bool(case["inverse"]))
+    elif op == "test_pattern":
+        fx = port.buf(pc.FX_X * pc.FX_Y, pad); fx[:] = pc.test_pattern()
+        port.fx_blit_2x2(dst, fx)
     elif op == "old_blur":
         if case["inplace"]:
             dst[:] = src0
