@@ -76,7 +76,7 @@ def build(force=False, verbose=False):
         for o in outs:
             print(o)
     if jobs or not os.path.exists(OUT):
-        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs, "-Xcompiler", "-fPIC"], os.path.join(OBJ, "link.log"))
+        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs, "-Xcompiler", "-fPIC", "-lz"], os.path.join(OBJ, "link.log"))
     return OUT
 
 

@@ -80,7 +80,18 @@ void CkdHost_RegisterImage(const char *path, const void *pixels, int width, int 
 	img.pixels.assign(static_cast<const uint8_t *>(pixels), static_cast<const uint8_t *>(pixels) + bytes);
 }
 
-// Image_Load32 / Image_Load8 equivalent: registered pixels -> device image slot
+// a path nobody registered is decoded from its file (host/ckd_image.cpp), like Image_Load32 / Image_Load8 would
+static bool DecodeIntoRegistry(const char *path, int bpp)
+{
+	HostImage img;
+	img.bpp = bpp;
+	if (!ckdhost::DecodeImageFile(path, bpp, img.pixels, img.width, img.height))
+		return false;
+	s_images[path] = std::move(img);
+	return true;
+}
+
+// Image_Load32 / Image_Load8 equivalent: registered (or decoded) pixels -> device image slot
 static bool LoadImage(const char *path, ckd_image slot, int bpp)
 {
 	if (nullptr == s_ctx)
@@ -89,9 +100,12 @@ static bool LoadImage(const char *path, ckd_image slot, int bpp)
 		return false;
 	}
 	auto it = s_images.find(path);
+	if (it == s_images.end() && !DecodeIntoRegistry(path, bpp))
+		return false; // DecodeImageFile has set "Can not load image: <path>" (image.cpp:40)
+	it = s_images.find(path);
 	if (it == s_images.end() || it->second.bpp != bpp)
 	{
-		SetLastError(std::string("Can not load image: ") + path); // image.cpp:40
+		SetLastError(std::string("Can not load image: ") + path);
 		return false;
 	}
 	return Check(ckd_set_image(s_ctx, slot, it->second.pixels.data(), it->second.width, it->second.height, bpp), path);
@@ -371,6 +385,8 @@ namespace ckdhost
 	bool FindImage(const char *path, ImageView &view)
 	{
 		auto it = s_images.find(path);
+		if (it == s_images.end() && DecodeIntoRegistry(path, 4)) // the compositor's art is all Image_Load32 (demo.cpp:198-374)
+			it = s_images.find(path);
 		if (it == s_images.end())
 			return false;
 		view = { it->second.pixels.data(), it->second.width, it->second.height, it->second.bpp };
@@ -1065,6 +1081,8 @@ void FxBlitter_Destroy() { FreeHostImages(g_pFxMap, kNumFxMaps); }
 static bool CopyImage32(const char *path, std::vector<uint32_t> &out)
 {
 	auto it = s_images.find(path);
+	if (it == s_images.end() && DecodeIntoRegistry(path, 4))
+		it = s_images.find(path);
 	if (it == s_images.end() || 4 != it->second.bpp)
 	{
 		SetLastError(std::string("Can not load image: ") + path); // image.cpp:40
@@ -1124,6 +1142,24 @@ int ckdhost_launch()
 	if (!Tunnelscape_Create()) return -6;
 	if (!Shadertoy_Create()) return -7;
 	return 0;
+}
+
+// forget a registered image, so that the next X_Create decodes the file instead (host/ckd_image.cpp)
+void ckdhost_release_image(const char *path) { s_images.erase(path); }
+
+// X_Create of one effect module on its own: 0 twister, 1 landscape, 2 ball, 3 tunnelscape, 4 shadertoy
+int ckdhost_effect_create(int module)
+{
+	s_lastError.clear();
+	switch (module)
+	{
+	case 0: return Twister_Create() ? 0 : -2;
+	case 1: return Landscape_Create() ? 0 : -2;
+	case 2: return Ball_Create() ? 0 : -2;
+	case 3: return Tunnelscape_Create() ? 0 : -2;
+	case 4: return Shadertoy_Create() ? 0 : -2;
+	}
+	return -1;
 }
 
 void ckdhost_destroy()

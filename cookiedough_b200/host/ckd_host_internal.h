@@ -4,6 +4,8 @@
 #include "../../include/ckd_host.h"
 
 #include <stddef.h>
+#include <stdint.h>
+#include <vector>
 
 namespace ckdhost
 {
@@ -13,6 +15,9 @@ namespace ckdhost
 	struct ImageView { const void *pixels; int width, height, bpp; };
 	bool FindImage(const char *path, ImageView &view);
 	void ReleaseImage(const char *path);           // drop the host copy (after it went to the device)
+
+	// host/ckd_image.cpp: decode `path` (PNG or JPEG, relative to the asset root) to BGRA (bpp 4) or L8 (bpp 1)
+	bool DecodeImageFile(const char *path, int bpp, std::vector<uint8_t> &pixels, int &width, int &height);
 
 	// While composing, X_Draw(pDest, ...) renders into d_frame and leaves it on the device (pDest is ignored):
 	// the compositor downloads the finished frame once.

@@ -36,6 +36,9 @@ def _lib():
     L.ckdhost_track_i.argtypes = [C.c_char_p]
     L.ckdhost_draw.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_float]
     L.ckdhost_post.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_uint]
+    L.ckdhost_release_image.argtypes = [C.c_char_p]
+    L.ckdhost_effect_create.argtypes = [C.c_int]
+    L.ckdhost_set_asset_root.argtypes = [C.c_char_p]
     L.ckdhost_module.argtypes = [C.c_int, C.c_int]
     L.ckdhost_global.argtypes = [C.c_int]
     L.ckdhost_global.restype = C.c_void_p
@@ -102,6 +105,16 @@ class Host:
         """CkdHost_RegisterImage: pre-decoded pixels (uint32 BGRA or uint8 L8, HxW) under the path the reference loads them by"""
         arr = np.ascontiguousarray(arr)
         self.L.ckdhost_register_image(path.encode(), arr.ctypes.data, arr.shape[1], arr.shape[0], 1 if arr.dtype == np.uint8 else 4)
+
+    def reload_from_files(self, effect_module, paths, asset_root):
+        """drops the registered copies of 'paths' and runs the module's X_Create again, which then decodes the files under
+        asset_root with the host layer's own PNG/JPEG decoders -- the reference's Image_Load32/Image_Load8 route"""
+        for path in paths:
+            self.L.ckdhost_release_image(path.encode())
+        self.L.ckdhost_set_asset_root(str(asset_root).encode())
+        rc = self.L.ckdhost_effect_create({"twister": 0, "landscape": 1, "ball": 2, "tunnelscape": 3, "shadertoy": 4}[effect_module])
+        if rc != 0:
+            raise capi.CkdError(f"{effect_module}: {self.L.ckdhost_last_error().decode()}")
 
     def context(self):
         """a capi.Context view of the host layer's ckd_ctx (not owning)"""

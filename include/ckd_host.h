@@ -34,6 +34,18 @@ void CkdHost_SetTime(double seconds);
 // bytesPerPixel 4 = BGRA, 1 = luminance.  The pixels are copied.
 void CkdHost_RegisterImage(const char *path, const void *pixels, int width, int height, int bytesPerPixel);
 
+// image.h:7-17 -- the reference's loader, without DevIL: PNG and JPEG decoders of the host layer (host/ckd_image.cpp), BGRA
+// (0xAARRGGBB) or 8-bit luminance, upper-left origin, pointers collected and freed by Image_Destroy.  X_Create / Demo_Create
+// look a path up in the registry first (CkdHost_RegisterImage) and decode the file when it is not there, so a caller that
+// runs next to the reference's target/ directory registers nothing.  Relative paths resolve against the asset root
+// (default: the working directory, like the reference).
+void CkdHost_SetAssetRoot(const char *directory);
+bool Image_Create();
+void Image_Destroy();
+uint32_t *Image_Load32(const std::string &path);
+uint8_t *Image_Load8(const std::string &path);
+uint32_t *Image_Load32_CA(const std::string &pathC, const std::string &pathA);
+
 // Page-locks the caller's frame buffer in place (pDest of main.cpp:307 is an aligned malloc): X_Draw's copy-back then runs at
 // the full PCIe rate instead of through the driver's staging buffers.  Optional; undo before freeing the buffer.
 bool CkdHost_PinFrameBuffer(uint32_t *pDest);

@@ -86,7 +86,7 @@ def test_host_rect_blits_into_a_frame(host_and_ref):
     for op, alpha in (("BlitSrc32", 0.0), ("BlitSrc32A", 0.6), ("BlitAdd32", 0.0), ("BlitAdd32A", 0.35)):
         a, b = pair()
         R.blit(op, a[offs:], sprite, R.res_x, sprite_w, sprite_h, alpha)
-        host.post(op, b[offs:], sprite, R.res_x, sprite_w, sprite_h, f0=alpha)
+        host.post(op, b[offs:], sprite, R.res_x, sprite_w, f0=alpha, u=sprite_h)
         assert_bit_exact(b, a, op)
 
     ribbons = aligned_u32(2160 * (R.res_y - 1) + R.res_x, pad=64); ribbons[:] = pc.seeded(ribbons.size, "noise2")
@@ -150,6 +150,34 @@ def test_host_module_setup_and_globals(host_and_ref):
         for name in ("Shared", "FxBlitter", "BoxBlur", "Polar"):
             host.module(name, create=False)
     assert host.global_array("g_renderTarget", 0, (4,)) is None and host.global_array("g_pFxMap", 0, (4,)) is None
+
+
+def test_effect_created_from_image_files(host_and_ref, tmp_path):
+    """X_Create with nothing registered: the host layer decodes the files itself (Image_Load32 / Image_Load8 without DevIL).
+    The landscape's three maps are written out as PNG (lossless, so the reference sees the same pixels) under the names
+    the reference loads, dropped from the registry, and Landscape_Create reads them back through host/ckd_image.cpp."""
+    from PIL import Image
+    host, R = host_and_ref
+    paths = ["assets/scape/D17.png", "assets/scape/C17W-edit.png", "assets/scape/foggradient.jpg"]
+    for path in paths:
+        arr = R.assets[path]
+        out = tmp_path / path
+        out.parent.mkdir(parents=True, exist_ok=True)
+        if arr.dtype == np.uint8:
+            img = Image.fromarray(arr, "L")
+        else:
+            bgra = arr.view(np.uint8).reshape(arr.shape[0], arr.shape[1], 4)
+            img = Image.fromarray(np.ascontiguousarray(bgra[..., [2, 1, 0, 3]]), "RGBA")
+        with open(out, "wb") as f:       # a PNG stream under the reference's file name: the decoder goes by content
+            img.save(f, "PNG")
+    host.reload_from_files("landscape", paths, tmp_path)
+    R.set_row(500); host.set_row(500)
+    out = np.zeros((R.res_y, R.res_x), dtype=np.uint32)
+    host.draw("landscape", out)
+    assert_bit_exact(out, R.draw("landscape").copy(), "landscape from decoded files")
+    with pytest.raises(Exception, match="Can not load image"):
+        host.reload_from_files("landscape", paths[:1], tmp_path / "nowhere")
+    host.reload_from_files("landscape", paths[:1], tmp_path)
 
 
 def test_pinning_the_callers_frame_buffer(host_and_ref):

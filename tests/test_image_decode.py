@@ -1,0 +1,95 @@
+"""The host layer's own PNG / JPEG decoders (host/ckd_image.cpp; SURVEY 8 row f3, image.cpp:31-73 without DevIL) against
+committed fixtures whose expected pixels were read back with Pillow (tests/golden/make_image_fixtures.py), and -- where the
+reference tree is present -- against every image the reference loads (refdata/assets.npz, decoded by Pillow once)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+IMAGES = os.path.join(REPO, "tests", "golden", "images")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from cookiedough_b200 import capi
+    L = C.CDLL(capi.LIB_PATH)
+    L.ckdhost_image_load.restype = C.c_void_p
+    L.ckdhost_image_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ckdhost_image_free.argtypes = [C.c_void_p]
+    L.ckdhost_set_asset_root.argtypes = [C.c_char_p]
+    L.ckdhost_last_error.restype = C.c_char_p
+    return L
+
+
+def decode(L, path, gray):
+    w, h = C.c_int(), C.c_int()
+    p = L.ckdhost_image_load(path.encode(), int(gray), C.byref(w), C.byref(h))
+    if not p:
+        return None
+    n = w.value * h.value
+    try:
+        buf = (C.c_uint8 * (n * (1 if gray else 4))).from_address(p)
+        return np.frombuffer(buf, dtype=np.uint8 if gray else np.uint32).reshape(h.value, w.value).copy()
+    finally:
+        L.ckdhost_image_free(p)
+
+
+EXPECTED = np.load(os.path.join(IMAGES, "expected.npz"))
+FIXTURES = sorted({k.split(":")[0] for k in EXPECTED.files})
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_decoder_matches_fixture(lib, name):
+    lib.ckdhost_set_asset_root(IMAGES.encode())
+    bgra = decode(lib, name, False)
+    assert bgra is not None, lib.ckdhost_last_error().decode()
+    assert bgra.shape == EXPECTED[name + ":bgra"].shape
+    assert np.array_equal(bgra, EXPECTED[name + ":bgra"]), f"{name}: {np.count_nonzero(bgra != EXPECTED[name + ':bgra'])} BGRA pixels differ"
+    l8 = decode(lib, name, True)
+    assert l8 is not None and np.array_equal(l8, EXPECTED[name + ":l8"]), f"{name}: luminance differs"
+
+
+def test_fixture_set_covers_the_formats():
+    names = set(FIXTURES)
+    assert {"rgb8.png", "rgba8.png", "grey8.png", "greyalpha8.png", "grey1.png", "grey16.png", "rgb16.png", "palette8_trns.png", "palette4.png",
+            "palette2.png", "rgb8_colourkey.png", "rgba8_adam7.png", "rgba16_adam7.png", "base_444.jpg", "base_422.jpg", "base_420.jpg",
+            "prog_444.jpg", "prog_420.jpg", "base_420_restart.jpg", "prog_444_restart.jpg", "grey.jpg", "grey_prog.jpg", "narrow_420.jpg"} <= names
+
+
+def test_errors_are_reported_like_the_reference(lib, tmp_path):
+    lib.ckdhost_set_asset_root(str(tmp_path).encode())
+    assert decode(lib, "missing.png", False) is None
+    assert lib.ckdhost_last_error().decode().startswith("Can not load image: missing.png")      # image.cpp:40
+    good = open(os.path.join(IMAGES, "rgb8.png"), "rb").read()
+    (tmp_path / "crc.png").write_bytes(good[:60] + bytes([good[60] ^ 0x40]) + good[61:])
+    assert decode(lib, "crc.png", False) is None and "CRC" in lib.ckdhost_last_error().decode()
+    (tmp_path / "short.png").write_bytes(good[:len(good) // 2])
+    assert decode(lib, "short.png", False) is None
+    jpeg = open(os.path.join(IMAGES, "base_444.jpg"), "rb").read()
+    (tmp_path / "short.jpg").write_bytes(jpeg[:200])
+    assert decode(lib, "short.jpg", False) is None
+    (tmp_path / "text.png").write_bytes(b"not an image at all, just bytes" * 4)
+    assert decode(lib, "text.png", False) is None and "not a PNG" in lib.ckdhost_last_error().decode()
+
+
+def test_every_reference_asset_decodes_to_the_shared_pixels(lib):
+    """all 105 files the reference loads (90 PNG, 12 baseline + 3 progressive JPEG): the native decoders return exactly the
+    pixels both sides of the parity tests share (Pillow's decode, oracle/build_ref.py prepare_assets)"""
+    target = os.path.join(os.environ.get("CKD_REFERENCE", "/root/reference"), "target")
+    npz_path = os.path.join(REPO, "refdata", "assets.npz")
+    if not os.path.isdir(os.path.join(target, "assets")) or not os.path.exists(npz_path):
+        pytest.skip("reference tree not present on this machine")
+    from cookiedough_b200.assets import SPEC
+    npz = np.load(npz_path)
+    lib.ckdhost_set_asset_root(target.encode())
+    checked = 0
+    for path, spec in SPEC.items():
+        if path not in npz.files:
+            continue
+        got = decode(lib, path, bool(spec[2]))
+        assert got is not None, lib.ckdhost_last_error().decode()
+        assert got.shape == npz[path].shape and np.array_equal(got, npz[path]), path
+        checked += 1
+    assert checked >= 100
