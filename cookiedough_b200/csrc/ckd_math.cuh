@@ -75,10 +75,14 @@ __device__ __forceinline__ float lutcosf(CosLut lut, float angle)
 	// above: bit 31 of it is set exactly when cvttss2si overflows, and its sign smear clears the index -- one shift instead of
 	// a compare and a select.  (An F2I-free variant built on the 2^23 rounding trick was measured slower: these kernels are
 	// issue bound, not XU bound -- profiles/r01_notes.md.)
+	// Written as PRMT (byte 3's sign replicated into every byte) + one three-input LOP3 on the pre-shifted value: left to
+	// itself ptxas turns the C expression into ISETP + SEL next to the shift and the mask, one issue slot more per lookup.
 	const unsigned u = __float2uint_rz(angle);
-	const unsigned index = u & 2047u & ~unsigned(int(u) >> 31);
+	unsigned smear, offset;
+	asm("prmt.b32 %0, %1, 0, 0xbbbb;" : "=r"(smear) : "r"(u));
+	asm("lop3.b32 %0, %1, 0x3ff8, %2, 0x40;" : "=r"(offset) : "r"(u << 3), "r"(smear)); // a & b & ~c = (u*8) & (2047*8) & ~smear
 	float2 pair;                               // (LUT[i], LUT[i+1] - LUT[i])
-	asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pair.x), "=f"(pair.y) : "r"(lut + index*8u));
+	asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pair.x), "=f"(pair.y) : "r"(lut + offset));
 	return pair.x + pair.y*(angle - truncf(angle)); // lerpf(a, b, t) = a + (b-a)*t, Math.h:52-56
 }
 

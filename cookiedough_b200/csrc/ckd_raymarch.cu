@@ -8,6 +8,9 @@
 
 #include "ckd_internal.h"
 #include "ckd_math.cuh"
+
+// unroll factor of the fixed-count march loops (plasma 24, spikey specular-only 36, laura 32 steps)
+constexpr int kFixedUnroll = 1; // 2 and 4 measured: no change (the loop overhead is not what limits these kernels)
 #include "ckd_hostmath.h"
 
 using namespace ckd;
@@ -84,7 +87,7 @@ struct PlasmaEffect
 
 		float total = 0.f, march = 0.f;
 		float hx = 0.f, hy = 0.f, hz = 0.f;
-		#pragma unroll 1
+		#pragma unroll kFixedUnroll
 		for (int iStep = 0; iStep < 24; ++iStep)
 		{
 			march = fPlasma(e.lut, hx, hy, hz, f.time);
@@ -314,7 +317,7 @@ struct SpikeySpecOnlyEffect
 
 		float hx = 0.f, hy = 0.f, hz = 0.f;
 		float march = 1.f, total = 0.f;
-		#pragma unroll 1
+		#pragma unroll kFixedUnroll
 		for (int iStep = 0; iStep < 36; ++iStep)
 		{
 			hx = ox + dir.x*total;
@@ -451,7 +454,7 @@ struct LauraEffect
 		const vec3 origin = { 0.f, 0.f, f.originZ };
 		vec3 hit = { 0.f, 0.f, 0.f };
 		float march = 0.f, total = 0.f;
-		#pragma unroll 1
+		#pragma unroll kFixedUnroll
 		for (int iStep = 0; iStep < 32; ++iStep)
 		{
 			hit.x = origin.x + dir.x*total;

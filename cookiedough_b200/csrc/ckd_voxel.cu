@@ -71,6 +71,21 @@ __device__ __forceinline__ uint32_t sample_argb(const uint32_t *__restrict__ tex
 	return bilerp_argb(__ldg(tex + t.i00), __ldg(tex + t.i10), __ldg(tex + t.i01), __ldg(tex + t.i11), t.fu, t.fv);
 }
 
+// the raw texels of one step (height + colour gathers, fog entry): loaded one chunk ahead of their use
+struct RawSample { int h[4]; uint32_t c[4]; uint32_t fog, fu, fv; };
+
+__device__ __forceinline__ RawSample fetch_sample(const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap, const uint32_t *__restrict__ fogGradient,
+	unsigned iStep, int curX, int curY, unsigned mapAnd, unsigned mapShift)
+{
+	const TexCoords t = prep_uvs(curX, curY, mapAnd, mapShift);
+	RawSample r;
+	r.h[0] = __ldg(heightMap + t.i00); r.h[1] = __ldg(heightMap + t.i10); r.h[2] = __ldg(heightMap + t.i01); r.h[3] = __ldg(heightMap + t.i11);
+	r.c[0] = __ldg(colorMap + t.i00); r.c[1] = __ldg(colorMap + t.i10); r.c[2] = __ldg(colorMap + t.i01); r.c[3] = __ldg(colorMap + t.i11);
+	r.fog = __ldg(fogGradient + (iStep >> 1));
+	r.fu = t.fu; r.fv = t.fv;
+	return r;
+}
+
 // ---- cspanISSE16 (cspan.h:47-78) --------------------------------------------------------------------------------------
 // 16.16 fixed-point ramp from colour A to colour B over 'length' pixels of which the last... 'drawLength' are drawn, with
 // the reference's pmaddwd / pmuldq quirks restated literally: the divisor and the deltas are read as
@@ -351,17 +366,25 @@ __global__ void __launch_bounds__(kRowsPerBlock*32) tunnelscape_kernel(uint32_t 
 		carryLastColor = unpack16(__ldg(colorMap + (U|V)));
 	}
 
+	// The samples of a chunk do not depend on the carry, and at 4K there are only 2160 rays (15 warps per SM): the gathers of
+	// the NEXT chunk are issued before this chunk's scan and span stores, so their L2 latency overlaps the emission
+	// instead of heading every iteration (registers are free at this occupancy).
+	RawSample next = fetch_sample(heightMap, colorMap, fogGradient, lane, int(unsigned(fpFromX) + (lane+1)*unsigned(f.dX)), int(unsigned(f.fpFromY) + (lane+1)*unsigned(f.dY)), 2047u, 11u);
+
 	for (unsigned base = 0; base < 512; base += 32)
 	{
 		const unsigned iStep = base + lane;
-		const int curX = int(unsigned(fpFromX) + (iStep+1)*unsigned(f.dX));
-		const int curY = int(unsigned(f.fpFromY) + (iStep+1)*unsigned(f.dY));
+		const RawSample raw = next;
+		if (base + 32 < 512)
+		{
+			const unsigned nStep = iStep + 32;
+			next = fetch_sample(heightMap, colorMap, fogGradient, nStep, int(unsigned(fpFromX) + (nStep+1)*unsigned(f.dX)), int(unsigned(f.fpFromY) + (nStep+1)*unsigned(f.dY)), 2047u, 11u);
+		}
 
-		const TexCoords t = prep_uvs(curX, curY, 2047u, 11u);
-		const unsigned mapHeight = sample_u8(heightMap, t);
-		Color16 color = unpack16(sample_argb(colorMap, t));
+		const unsigned mapHeight = bilerp_u8(raw.h[0], raw.h[1], raw.h[2], raw.h[3], int(raw.fu), int(raw.fv));
+		Color16 color = unpack16(bilerp_argb(raw.c[0], raw.c[1], raw.c[2], raw.c[3], raw.fu, raw.fv));
 
-		const Color16 fog = unpack16(__ldg(fogGradient + (iStep >> 1)));
+		const Color16 fog = unpack16(raw.fog);
 		#pragma unroll
 		for (int i = 0; i < 4; ++i) color.c[i] = subs16(color.c[i], fog.c[i]);
 
