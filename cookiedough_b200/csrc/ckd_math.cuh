@@ -86,8 +86,30 @@ __device__ __forceinline__ float lutcosf(CosLut lut, float angle)
 	return pair.x + pair.y*(angle - truncf(angle)); // lerpf(a, b, t) = a + (b-a)*t, Math.h:52-56
 }
 
+// The same lookup without a single conversion instruction, for the march loops of the raymarchers, where F2I + FRND keep
+// the XU pipe as busy as the issue port (ncu: XU 70 %, issue 85 %; profiles/r01_notes.md).  For 0 <= angle < 2^23,
+// t = angle + 2^23 rounded TOWARDS ZERO is exactly 2^23 + trunc(angle): the low mantissa bits of t are the integer part
+// (-> table offset) and t - 2^23 is truncf(angle) (-> fraction), all on the FMA/ALU pipes.  NaN and +inf come out as NaN
+// from either variant (NaN fraction times a table entry).  For FINITE scaled angles >= 2^23 (|x| >= 25736 rad) the trick
+// does not hold -- the reference then indexes with the low bits of the integer and a zero fraction -- so a kernel may be
+// built on this variant only where the host has PROVED every angle of the frame smaller (LutRangeProof in
+// ckd_raymarch.cu: effects whose distance functions are bounded, checked against the frame's parameters); every other
+// frame runs the exact lutcosf above.
+struct CosLutFast { unsigned handle; };
+
+__device__ __forceinline__ float lutcosf(const CosLutFast &lut, float angle)
+{
+	angle = fabsf(angle);
+	angle *= (1.f/k2PI)*2048;
+	const float t = __fadd_rz(angle, 8388608.f);
+	const unsigned offset = (__float_as_uint(t) << 3) & 0x3ff8u;
+	float2 pair;
+	asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pair.x), "=f"(pair.y) : "r"(lut.handle + offset));
+	return pair.x + pair.y*(angle - (t - 8388608.f));
+}
+
 // ARRESTED_DEV_LEGACY (main.h:9): lutsinf(a) = lutcosf(a + pi/2)
-__device__ __forceinline__ float lutsinf(CosLut lut, float angle)
+template <class Lut> __device__ __forceinline__ float lutsinf(const Lut &lut, float angle)
 {
 	return lutcosf(lut, angle + kPI*0.5f);
 }
@@ -385,21 +407,21 @@ __device__ __forceinline__ void fast_norm3(const RsqrtTab tab, vec3 &v)
 __device__ __forceinline__ float fast_len3(const vec3 &v) { return sqrtf(dp_ps3(v, v)); }
 
 // Shadertoy::rotX/rotY/rotZ, shadertoy-util.h:31-59
-__device__ __forceinline__ void rotX(CosLut lut, float angle, float &Y, float &Z)
+template <class Lut> __device__ __forceinline__ void rotX(const Lut &lut, float angle, float &Y, float &Z)
 {
 	const float cosine = lutcosf(lut, angle), sine = lutsinf(lut, angle);
 	const float rY = cosine*Y + -sine*Z;
 	const float rZ = sine*Y + cosine*Z;
 	Y = rY; Z = rZ;
 }
-__device__ __forceinline__ void rotY(CosLut lut, float angle, float &X, float &Z)
+template <class Lut> __device__ __forceinline__ void rotY(const Lut &lut, float angle, float &X, float &Z)
 {
 	const float cosine = lutcosf(lut, angle), sine = lutsinf(lut, angle);
 	const float rX = cosine*X + sine*Z;
 	const float rZ = -sine*X + cosine*Z;
 	X = rX; Z = rZ;
 }
-__device__ __forceinline__ void rotZ(CosLut lut, float angle, float &X, float &Y)
+template <class Lut> __device__ __forceinline__ void rotZ(const Lut &lut, float angle, float &X, float &Y)
 {
 	const float cosine = lutcosf(lut, angle), sine = lutsinf(lut, angle);
 	const float rX = cosine*X + sine*Y;

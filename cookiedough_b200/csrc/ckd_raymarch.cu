@@ -9,6 +9,8 @@
 #include "ckd_internal.h"
 #include "ckd_math.cuh"
 
+#include <type_traits>
+
 // unroll factor of the fixed-count march loops (plasma 24, spikey specular-only 36, laura 32 steps)
 constexpr int kFixedUnroll = 1; // 2 and 4 measured: no change (the loop overhead is not what limits these kernels)
 #include "ckd_hostmath.h"
@@ -45,9 +47,10 @@ __device__ __forceinline__ void rot_y(const Rot r, float &X, float &Z) { const f
 // lerp to a constant per lane: Shadertoy::vLerp4(A, B, f) = A + f*(B-A), shadertoy-util.h:62-67
 __device__ __forceinline__ float vlerp(float a, float b, float f) { return a + f*(b-a); }
 
-struct Env
+// Lut = CosLutFast (conversion-free lookups that track their largest angle) or CosLut (exact for every input)
+template <class Lut> struct EnvT
 {
-	CosLut lut;          // shared-memory cosine LUT
+	Lut lut;             // shared-memory cosine LUT
 	RsqrtTab rsqrt;
 	FrameGeom geom;
 };
@@ -64,7 +67,7 @@ struct PlasmaFrame
 	float gamma;
 };
 
-__device__ __forceinline__ float fPlasma(CosLut lut, float px, float py, float pz, float time)
+template <class Lut> __device__ __forceinline__ float fPlasma(const Lut &lut, float px, float py, float pz, float time)
 {
 	const float sine = 0.2f*lutsinf(lut, px-py);
 	const float fX = sine + lutcosf(lut, px*0.33f);
@@ -76,7 +79,7 @@ __device__ __forceinline__ float fPlasma(CosLut lut, float px, float py, float p
 struct PlasmaEffect
 {
 	PlasmaFrame f;
-	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	template <class Lut> __device__ __forceinline__ uint32_t shade(const EnvT<Lut> &e, unsigned iX, unsigned iY) const
 	{
 		float u, v;
 		to_uv_fxmap(e.geom, iX, iY, 4.f, u, v);
@@ -122,7 +125,7 @@ struct NautilusFrame
 	Rot roll;
 };
 
-__device__ __forceinline__ float fNautilus(CosLut lut, const NautilusFrame &f, float px, float py, float pz)
+template <class Lut> __device__ __forceinline__ float fNautilus(const Lut &lut, const NautilusFrame &f, float px, float py, float pz)
 {
 	const float cosX = lutcosf(lut, lutcosf(lut, px + f.gx)*px - lutcosf(lut, py + f.gy)*py);
 	const float cosY = lutcosf(lut, pz*0.33f*px - f.gz*py);
@@ -134,7 +137,7 @@ __device__ __forceinline__ float fNautilus(CosLut lut, const NautilusFrame &f, f
 struct NautilusEffect
 {
 	NautilusFrame f;
-	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	template <class Lut> __device__ __forceinline__ uint32_t shade(const EnvT<Lut> &e, unsigned iX, unsigned iY) const
 	{
 		float u, v;
 		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
@@ -200,8 +203,8 @@ struct SpikeyFrame
 	float warmup;
 };
 
-template <bool GOLDEN_ANGLE>
-__device__ __forceinline__ float fSpikey(CosLut lut, const SpikeyFrame &f, float px, float py, float pz)
+template <bool GOLDEN_ANGLE, class Lut>
+__device__ __forceinline__ float fSpikey(const Lut &lut, const SpikeyFrame &f, float px, float py, float pz)
 {
 	// fSpikey1 (kGoldenAngle) / fSpikey2 (kGoldenRatio), shadertoy.cpp:418-430
 	constexpr float scale = (GOLDEN_ANGLE ? kGoldenAngle : kGoldenRatio)*0.1f;
@@ -213,7 +216,7 @@ __device__ __forceinline__ float fSpikey(CosLut lut, const SpikeyFrame &f, float
 struct SpikeyCloseEffect
 {
 	SpikeyFrame f;
-	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	template <class Lut> __device__ __forceinline__ uint32_t shade(const EnvT<Lut> &e, unsigned iX, unsigned iY) const
 	{
 		float u, v;
 		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
@@ -259,7 +262,7 @@ struct SpikeyCloseEffect
 struct SpikeyDistantEffect
 {
 	SpikeyFrame f;
-	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	template <class Lut> __device__ __forceinline__ uint32_t shade(const EnvT<Lut> &e, unsigned iX, unsigned iY) const
 	{
 		float u, v;
 		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
@@ -305,7 +308,7 @@ struct SpikeyDistantEffect
 struct SpikeySpecOnlyEffect
 {
 	SpikeyFrame f;
-	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	template <class Lut> __device__ __forceinline__ uint32_t shade(const EnvT<Lut> &e, unsigned iX, unsigned iY) const
 	{
 		float u, v;
 		to_uv_fxmap(e.geom, iX, iY, kGoldenRatio, u, v);
@@ -354,7 +357,7 @@ struct SinusesFrame
 	float specPow, gamma, offsX;
 };
 
-__device__ __forceinline__ float fSinMap(CosLut lut, float px0, float py0, float pZ)
+template <class Lut> __device__ __forceinline__ float fSinMap(const Lut &lut, float px0, float py0, float pZ)
 {
 	const float zMod = pZ*0.314f;
 	const float pathCos = lutcosf(lut, zMod);
@@ -377,7 +380,7 @@ __device__ __forceinline__ float fSinMap(CosLut lut, float px0, float py0, float
 struct SinusesEffect
 {
 	SinusesFrame f;
-	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	template <class Lut> __device__ __forceinline__ uint32_t shade(const EnvT<Lut> &e, unsigned iX, unsigned iY) const
 	{
 		float u, v;
 		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
@@ -432,7 +435,7 @@ struct LauraFrame
 	Rot yaw, pitch, roll;
 };
 
-__device__ __forceinline__ float fLaura(CosLut lut, float px, float py, float pz)
+template <class Lut> __device__ __forceinline__ float fLaura(const Lut &lut, float px, float py, float pz)
 {
 	return lutcosf(lut, px)+lutcosf(lut, py)+lutcosf(lut, pz) + 1.f;
 }
@@ -440,7 +443,7 @@ __device__ __forceinline__ float fLaura(CosLut lut, float px, float py, float pz
 struct LauraEffect
 {
 	LauraFrame f;
-	__device__ __forceinline__ uint32_t shade(const Env &e, unsigned iX, unsigned iY) const
+	template <class Lut> __device__ __forceinline__ uint32_t shade(const EnvT<Lut> &e, unsigned iX, unsigned iY) const
 	{
 		float u, v;
 		to_uv_fxmap(e.geom, iX, iY, 2.f, u, v);
@@ -534,7 +537,9 @@ __device__ __forceinline__ bool next_tile(const TileQueue &q, unsigned &iX, unsi
 	return true;
 }
 
-template <class Effect>
+// FAST = true: the conversion-free LUT lookups (CosLutFast), launched only for frames whose LUT angles the host has proved
+// in range (LutRangeProof below); FAST = false: the exact lookups, bit-exact for every input.
+template <class Effect, bool FAST>
 __global__ void __launch_bounds__(kTileX*kTileY) raymarch_kernel(const Effect effect, uint32_t *__restrict__ pDest, const FrameGeom geom,
 	const float2 *__restrict__ g_lut2, const RsqrtTab rsqrt, const TileQueue queue)
 {
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(kTileX*kTileY) raymarch_kernel(const Effect ef
 		*queue.nextCounter = 0;
 	const CosLut lut = stage_cos_lut(s_lut2, g_lut2);
 
-	Env env = { lut, rsqrt, geom };
+	const typename std::conditional<FAST, EnvT<CosLutFast>, EnvT<CosLut>>::type env = { { lut }, rsqrt, geom };
 
 	unsigned iX, iY;
 	while (next_tile(queue, iX, iY))
@@ -670,17 +675,41 @@ TileQueue MakeQueue(ckd_ctx *ctx, const FrameGeom &geom)
 	return q;
 }
 
-template <class Effect> int LaunchRaymarch(ckd_ctx *ctx, const Effect &effect, uint32_t *d_fxmap, const char *name)
+// Host-side proof that every LUT angle of a frame stays below the range of the conversion-free lookup (CosLutFast:
+// scaled angle < 2^23, i.e. |angle| < 25735.9 rad).  It exists for the four effects whose distance function is BOUNDED --
+// a sum of table values, each within [-1, 1] -- so the march total, hence every sample position, is bounded by the step
+// count alone; what remains are the frame's own parameters (time offsets, origins), which 'add' folds in.  The spikey
+// variants march |p| - radius, which grows geometrically on rays that miss (their background pixels do reach such
+// angles, and the reference's aliased lookups there are part of the picture): they always run the exact kernel.
+// The induction behind the bound: while every angle so far was in range, every table value so far is within [-1, 1] (a
+// lerp between two entries), so the next position obeys the bound, so the next angle is in range.  NaN/inf parameters fail
+// the comparison and select the exact kernel.
+struct LutRangeProof
 {
+	double worst = 0.0;            // largest |angle| (radians) any lookup of the frame can see
+	void add(double bound) { if (!(bound <= worst)) worst = bound; } // NaN-proof: a NaN bound sticks
+	bool holds() const { return worst < 8000.0; }                     // 3x below 25735.9: float rounding is no concern
+};
+
+template <class Effect> int LaunchRaymarch(ckd_ctx *ctx, const Effect &effect, uint32_t *d_fxmap, const char *name, const LutRangeProof *proof = nullptr)
+{
+	static const bool forceExact = nullptr != getenv("CKD_EXACT_LUT"); // tests: run every frame through the exact kernel
 	const FrameGeom geom = MakeGeom(ctx);
+	const RsqrtTab rsqrt = { ctx->d_rsqrtTab, ctx->rsqrtLog2Bin };
 	const TileQueue queue = MakeQueue(ctx, geom);
 	const int blocks = int(std::min<unsigned>(ckd_div_up(queue.numTiles, kTileY), unsigned(ctx->numSMs)*8));
-	const RsqrtTab rsqrt = { ctx->d_rsqrtTab, ctx->rsqrtLog2Bin };
 	ckd_prof_begin(ctx, name, 4.0*geom.fxX*geom.fxY);
-	raymarch_kernel<Effect><<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(effect, d_fxmap, geom, ctx->d_cosLUT2, rsqrt, queue);
+	if (nullptr != proof && proof->holds() && !forceExact)
+		raymarch_kernel<Effect, true><<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(effect, d_fxmap, geom, ctx->d_cosLUT2, rsqrt, queue);
+	else
+		raymarch_kernel<Effect, false><<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(effect, d_fxmap, geom, ctx->d_cosLUT2, rsqrt, queue);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
 }
+
+// |u| and |v| of to_uv_fxmap for any pixel of the map
+double MaxU(const FrameGeom &g, double scale) { return 0.5*scale*double(g.oneOverAspect); }
+double MaxV(double scale) { return 0.5*scale; }
 
 void CopyColor(float *dst, const ckdh::vec4 &c, int n)
 {
@@ -708,7 +737,18 @@ extern "C" int ckd_plasma_draw(ckd_ctx *ctx, const ckd_plasma_params *p, float t
 	fx.f.dirSin = ckdh::lutsinf(lut, angle);
 	fx.f.gamma = p->gamma;
 
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_plasma"));
+	// fPlasma = |(fX, fY, fZ)| - 0.8 with |f| <= 1.2: march in [-0.8, 1.28], 24 steps of march*0.809 -> |total| <= 24.9;
+	// h = d*total with |dx| <= |u|*aspect + 0.75, |dy| <= |v|, |dz| <= |u| + 0.75; angles: hx - hy + pi/2, hx*0.33, hy*0.43,
+	// (5*time + hz)*0.53 (shadertoy.cpp:201-209)
+	LutRangeProof proof;
+	{
+		const FrameGeom g = MakeGeom(ctx);
+		const double total = 25.0, u = MaxU(g, 4.0), v = MaxV(4.0);
+		const double hx = (u*double(g.aspect) + 0.75)*total, hy = v*total, hz = (u + 0.75)*total;
+		proof.add(hx + hy + 1.6);
+		proof.add((5.0*fabs(double(time)) + hz)*0.53);
+	}
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_plasma", &proof));
 	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
 }
 
@@ -730,7 +770,18 @@ extern "C" int ckd_nautilus_draw(ckd_ctx *ctx, const ckd_nautilus_params *p, flo
 	fx.f.funkCos = ckdh::lutcosf(lut, time*ckdh::kGoldenRatio*0.1f);
 	fx.f.roll = MakeRot(ctx, p->roll*time);
 
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_nautilus"));
+	// fNautilus = dotted*0.5 - 0.7 in [-0.7, 0.8]; total starts at 0.01 and takes <= 48 steps of march*0.628 -> |total| <= 24.2;
+	// |dir| = 1 (+ the RSQRTPS error), taps at +0.15 and +cosHitOffs: |p| <= 24.3 + 0.15 + |cosHitOffs| (shadertoy.cpp:289-298)
+	LutRangeProof proof;
+	{
+		const double p = 24.3*1.001 + 0.15 + fabs(double(fx.f.cosHitOffs));
+		proof.add(p + fabs(double(fx.f.gx)));
+		proof.add(p + fabs(double(fx.f.gy)));
+		proof.add(2.0*1.001*p);                                  // cos*px - cos*py
+		proof.add(0.33*p*p + fabs(double(fx.f.gz))*p);
+		proof.add(2.8*p + fabs(double(fx.f.time)));
+	}
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_nautilus", &proof));
 	CKD_TRY(ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]));
 	const float blur = ckdh::BoxBlurScale(p->blur);
 	if (0.f != blur)
@@ -891,7 +942,13 @@ extern "C" int ckd_sinuses_draw(ckd_ctx *ctx, const ckd_sinuses_params *p, float
 	fx.f.origin[1] = cosine*3.14f + sine*ckdh::kGoldenRatio;
 	fx.f.origin[2] = pathTime;
 
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_sinuses"));
+	// fSinMap = (|(cosX, cosY, cosZ)| - 1.025)*1.33 in [-1.37, 0.95]; <= 32 steps of march*0.814 -> |total| <= 35.7; |dir| = 1;
+	// normal taps at +0.2: |p_i| <= |origin_i| + 36; inside: |pX| <= |px0| + 4.74, |pY| <= |py0| + 4.76, every angle is at
+	// most 1.0175*|coordinate| + pi/2 or 0.394*|coordinate| + 1 (shadertoy.cpp:879-899)
+	LutRangeProof proof;
+	for (int i = 0; i < 3; ++i)
+		proof.add(1.0175*(fabs(double(fx.f.origin[i])) + 36.0*1.001 + 0.2 + 4.76) + 1.6);
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_sinuses", &proof));
 	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
 }
 
@@ -908,6 +965,10 @@ extern "C" int ckd_laura_draw(ckd_ctx *ctx, const ckd_laura_params *p, float tim
 	fx.f.pitch = MakeRot(ctx, p->pitch);
 	fx.f.roll = MakeRot(ctx, p->roll*time);
 
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_laura"));
+	// fLaura = three table values + 1 in [-2, 4]; 32 steps of march*0.5 -> |total| <= 64; |dir| = 1; hit = origin + dir*total,
+	// normal taps at +0.1628; the angles are the coordinates themselves (shadertoy.cpp:998-1015)
+	LutRangeProof proof;
+	proof.add(fabs(double(fx.f.originZ)) + 64.1*1.001 + 0.17);
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_laura", &proof));
 	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
 }

@@ -75,6 +75,12 @@ SCENARIOS = [
     ("plasma_gamma", "plasma", "plasma", None, 2600, {"plasma:Gamma": 2.2, "plasma:Desaturation": 0.5, "plasma:Hue": 4.0}),
     ("sinuses_spec", "sinuses", "sinuses", None, 7800, {"sinusesTunnel:Specular": 7.5, "sinusesTunnel:Roll": 0.9, "sinusesTunnel:OffsX": 0.25}),
     ("laura_yaw", "laura", "laura", None, 8900, {"laura:Yaw": 0.6, "laura:Pitch": -0.3, "laura:Saturate": 1.3}),
+    # LUT angles far outside the table's exact range (scaled angle >= 2^23: the reference's lutcosf aliases there): these
+    # frames must take the exact-lookup kernel on the device (LutRangeProof in csrc/ckd_raymarch.cu)
+    ("plasma_far", "plasma", "plasma", None, 2600, {"plasma:Speed": 40000.0}),
+    ("nautilus_far", "nautilus", "nautilus", None, 5700, {"nautilus:Speed": 300.0, "nautilus:Blur": 0.0}),
+    ("sinuses_far", "sinuses", "sinuses", None, 7800, {"sinusesTunnel:Speed": 300.0}),
+    ("laura_far", "laura", "laura", None, 8900, {"laura:Speed": 500.0}),
 ]
 SCENARIO_ROW_STEP = 8
 
@@ -259,6 +265,25 @@ def main():
     with open(os.path.join(HERE, "golden_demo_720.json"), "w") as f:
         json.dump({"meta": meta, "frames": demo}, f, indent=1)
     if sys.argv[1:3] == ["--only", "demo"]:
+        return
+
+    if sys.argv[1:3] == ["--only", "effects"]:   # refresh the effect pins alone (new cases); existing pins may not move
+        with tempfile.TemporaryDirectory() as tmp:
+            parts = {}
+            for mode in ("timeline", "scenario"):
+                part = os.path.join(tmp, mode + ".json")
+                subprocess.check_call([sys.executable, os.path.abspath(__file__), "--child", mode, part])
+                with open(part) as f:
+                    parts[mode] = json.load(f)
+        path = os.path.join(HERE, "golden_effects_720.json")
+        with open(path) as f:
+            golden = json.load(f)
+        moved = [f"{mode}/{k}" for mode in parts for k, v in golden[mode].items() if parts[mode].get(k, {}).get("sha256") != v["sha256"]]
+        if moved:
+            sys.exit(f"existing pins changed: {moved}")
+        golden["timeline"], golden["scenario"] = parts["timeline"], parts["scenario"]
+        with open(path, "w") as f:
+            json.dump(golden, f, indent=1)
         return
 
     if sys.argv[1:3] == ["--only", "post"]:   # refresh the post-chain pins alone (new cases); existing pins may not move

@@ -4,6 +4,8 @@ Integer paths (voxel casters + their post ops) must be bit-exact; float paths (r
 2 LSB per channel with >= 99.5 % of the pixels exact (BASELINE.json north star)."""
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 
@@ -11,6 +13,7 @@ from cookiedough_b200 import capi
 from util import INTEGER_EFFECTS, assert_bit_exact, assert_float_parity, pixel_stats, seed_frame, sha256_u32
 
 pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _params(case):
@@ -49,6 +52,22 @@ def test_every_golden_effect_case(ctx_synth, golden_effects):
             if max_delta > 2 or exact < 97.0:  # 288-pixel crop: a few 1-LSB pixels are within the tolerance
                 failures.append(f"{label}: crop {exact:.2f}% exact, max delta {max_delta}")
     assert not failures, "\n".join(failures)
+
+
+def test_golden_cases_through_the_exact_lut_kernel():
+    """The raymarchers run on the conversion-free LUT lookup wherever the host proves the frame's angles in range (every
+    timeline row); CKD_EXACT_LUT=1 sends every frame through the exact-lookup kernel instead, which must reproduce the
+    same pins -- including the *_far scenarios, whose angles alias in the reference's table and never take the fast one."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CKD_EXACT_LUT="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k", "test_every_golden_effect_case"],
+                       env=env, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_far_scenarios_exist(golden_effects):
+    assert {"plasma_far", "nautilus_far", "sinuses_far", "laura_far"} <= set(golden_effects["scenario"])
 
 
 LIVE_ROWS = [
