@@ -62,7 +62,7 @@ FLOP_PER_FX_PIXEL = {
 # what ncu says bounds each kernel (profiles/r01_notes.md): reported next to the roofline fraction so that a small HBM
 # fraction of a kernel that is not HBM bound is not misread
 LIMITER = {
-    "raymarch": "instruction issue (87 % issue-active) with the XU pipe (F2I/FRND of lutcosf) at 60-70 %; no FMA contraction allowed",
+    "raymarch": "instruction issue: FMUL/FADD chains without FMA contraction (bit parity) + 4 non-FP instructions per LUT lookup; the XU pipe is out of the picture since the conversion-free lookup (spikey kernels: exact lookup, XU 70 %)",
     "old_blur": "integer ALU pipe + dependent chain of the saturating in-place recurrence (ALU 57 %, issue 62 %); DRAM traffic = algorithmic bytes",
     "voxel": "L2 gather latency of the height/colour map samples (warp per ray)",
     "polar_blit": "dependent map -> texel gather chain; DRAM traffic = algorithmic bytes",

@@ -688,7 +688,7 @@ struct LutRangeProof
 {
 	double worst = 0.0;            // largest |angle| (radians) any lookup of the frame can see
 	void add(double bound) { if (!(bound <= worst)) worst = bound; } // NaN-proof: a NaN bound sticks
-	bool holds() const { return worst < 8000.0; }                     // 3x below 25735.9: float rounding is no concern
+	bool holds() const { return worst < 20000.0; }                    // 22 % below 25735.9; the bounds themselves are generous and float rounding is 1e-7
 };
 
 template <class Effect> int LaunchRaymarch(ckd_ctx *ctx, const Effect &effect, uint32_t *d_fxmap, const char *name, const LutRangeProof *proof = nullptr)

@@ -23,7 +23,7 @@ METRICS = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_e
 
 def bench_name(kernel):
     """kernel function name -> the name bench.py's per-kernel profiler uses"""
-    m = re.search(r"raymarch_kernel<.*?(\w+)Effect>", kernel)
+    m = re.search(r"raymarch_kernel<.*?(\w+)Effect[,>]", kernel)   # raymarch_kernel<Effect, FAST>
     if m:
         name = re.sub(r"(?<!^)(?=[A-Z])", "_", m.group(1)).lower()
         return "raymarch_" + name
