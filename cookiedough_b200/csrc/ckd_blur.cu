@@ -367,7 +367,8 @@ __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t 
 				// KM > 0: the next batch's pixels are requested before this batch's chain (the compiler cannot hoist them over the
 				// ring stores itself); KM == 0: plain loads at the top of the batch measured faster than carrying 16 more registers
 				int pxNext[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-				if (KM > 0) loadPx(tb + 8, pxNext);
+				// (the batch after the last one belongs to a stage that may still be in flight: the last batch requests itself again)
+				if (KM > 0) loadPx(min(tb + 8, batchEnd - 8), pxNext);
 				else { loadPx(tb, px); loadSpx(tb, spx); }
 
 				const unsigned outPos = (tb - edgeSpan) & (kRing-1);
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 	const int lastMine = (cnt == unsigned(QT)) ? 1 : 0;
 
 	// one block.  kSteady: every step is Add + Sub at full weight and all operands exist
-	auto block = [&](unsigned tb, auto steadyTag)
+	auto block = [&](unsigned tb, unsigned landed, auto steadyTag)   // pixels [0, landed) are in the ring
 	{
 		constexpr bool kSteady = decltype(steadyTag)::value;
 		const unsigned t0 = tb + s0;
@@ -571,8 +572,11 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 		#pragma unroll
 		for (int q = 0; q <= QT; ++q)
 		{
-			unsigned v;
-			asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(inAddr + q*kStep) : "memory");
+			unsigned v = 0;
+			// ramp blocks touch pixels that do not exist (t0 - 1 = -1, positions past the line) or whose stage is still in
+			// flight (past the end of a cut-off block): their values are masked below, the read itself is skipped
+			if (kSteady || t0 + q - 1 < landed)
+				asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(inAddr + q*kStep) : "memory");
 			pxs[q] = int(v);
 		}
 
@@ -649,18 +653,15 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 			lastOut1 = lastMine ? o[QT-1] : o[(QT >= 2) ? QT-2 : 0];
 		}
 
-		// stores: a step outside the share (or outside the line, at the ramps) goes to a dummy slot behind the ring
+		// stores: a step outside the share (or outside the line, at the ramps) is not written
 		const unsigned outPos = (t0 - edgeSpan) & (kRing-1);
-		const unsigned dummy = outBase + (kRing + kMirror - 1)*kStep;
 		if (kSteady && outPos + QT <= kRing)
 		{
 			const unsigned addr0 = outBase + outPos*kStep;
 			#pragma unroll
 			for (int q = 0; q < QT; ++q)
-			{
-				const unsigned addr = (q < QT-1 || lastMine) ? addr0 + q*kStep : dummy;
-				asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(o[q]) : "memory");
-			}
+				if (q < QT-1 || lastMine)
+					asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr0 + q*kStep), "r"(o[q]) : "memory");
 		}
 		else
 		{
@@ -670,8 +671,8 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 				const unsigned t = t0 + q;
 				bool emit = (q < QT-1) || lastMine;
 				if (!kSteady) emit = emit && t >= edgeSpan && t < total;
-				const unsigned addr = emit ? outBase + ((outPos + q) & (kRing-1))*kStep : dummy;
-				asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(o[q]) : "memory");
+				if (emit)
+					asm volatile("st.shared.u8 [%0], %1;" :: "r"(outBase + ((outPos + q) & (kRing-1))*kStep), "r"(o[q]) : "memory");
 			}
 		}
 	};
@@ -709,20 +710,20 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 	{
 		const unsigned te = min(tb + kM, total);
 		advance(min(te, len));
-		block(tb, BoolTag<false>());
+		block(tb, min(te, len), BoolTag<false>());
 		retire(te);
 	}
 	for (; tb + kM <= len; tb += kM)
 	{
 		advance(tb + kM);
-		block(tb, BoolTag<true>());
+		block(tb, tb + kM, BoolTag<true>());
 		retire(tb + kM);
 	}
 	for (; tb < total; tb += kM)
 	{
 		const unsigned te = min(tb + kM, total);
 		advance(min(te, len));
-		block(tb, BoolTag<false>());
+		block(tb, min(te, len), BoolTag<false>());
 		retire(te);
 	}
 
