@@ -352,7 +352,7 @@ struct JpegDecoder
 	// --- block decoders ---------------------------------------------------------------------------------------
 	void BaselineBlock(Component &c, int16_t *blk)
 	{
-		const int t = DecodeSymbol(dc[c.dcTable]);
+		const int t = DecodeSymbol(dc[c.dcTable]) & 15; // categories 0..11 (a corrupt table cannot ask for more bits than the reader holds)
 		c.dcPred += Extend(br.Bits(t), t);
 		blk[0] = int16_t(c.dcPred);
 		for (int k = 1; k < 64; )
@@ -372,7 +372,7 @@ struct JpegDecoder
 
 	void DcFirst(Component &c, int16_t *blk, int al)
 	{
-		const int t = DecodeSymbol(dc[c.dcTable]);
+		const int t = DecodeSymbol(dc[c.dcTable]) & 15; // categories 0..11 (a corrupt table cannot ask for more bits than the reader holds)
 		c.dcPred += Extend(br.Bits(t), t);
 		blk[0] = int16_t(c.dcPred*(1 << al));
 	}
@@ -635,24 +635,24 @@ struct JpegDecoder
 				height = int(Be16(seg + 1)); width = int(Be16(seg + 3));
 				const int n = seg[5];
 				if (0 == width || 0 == height || (1 != n && 3 != n) || length < size_t(8 + 3*n)) return Fail(path, "unsupported JPEG frame (grey or 3 components expected)");
+				if (width > 16384 || height > 16384) return Fail(path, "JPEG larger than 16384 pixels a side");
 				comps.resize(size_t(n));
 				for (int i = 0; i < n; ++i)
 				{
 					Component &c = comps[size_t(i)];
 					c.id = seg[6 + i*3]; c.h = seg[7 + i*3] >> 4; c.v = seg[7 + i*3] & 15; c.tq = seg[8 + i*3] & 3;
 					if (c.h < 1 || c.h > 2 || c.v < 1 || c.v > 2) return Fail(path, "unsupported JPEG sampling factors");
+					if (1 == n) c.h = c.v = 1; // a single component is never interleaved: its sampling factors mean nothing (T.81 A.2.2)
 					hMax = c.h > hMax ? c.h : hMax; vMax = c.v > vMax ? c.v : vMax;
 				}
 				mcusX = (width + 8*hMax - 1)/(8*hMax); mcusY = (height + 8*vMax - 1)/(8*vMax);
 				for (Component &c : comps)
 				{
-					if (1 == n) { c.h = c.v = 1; }
 					c.blocksW = mcusX*c.h; c.blocksH = mcusY*c.v;
 					const int cw = (width*c.h + hMax - 1)/hMax, ch = (height*c.v + vMax - 1)/vMax;
 					c.widthInBlocks = (cw + 7)/8; c.heightInBlocks = (ch + 7)/8;
 					c.coef.assign(size_t(c.blocksW)*c.blocksH*64, 0);
 				}
-				if (1 == n) { hMax = vMax = 1; mcusX = (width + 7)/8; mcusY = (height + 7)/8; comps[0].blocksW = mcusX; comps[0].blocksH = mcusY; comps[0].coef.assign(size_t(mcusX)*mcusY*64, 0); }
 				haveFrame = true;
 				break;
 			}

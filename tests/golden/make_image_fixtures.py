@@ -139,6 +139,16 @@ def main():
 
     sixteen = {"grey16.png": g16, "rgb16.png": (_hash(h * w * 3, 17) >> np.uint32(7)).astype(np.uint16).reshape(h, w, 3),
                "rgba16_adam7.png": (_hash(h * w * 4, 18) >> np.uint32(7)).astype(np.uint16).reshape(h, w, 4)}
+    # a grey file whose only component declares 2x2 sampling factors (some encoders write that; T.81 A.2.2: a single
+    # component is never interleaved, so the factors mean nothing and the image is the same)
+    data = bytearray(open(os.path.join(HERE, "grey.jpg"), "rb").read())
+    sof = data.index(b"\xff\xc0")
+    assert data[sof + 9] == 1 and data[sof + 11] == 0x11
+    data[sof + 11] = 0x22
+    with open(os.path.join(HERE, "grey_h2v2.jpg"), "wb") as f:
+        f.write(bytes(data))
+    files["grey_h2v2.jpg"] = None
+
     arrays = {}
     for name in sorted(files):
         bgra, gray = strip16(sixteen[name]) if name in sixteen else expected(os.path.join(HERE, name))

