@@ -503,7 +503,7 @@ struct JpegDecoder
 			}
 
 		// continue the marker walk behind the entropy-coded data
-		const uint8_t *q = br.hitMarker ? br.p : br.p;
+		const uint8_t *q = br.p;
 		while (q + 1 < br.end && !(0xff == q[0] && 0 != q[1] && !(q[1] >= 0xd0 && q[1] <= 0xd7) && 0xff != q[1])) ++q;
 		pos = size_t(q - file.data());
 		return true;
