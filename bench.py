@@ -358,6 +358,21 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = world * PIXELS_PER_STEP * e2e_steps / e2e_s / 1e6
 
+    # the same synchronous calls with the banded read-back switched off (one copy after the frame is finished)
+    host.set_readback_bands(0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_plain_s = time.perf_counter() - t0
+    host.set_readback_bands(-1)
+    if dist is not None:
+        t = torch.tensor([e2e_plain_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_plain_s = float(t.item())
+    e2e_unbanded = world * PIXELS_PER_STEP * e2e_steps / e2e_plain_s / 1e6
+
     # same calls with the host layer's two-deep frame pipeline (CkdHost_SetPipelined): frame i's copy overlaps frame i+1's render
     h_frame2 = ctx.malloc_host(frame_bytes)
     host.set_pipelined(True)
@@ -480,6 +495,8 @@ def run_ours(args):
                        "l2": f"no explicit flush: one step streams ~{working_set_mb:.0f} MB (frames, render targets, polar maps, textures) through the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                     "api": "X_Draw(uint32_t *pDest, float time, float delta) of include/ckd_host.h, pinned host pDest, synchronous (drop-in semantics)",
+                    "readback": "automatic (CkdHost_SetReadbackBands(-1)): the raymarched frames without a post chain render in 4 row bands and every finished band is copied while the next one renders; the other frames are copied whole",
+                    "unbanded_value": e2e_unbanded,
                     "pipelined_value": e2e_pipelined,
                     "pipelined_note": "same calls with CkdHost_SetPipelined(true): two device frame buffers, copy stream; pDest valid after CkdHost_Flush()"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "per_effect": per_effect,

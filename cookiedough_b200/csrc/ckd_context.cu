@@ -338,6 +338,8 @@ extern "C" void ckd_destroy(ckd_ctx *ctx)
 		if (ctx->evRendered[i]) cudaEventDestroy(ctx->evRendered[i]);
 		if (ctx->evCopied[i]) cudaEventDestroy(ctx->evCopied[i]);
 	}
+	for (auto &ev : ctx->evBand)
+		if (ev) cudaEventDestroy(ev);
 	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 	if (ctx->evStart) cudaEventDestroy(ctx->evStart);
 	if (ctx->evStop) cudaEventDestroy(ctx->evStop);
@@ -440,19 +442,64 @@ extern "C" uint32_t *ckd_frame_slot(ckd_ctx *ctx, int slot)
 	return slot ? ctx->d_scratch[1] : ctx->d_frame; // the second blur scratch image is only used by ckd_new_blur
 }
 
+int ckd_ensure_copy_stream(ckd_ctx *ctx)
+{
+	if (ctx->copyStream)
+		return CKD_OK;
+	CKD_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; ++i)
+	{
+		CKD_CUDA(cudaEventCreateWithFlags(&ctx->evRendered[i], cudaEventDisableTiming));
+		CKD_CUDA(cudaEventCreateWithFlags(&ctx->evCopied[i], cudaEventDisableTiming));
+	}
+	for (auto &ev : ctx->evBand)
+		CKD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	return CKD_OK;
+}
+
+// ---- banded read-back ------------------------------------------------------------------------------------------------
+// A synchronous X_Draw at 4K spends three quarters of its time copying the finished frame over PCIe (33 MB, 0.6 ms) after
+// 0.15-0.25 ms of rendering.  Armed with the caller's page-locked frame buffer, the next draw whose last stages are a
+// raymarch kernel + Fx_Blit_2x2 issues them per band of FX-map rows and sends every finished band of output rows to the host
+// on the copy stream while the next band renders (csrc/ckd_raymarch.cu, RaymarchAndBlit).  Draws that end differently
+// ignore the arm; ckd_finish_readback tells the caller which of the two happened.
+extern "C" int ckd_arm_readback(ckd_ctx *ctx, void *h_dest, int bands)
+{
+	CKD_REQUIRE(ctx && h_dest, "null argument");
+	ctx->rbHost = nullptr;
+	ctx->rbIssued = false;
+	if (bands < 2)
+		return CKD_OK;
+	cudaPointerAttributes attr;
+	if (cudaSuccess != cudaPointerGetAttributes(&attr, h_dest) || attr.type != cudaMemoryTypeHost)
+	{
+		cudaGetLastError(); // pageable memory: an asynchronous copy would be staged and serialise the bands -- leave it to the caller
+		return CKD_OK;
+	}
+	CKD_TRY(ckd_ensure_copy_stream(ctx));
+	ctx->rbHost = h_dest;
+	ctx->rbBands = bands < ckd_ctx::kMaxBands ? bands : ckd_ctx::kMaxBands;
+	return CKD_OK;
+}
+
+extern "C" int ckd_finish_readback(ckd_ctx *ctx, int *out_done)
+{
+	CKD_REQUIRE(ctx && out_done, "null argument");
+	*out_done = 0;
+	ctx->rbHost = nullptr;
+	if (!ctx->rbIssued)
+		return CKD_OK;
+	ctx->rbIssued = false;
+	CKD_CUDA(cudaStreamSynchronize(ctx->copyStream));
+	*out_done = 1;
+	return CKD_OK;
+}
+
 extern "C" int ckd_download_overlapped(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, int slot)
 {
 	CKD_REQUIRE(ctx && h_dst && d_src, "null argument");
 	CKD_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
-	if (!ctx->copyStream)
-	{
-		CKD_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
-		for (int i = 0; i < 2; ++i)
-		{
-			CKD_CUDA(cudaEventCreateWithFlags(&ctx->evRendered[i], cudaEventDisableTiming));
-			CKD_CUDA(cudaEventCreateWithFlags(&ctx->evCopied[i], cudaEventDisableTiming));
-		}
-	}
+	CKD_TRY(ckd_ensure_copy_stream(ctx));
 	CKD_CUDA(cudaEventRecord(ctx->evRendered[slot], ctx->stream));
 	CKD_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evRendered[slot], 0));
 	CKD_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->copyStream));

@@ -29,6 +29,14 @@ struct ckd_ctx {
 	cudaStream_t copyStream = nullptr;             // read-back overlapped with rendering (ckd_download_overlapped)
 	cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
 	bool copyPending[2] = { false, false };
+
+	// banded read-back (ckd_arm_readback): the next effect draw whose last stages are raymarch + Fx_Blit_2x2 renders and
+	// copies its frame in row bands
+	static constexpr int kMaxBands = 8;
+	void *rbHost = nullptr;                         // armed destination (page-locked host memory), cleared by the draw that uses it
+	int rbBands = 0;
+	bool rbIssued = false;                          // band copies are on the copy stream
+	cudaEvent_t evBand[kMaxBands] = {};
 	bool newBlurAttrSet = false;                   // opt-in shared-memory size set for new_blur_line_kernel on this device
 	bool blurAttrSet[64] = {};                     // opt-in shared-memory size set for the staged blur variants on this device
 	unsigned long long launches = 0;
@@ -71,7 +79,9 @@ struct ckd_ctx {
 void ckd_prof_begin(ckd_ctx *ctx, const char *name, double algoBytes);
 void ckd_prof_end(ckd_ctx *ctx);
 
-int ckd_ensure_polar_maps_2x2(ckd_ctx *ctx); // builds and uploads the FX-map sized polar maps once
+int ckd_ensure_polar_maps_2x2(ckd_ctx *ctx);
+int ckd_ensure_copy_stream(ckd_ctx *ctx);         // copy stream + its events, created on first use
+int ckd_fx_blit_2x2_rows(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int y0, int y1); // FX rows [y0, y1) -> output rows [2*y0, 2*y1) // builds and uploads the FX-map sized polar maps once
 
 void ckd_set_error(const std::string &message);
 int ckd_cuda_fail(cudaError_t err, const char *what, const char *file, int line);

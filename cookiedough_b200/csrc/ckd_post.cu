@@ -18,11 +18,11 @@ using namespace ckd;
 // Each thread takes 2 horizontally adjacent FX-map pixels (plus their right/down neighbours from the guard band)
 // and writes 4 output pixels on each of 2 output rows with one 128-bit store per row.
 
-__global__ void __launch_bounds__(256) fx_blit_2x2_kernel(uint32_t *__restrict__ pDest, const uint32_t *__restrict__ pSrc, int fxX, int resX, int halfX, int halfY)
+__global__ void __launch_bounds__(256) fx_blit_2x2_kernel(uint32_t *__restrict__ pDest, const uint32_t *__restrict__ pSrc, int fxX, int resX, int halfX, int y0, int y1)
 {
 	const int pairX = blockIdx.x*blockDim.x + threadIdx.x; // index of the source pixel pair
-	const int iY = blockIdx.y*blockDim.y + threadIdx.y;
-	if (pairX*2 >= halfX || iY >= halfY)
+	const int iY = y0 + blockIdx.y*blockDim.y + threadIdx.y; // FX-map rows [y0, y1)
+	if (pairX*2 >= halfX || iY >= y1)
 		return;
 
 	const int sx = pairX*2;
@@ -44,17 +44,26 @@ __global__ void __launch_bounds__(256) fx_blit_2x2_kernel(uint32_t *__restrict__
 	*reinterpret_cast<uint4 *>(top + resX) = make_uint4(avgV0_0, center0, avgV0_1, center1);
 }
 
-extern "C" int ckd_fx_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src)
+int ckd_fx_blit_2x2_rows(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int y0, int y1)
 {
 	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
 	CKD_REQUIRE(0 == (reinterpret_cast<uintptr_t>(d_dest) & 15) && 0 == (reinterpret_cast<uintptr_t>(d_src) & 15), "buffers must be 16-byte aligned (fx-blitter.cpp:29-30)");
 	const int halfX = ctx->fxX - 4, halfY = ctx->fxY - 4;
+	CKD_REQUIRE(0 <= y0 && y0 <= y1 && y1 <= halfY, "row range outside the FX map");
+	if (y0 == y1)
+		return CKD_OK;
 	const dim3 block(64, 4);
-	const dim3 grid(ckd_div_up(halfX/2, block.x), ckd_div_up(halfY, block.y));
-	ckd_prof_begin(ctx, "fx_blit_2x2", 5.0*ctx->resX*ctx->resY);
-	fx_blit_2x2_kernel<<<grid, block, 0, ctx->stream>>>(d_dest, d_src, ctx->fxX, ctx->resX, halfX, halfY);
+	const dim3 grid(ckd_div_up(halfX/2, block.x), ckd_div_up(y1 - y0, block.y));
+	ckd_prof_begin(ctx, "fx_blit_2x2", 5.0*ctx->resX*2.0*(y1 - y0));
+	fx_blit_2x2_kernel<<<grid, block, 0, ctx->stream>>>(d_dest, d_src, ctx->fxX, ctx->resX, halfX, y0, y1);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
+}
+
+extern "C" int ckd_fx_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src)
+{
+	CKD_REQUIRE(ctx, "null argument");
+	return ckd_fx_blit_2x2_rows(ctx, d_dest, d_src, 0, ctx->fxY - 4);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

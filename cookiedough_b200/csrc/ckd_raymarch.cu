@@ -520,14 +520,14 @@ struct LauraEffect
 // to the end.  Two counters alternate between launches: launch k consumes counter[k&1] and zeroes the other one.
 constexpr int kWarpTileX = 8, kWarpTileY = 4;
 
-struct TileQueue { unsigned *counter; unsigned *nextCounter; int tilesX; unsigned numTiles; };
+struct TileQueue { unsigned *counter; unsigned *nextCounter; int tilesX; unsigned firstTile, numTiles; }; // tiles [firstTile, numTiles)
 
 __device__ __forceinline__ bool next_tile(const TileQueue &q, unsigned &iX, unsigned &iY)
 {
 	const unsigned lane = threadIdx.x;
 	unsigned tile = 0;
 	if (lane == 0)
-		tile = atomicAdd(q.counter, 1u);
+		tile = q.firstTile + atomicAdd(q.counter, 1u);
 	tile = __shfl_sync(0xffffffffu, tile, 0);
 	if (tile >= q.numTiles)
 		return false;
@@ -664,11 +664,14 @@ Rot MakeRot(const ckd_ctx *ctx, float angle)
 	return { ckdh::lutcosf(ctx->h_cosLUT, angle), ckdh::lutsinf(ctx->h_cosLUT, angle) };
 }
 
-TileQueue MakeQueue(ckd_ctx *ctx, const FrameGeom &geom)
+// the queue of tile rows [row0, row1) (row1 < 0: all of them)
+TileQueue MakeQueue(ckd_ctx *ctx, const FrameGeom &geom, int row0 = 0, int row1 = -1)
 {
 	TileQueue q;
 	q.tilesX = ckd_div_up(geom.fxX, kWarpTileX);
-	q.numTiles = unsigned(q.tilesX)*ckd_div_up(geom.fxY, kWarpTileY);
+	const unsigned tileRows = ckd_div_up(geom.fxY, kWarpTileY);
+	q.firstTile = unsigned(q.tilesX)*unsigned(row0);
+	q.numTiles = unsigned(q.tilesX)*(row1 < 0 ? tileRows : unsigned(row1));
 	q.counter = ctx->d_tileCounters + (ctx->tileLaunches & 1);
 	q.nextCounter = ctx->d_tileCounters + ((ctx->tileLaunches + 1) & 1);
 	ctx->tileLaunches++;
@@ -691,19 +694,59 @@ struct LutRangeProof
 	bool holds() const { return worst < 20000.0; }                    // 22 % below 25735.9; the bounds themselves are generous and float rounding is 1e-7
 };
 
-template <class Effect> int LaunchRaymarch(ckd_ctx *ctx, const Effect &effect, uint32_t *d_fxmap, const char *name, const LutRangeProof *proof = nullptr)
+template <class Effect> int LaunchRaymarch(ckd_ctx *ctx, const Effect &effect, uint32_t *d_fxmap, const char *name, const LutRangeProof *proof = nullptr,
+	int tileRow0 = 0, int tileRow1 = -1)
 {
 	static const bool forceExact = nullptr != getenv("CKD_EXACT_LUT"); // tests: run every frame through the exact kernel
 	const FrameGeom geom = MakeGeom(ctx);
 	const RsqrtTab rsqrt = { ctx->d_rsqrtTab, ctx->rsqrtLog2Bin };
-	const TileQueue queue = MakeQueue(ctx, geom);
-	const int blocks = int(std::min<unsigned>(ckd_div_up(queue.numTiles, kTileY), unsigned(ctx->numSMs)*8));
-	ckd_prof_begin(ctx, name, 4.0*geom.fxX*geom.fxY);
+	const TileQueue queue = MakeQueue(ctx, geom, tileRow0, tileRow1);
+	const unsigned tiles = queue.numTiles - queue.firstTile;
+	const int blocks = int(std::max(1u, std::min<unsigned>(ckd_div_up(tiles, kTileY), unsigned(ctx->numSMs)*8)));
+	ckd_prof_begin(ctx, name, 4.0*kWarpTileX*kWarpTileY*tiles);
 	if (nullptr != proof && proof->holds() && !forceExact)
 		raymarch_kernel<Effect, true><<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(effect, d_fxmap, geom, ctx->d_cosLUT2, rsqrt, queue);
 	else
 		raymarch_kernel<Effect, false><<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(effect, d_fxmap, geom, ctx->d_cosLUT2, rsqrt, queue);
 	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
+}
+
+// raymarch into the FX map, then Fx_Blit_2x2 into d_dest: the tail of every effect without a post chain.  With a read-back
+// armed (ckd_arm_readback) both run per band of tile rows and every finished band of output rows leaves for the host on the
+// copy stream while the next band renders.  Output rows 2y, 2y+1 need FX rows y and y+1, so a band's blit stops one FX row
+// short of what has been rendered; the last band takes the rest.
+template <class Effect> int RaymarchAndBlit(ckd_ctx *ctx, const Effect &effect, const char *name, const LutRangeProof *proof, uint32_t *d_dest)
+{
+	uint32_t *d_fxmap = ctx->d_fxMap[0];
+	void *h_dest = ctx->rbHost;
+	ctx->rbHost = nullptr;
+	if (nullptr == h_dest)
+	{
+		CKD_TRY(LaunchRaymarch(ctx, effect, d_fxmap, name, proof));
+		return ckd_fx_blit_2x2(ctx, d_dest, d_fxmap);
+	}
+
+	const int bands = ctx->rbBands, halfY = ctx->fxY - 4;
+	const int tileRows = int(ckd_div_up(ctx->fxY, kWarpTileY));
+	int blitted = 0;
+	for (int k = 0; k < bands; ++k)
+	{
+		const int row0 = tileRows*k/bands, row1 = tileRows*(k + 1)/bands;
+		if (row1 > row0)
+			CKD_TRY(LaunchRaymarch(ctx, effect, d_fxmap, name, proof, row0, row1));
+		const int y1 = (k == bands-1) ? halfY : std::max(blitted, std::min(row1*kWarpTileY - 1, halfY));
+		if (y1 > blitted)
+		{
+			CKD_TRY(ckd_fx_blit_2x2_rows(ctx, d_dest, d_fxmap, blitted, y1));
+			const size_t offset = size_t(blitted)*2*ctx->resX, count = size_t(y1 - blitted)*2*ctx->resX;
+			CKD_CUDA(cudaEventRecord(ctx->evBand[k], ctx->stream));
+			CKD_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evBand[k], 0));
+			CKD_CUDA(cudaMemcpyAsync(static_cast<uint32_t *>(h_dest) + offset, d_dest + offset, count*sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copyStream));
+			blitted = y1;
+		}
+	}
+	ctx->rbIssued = true;
 	return CKD_OK;
 }
 
@@ -748,8 +791,7 @@ extern "C" int ckd_plasma_draw(ckd_ctx *ctx, const ckd_plasma_params *p, float t
 		proof.add(hx + hy + 1.6);
 		proof.add((5.0*fabs(double(time)) + hz)*0.53);
 	}
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_plasma", &proof));
-	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+	return RaymarchAndBlit(ctx, fx, "raymarch_plasma", &proof, d_dest);
 }
 
 // Nautilus_Draw, shadertoy.cpp:395-407
@@ -781,12 +823,13 @@ extern "C" int ckd_nautilus_draw(ckd_ctx *ctx, const ckd_nautilus_params *p, flo
 		proof.add(0.33*p*p + fabs(double(fx.f.gz))*p);
 		proof.add(2.8*p + fabs(double(fx.f.time)));
 	}
+	const float blur = ckdh::BoxBlurScale(p->blur);
+	if (0.f == blur)
+		return RaymarchAndBlit(ctx, fx, "raymarch_nautilus", &proof, d_dest);
+	ctx->rbHost = nullptr; // the blur works on the whole frame: no banded read-back
 	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_nautilus", &proof));
 	CKD_TRY(ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]));
-	const float blur = ckdh::BoxBlurScale(p->blur);
-	if (0.f != blur)
-		CKD_TRY(ckd_old_blur(ctx, d_dest, d_dest, unsigned(ctx->resX), unsigned(ctx->resY), blur));
-	return CKD_OK;
+	return ckd_old_blur(ctx, d_dest, d_dest, unsigned(ctx->resX), unsigned(ctx->resY), blur);
 }
 
 // Spikey_Draw, shadertoy.cpp:661-733
@@ -817,10 +860,10 @@ extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float t
 		f.zTerm = 1.f + zOffsFinal;
 		f.normalGrain = p->close_normal_grain;
 		SpikeyCloseEffect fx = { f };
-		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_close"));
-
 		const float mbOpacity = ckdh::saturatef(p->mix_blur_opacity);
-		if (mbOpacity > 0.f)
+		if (!(mbOpacity > 0.f))
+			return RaymarchAndBlit(ctx, fx, "raymarch_spikey_close", nullptr, d_dest);
+		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_close"));
 		{
 			// shadertoy.cpp:672-707
 			const float mbMap = ckdh::clampf(0, 1.f, p->mix_blur_map);
@@ -861,8 +904,7 @@ extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float t
 		f.yOffs = p->dist_y;
 		f.zTerm = -2.614f + p->dist_z;
 		SpikeyDistantEffect fx = { f };
-		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_distant"));
-		return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+		return RaymarchAndBlit(ctx, fx, "raymarch_spikey_distant", nullptr, d_dest);
 	}
 
 	// RenderSpikeyMap_2x2_Distant_SpecularOnly(…, 1.f+warmup), shadertoy.cpp:600-608, 727-729
@@ -948,8 +990,7 @@ extern "C" int ckd_sinuses_draw(ckd_ctx *ctx, const ckd_sinuses_params *p, float
 	LutRangeProof proof;
 	for (int i = 0; i < 3; ++i)
 		proof.add(1.0175*(fabs(double(fx.f.origin[i])) + 36.0*1.001 + 0.2 + 4.76) + 1.6);
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_sinuses", &proof));
-	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+	return RaymarchAndBlit(ctx, fx, "raymarch_sinuses", &proof, d_dest);
 }
 
 // Laura_Draw, shadertoy.cpp:1105-1109
@@ -969,6 +1010,5 @@ extern "C" int ckd_laura_draw(ckd_ctx *ctx, const ckd_laura_params *p, float tim
 	// normal taps at +0.1628; the angles are the coordinates themselves (shadertoy.cpp:998-1015)
 	LutRangeProof proof;
 	proof.add(fabs(double(fx.f.originZ)) + 64.1*1.001 + 0.17);
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_laura", &proof));
-	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
+	return RaymarchAndBlit(ctx, fx, "raymarch_laura", &proof, d_dest);
 }

@@ -349,10 +349,27 @@ void CkdHost_SetPipelined(bool enabled)
 }
 
 static uint32_t *s_composeTarget = nullptr;     // non-null while Demo_Draw composes a frame on the device
+static int s_readbackBands = -1;                // -1: automatic (4 bands for frames of 8 MB and more), 0/1: off, n: n bands
+
+void CkdHost_SetReadbackBands(int bands) { s_readbackBands = bands; }
+
+// A synchronous X_Draw into a page-locked pDest: let the effect stream its frame to the host in row bands while it is still
+// rendering (ckd_arm_readback; the raymarchers without a post chain do, the others ignore it).
+static void ArmReadback(uint32_t *pDest)
+{
+	if (nullptr == s_ctx || nullptr == pDest || nullptr != s_composeTarget || s_pipelined)
+		return;
+	const size_t bytes = size_t(ckd_res_x(s_ctx))*ckd_res_y(s_ctx)*sizeof(uint32_t);
+	static const int autoBands = getenv("CKD_READBACK_BANDS") ? atoi(getenv("CKD_READBACK_BANDS")) : 4;
+	const int bands = (s_readbackBands >= 0) ? s_readbackBands : (bytes >= (size_t(8) << 20) ? autoBands : 0);
+	if (bands >= 2)
+		Check(ckd_arm_readback(s_ctx, pDest, bands), "X_Draw");
+}
 
 // device buffer the next X_Draw renders into: the single frame twin, or the free slot of the two-deep pipeline
-static uint32_t *Target()
+static uint32_t *Target(uint32_t *pDestToStreamTo = nullptr)
 {
+	ArmReadback(pDestToStreamTo);
 	if (nullptr != s_composeTarget)
 		return s_composeTarget;
 	if (!s_pipelined)
@@ -363,10 +380,14 @@ static uint32_t *Target()
 
 static void Finish(int rc, uint32_t *pDest, const char *what)
 {
+	int streamed = 0;
+	const bool finished = (nullptr == s_ctx) || Check(ckd_finish_readback(s_ctx, &streamed), what); // always: it also disarms
 	if (!Check(rc, what) || nullptr != s_composeTarget)
 		return;
 	if (nullptr == pDest)
 		return; // extension: a null pDest leaves the finished frame on the device (ckd_frame / ckd_frame_slot)
+	if (finished && streamed)
+		return; // the frame arrived in row bands while it was being rendered
 	const size_t bytes = size_t(ckd_res_x(s_ctx))*ckd_res_y(s_ctx)*sizeof(uint32_t);
 	if (s_pipelined)
 	{
@@ -522,7 +543,7 @@ void Plasma_Draw(uint32_t *pDest, float time, float delta)
 	p.hue = Rocket::getf(trackPlasmaHue);
 	p.gamma = Rocket::getf(trackPlasmaGamma);
 	p.desaturation = Rocket::getf(trackPlasmaDesat);
-	Finish(ckd_plasma_draw(s_ctx, &p, time, Target()), pDest, "Plasma_Draw");
+	Finish(ckd_plasma_draw(s_ctx, &p, time, Target(pDest)), pDest, "Plasma_Draw");
 }
 
 // shadertoy.cpp:395-407
@@ -535,7 +556,7 @@ void Nautilus_Draw(uint32_t *pDest, float time, float delta)
 	p.speed = Rocket::getf(trackNautilusSpeed);
 	p.desaturation = Rocket::getf(trackNautilusDesaturation);
 	p.blur = Rocket::getf(trackNautilusBlur);
-	Finish(ckd_nautilus_draw(s_ctx, &p, time, Target()), pDest, "Nautilus_Draw");
+	Finish(ckd_nautilus_draw(s_ctx, &p, time, Target(pDest)), pDest, "Nautilus_Draw");
 }
 
 // shadertoy.cpp:661-733
@@ -565,7 +586,7 @@ void Spikey_Draw(uint32_t *pDest, float time, float delta, bool close /* = true 
 	p.mix_blur = Rocket::getf(trackCloseMixBlur);
 	p.mix_map_blur = Rocket::getf(trackCloseMixMapBlur);
 	p.mix_blur_opacity = Rocket::getf(trackCloseMixBlurOpacity);
-	Finish(ckd_spikey_draw(s_ctx, &p, time, close ? 1 : 0, Target()), pDest, "Spikey_Draw");
+	Finish(ckd_spikey_draw(s_ctx, &p, time, close ? 1 : 0, Target(pDest)), pDest, "Spikey_Draw");
 }
 
 // shadertoy.cpp:840-861
@@ -602,7 +623,7 @@ void Sinuses_Draw(uint32_t *pDest, float time, float delta)
 	p.gamma = Rocket::getf(trackSinusesGamma);
 	p.hue = Rocket::getf(trackSinusesHue);
 	p.desaturation = Rocket::getf(trackSinusesDesat);
-	Finish(ckd_sinuses_draw(s_ctx, &p, time, Target()), pDest, "Sinuses_Draw");
+	Finish(ckd_sinuses_draw(s_ctx, &p, time, Target(pDest)), pDest, "Sinuses_Draw");
 }
 
 // shadertoy.cpp:1105-1109
@@ -616,7 +637,7 @@ void Laura_Draw(uint32_t *pDest, float time, float delta)
 	p.roll = Rocket::getf(trackLauraRoll);
 	p.hue = Rocket::getf(trackLauraHue);
 	p.saturate = Rocket::getf(trackLauraSaturate);
-	Finish(ckd_laura_draw(s_ctx, &p, time, Target()), pDest, "Laura_Draw");
+	Finish(ckd_laura_draw(s_ctx, &p, time, Target(pDest)), pDest, "Laura_Draw");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1188,6 +1209,7 @@ void ckdhost_demo_destroy()
 	CkdHost_Destroy();
 }
 
+void ckdhost_set_readback_bands(int bands) { CkdHost_SetReadbackBands(bands); }
 int ckdhost_pin_frame_buffer(uint32_t *pDest) { return CkdHost_PinFrameBuffer(pDest) ? 0 : -1; }
 void ckdhost_unpin_frame_buffer(uint32_t *pDest) { CkdHost_UnpinFrameBuffer(pDest); }
 

@@ -40,6 +40,7 @@ def _lib():
     L.ckdhost_effect_create.argtypes = [C.c_int]
     L.ckdhost_set_asset_root.argtypes = [C.c_char_p]
     L.ckdhost_module.argtypes = [C.c_int, C.c_int]
+    L.ckdhost_set_readback_bands.argtypes = [C.c_int]
     L.ckdhost_global.argtypes = [C.c_int]
     L.ckdhost_global.restype = C.c_void_p
     L.ckdhost_demo_create.argtypes = []
@@ -181,6 +182,10 @@ class Host:
 
     def unpin(self, out):
         self.L.ckdhost_unpin_frame_buffer(C.c_void_p(out.ctypes.data))
+
+    def set_readback_bands(self, bands):
+        """CkdHost_SetReadbackBands: -1 automatic, 0 off, n >= 2 row bands for the streamed read-back of a synchronous X_Draw"""
+        self.L.ckdhost_set_readback_bands(int(bands))
 
     def set_pipelined(self, enabled):
         """frame pipelining (CkdHost_SetPipelined): X_Draw returns once enqueued; call flush() before reading the buffers"""

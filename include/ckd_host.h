@@ -55,6 +55,11 @@ void CkdHost_UnpinFrameBuffer(uint32_t *pDest);
 // as soon as the frame is enqueued: pDest is complete after the *second* following X_Draw call or after CkdHost_Flush().
 // The device->host copy of frame i then overlaps the rendering of frame i+1 (two device frame buffers, copy stream).
 void CkdHost_SetPipelined(bool enabled);
+
+// Synchronous X_Draw into a page-locked pDest (CkdHost_PinFrameBuffer): the raymarched effects without a post chain render
+// their frame in row bands and copy every finished band while the next one renders, so most of the rendering hides under
+// the PCIe copy.  bands: -1 automatic (4 bands for frames of 8 MB and more; the default), 0 off, n >= 2 that many bands.
+void CkdHost_SetReadbackBands(int bands);
 void CkdHost_Flush();
 
 // Extension to every X_Draw / Demo_Draw below: pDest == nullptr renders the frame and leaves it on the device

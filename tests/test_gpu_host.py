@@ -180,6 +180,32 @@ def test_effect_created_from_image_files(host_and_ref, tmp_path):
     host.reload_from_files("landscape", paths[:1], tmp_path)
 
 
+@pytest.mark.parametrize("effect,row", [("plasma", 2600), ("sinuses", 7800), ("laura", 8900), ("spikey_distant", 3600), ("spikey_close", 6800),
+                                        ("nautilus", 5700), ("tunnel", 4500), ("ball", 1500)])
+def test_banded_readback_delivers_the_same_frame(host_and_ref, effect, row):
+    """CkdHost_SetReadbackBands: a synchronous X_Draw into a page-locked buffer renders and copies in row bands (raymarchers
+    without a post chain) or falls back to one copy (everything else): the frame in pDest is the same, bit for bit"""
+    host, R = host_and_ref
+    host.set_row(row)
+    plain = np.zeros((R.res_y, R.res_x), dtype=np.uint32)
+    host.set_readback_bands(0)
+    host.draw(effect, plain)
+    banded = np.zeros((R.res_y, R.res_x), dtype=np.uint32)
+    host.pin(banded)
+    try:
+        for bands in (4, 3, 8, 2):
+            banded[:] = 0x55aa55aa
+            host.set_readback_bands(bands)
+            host.draw(effect, banded)
+            assert np.array_equal(banded, plain), f"{effect}@{row}: {bands} bands differ in {np.count_nonzero(banded != plain)} pixels"
+        pageable = np.full((R.res_y, R.res_x), 0x55aa55aa, dtype=np.uint32)   # not page-locked: the arm is ignored, one copy
+        host.draw(effect, pageable)
+        assert np.array_equal(pageable, plain)
+    finally:
+        host.set_readback_bands(-1)
+        host.unpin(banded)
+
+
 def test_pinning_the_callers_frame_buffer(host_and_ref):
     """CkdHost_PinFrameBuffer: same frame, faster copy-back into a caller-owned (malloc'ed) buffer"""
     import time
