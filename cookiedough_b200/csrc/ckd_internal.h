@@ -81,6 +81,7 @@ void ckd_prof_end(ckd_ctx *ctx);
 
 int ckd_ensure_polar_maps_2x2(ckd_ctx *ctx);
 int ckd_ensure_copy_stream(ckd_ctx *ctx);         // copy stream + its events, created on first use
+int ckd_polar_tail(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse, bool alpha, const uint32_t *d_softLightSrc); // Polar_Blit[A] (+ halo) as a frame's last stage: banded when a read-back is armed
 int ckd_fx_blit_2x2_rows(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int y0, int y1); // FX rows [y0, y1) -> output rows [2*y0, 2*y1) // builds and uploads the FX-map sized polar maps once
 
 void ckd_set_error(const std::string &message);

@@ -569,6 +569,45 @@ static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, in
 	return CKD_OK;
 }
 
+// Polar_Blit / Polar_BlitA (+ the ball's SoftLight32A halo) as the LAST stage of a frame.  With a banded read-back armed
+// (ckd_arm_readback) the remap is issued per band of destination rows and every finished band leaves for the host on the
+// copy stream while the next one is remapped; the source is the complete render target, so bands are independent.
+int ckd_polar_tail(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse, bool alpha, const uint32_t *d_softLightSrc)
+{
+	void *h_dest = ctx->rbHost;
+	ctx->rbHost = nullptr;
+	const unsigned numPixels = unsigned(ctx->resX)*unsigned(ctx->resY);
+	if (nullptr == h_dest || 0 != (ctx->resX & 3))
+	{
+		CKD_TRY(LaunchPolar(ctx, d_dest, d_src, inverse, alpha));
+		return d_softLightSrc ? ckd_blend(ctx, CKD_SOFTLIGHT32A, d_dest, d_softLightSrc, numPixels, 0.f, 0) : CKD_OK;
+	}
+	CKD_REQUIRE(d_dest != d_src, "polar blit cannot run in place");
+	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap : ctx->d_polarMap);
+	const int bands = ctx->rbBands;
+	for (int k = 0; k < bands; ++k)
+	{
+		const int y0 = ctx->resY*k/bands, y1 = ctx->resY*(k + 1)/bands;
+		if (y1 <= y0)
+			continue;
+		const size_t offset = size_t(y0)*ctx->resX, count = size_t(y1 - y0)*ctx->resX;
+		const unsigned numQuads = unsigned(count/4);
+		ckd_prof_begin(ctx, alpha ? "polar_blit_a" : "polar_blit", (alpha ? 20.0 : 16.0)*double(count));
+		if (alpha)
+			polar_blit_kernel<true><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX));
+		else
+			polar_blit_kernel<false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX));
+		CKD_CHECK_LAUNCH(ctx);
+		if (d_softLightSrc)
+			CKD_TRY(ckd_blend(ctx, CKD_SOFTLIGHT32A, d_dest + offset, d_softLightSrc + offset, unsigned(count), 0.f, 0));
+		CKD_CUDA(cudaEventRecord(ctx->evBand[k], ctx->stream));
+		CKD_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evBand[k], 0));
+		CKD_CUDA(cudaMemcpyAsync(static_cast<uint32_t *>(h_dest) + offset, d_dest + offset, count*sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copyStream));
+	}
+	ctx->rbIssued = true;
+	return CKD_OK;
+}
+
 extern "C" int ckd_polar_blit(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse) { return LaunchPolar(ctx, d_dest, d_src, inverse, false); }
 extern "C" int ckd_polar_blit_a(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse) { return LaunchPolar(ctx, d_dest, d_src, inverse, true); }
 

@@ -759,9 +759,10 @@ extern "C" int ckd_tunnelscape_draw(ckd_ctx *ctx, const ckd_tunnelscape_params *
 		static_cast<const uint32_t *>(ctx->images[CKD_IMG_TSCAPE_FOG].d_pixels), f);
 	CKD_CHECK_LAUNCH(ctx);
 
+	if (0.f == p->blur)
+		return ckd_polar_tail(ctx, d_dest, ctx->d_renderTarget[0], 1, false, nullptr);
+	ctx->rbHost = nullptr; // the blur works on the whole frame: no banded read-back
 	CKD_TRY(ckd_polar_blit(ctx, d_dest, ctx->d_renderTarget[0], 1));
-
-	if (0.f != p->blur)
 	{
 		const float scaledBlur = ckdh::BoxBlurScale(p->blur);
 		CKD_TRY(ckd_old_blur(ctx, d_dest, d_dest, unsigned(ctx->resX), unsigned(ctx->resY), scaledBlur));
@@ -886,11 +887,7 @@ extern "C" int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time,
 
 	const void *pBackground = ctx->images[hasBeams ? CKD_IMG_BALL_BACKGROUND0 : CKD_IMG_BALL_BACKGROUND1].d_pixels;
 	CKD_CUDA(cudaMemcpyAsync(d_dest, pBackground, size_t(ctx->resX)*ctx->resY*4, cudaMemcpyDeviceToDevice, ctx->stream));
-	CKD_TRY(ckd_polar_blit_a(ctx, d_dest, ctx->d_renderTarget[0], 0));
-
-	if (hasBeams)
-		CKD_TRY(ckd_blend(ctx, CKD_SOFTLIGHT32A, d_dest, static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_HALO].d_pixels), unsigned(ctx->resX)*unsigned(ctx->resY), 0.f, 0));
-	return CKD_OK;
+	return ckd_polar_tail(ctx, d_dest, ctx->d_renderTarget[0], 0, true, hasBeams ? static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_HALO].d_pixels) : nullptr);
 }
 
 // Twister_Draw, torus-twister.cpp:166-188
@@ -944,5 +941,5 @@ extern "C" int ckd_twister_draw(ckd_ctx *ctx, const ckd_twister_params *p, float
 		CKD_TRY(ckd_old_blur_h(ctx, ctx->d_renderTarget[0], ctx->d_renderTarget[0], unsigned(ctx->resX), unsigned(ctx->resY), ckdh::BoxBlurScale(blur)));
 
 	CKD_CUDA(cudaMemcpyAsync(d_dest, ctx->images[CKD_IMG_TWISTER_BACKGROUND].d_pixels, size_t(ctx->resX)*ctx->resY*4, cudaMemcpyDeviceToDevice, ctx->stream));
-	return ckd_polar_blit_a(ctx, d_dest, ctx->d_renderTarget[0], 0);
+	return ckd_polar_tail(ctx, d_dest, ctx->d_renderTarget[0], 0, true, nullptr);
 }

@@ -354,7 +354,8 @@ static int s_readbackBands = -1;                // -1: automatic (4 bands for fr
 void CkdHost_SetReadbackBands(int bands) { s_readbackBands = bands; }
 
 // A synchronous X_Draw into a page-locked pDest: let the effect stream its frame to the host in row bands while it is still
-// rendering (ckd_arm_readback; the raymarchers without a post chain do, the others ignore it).
+// rendering (ckd_arm_readback; the raymarchers without a post chain and the casters that end in a polar remap do, the
+// others ignore it).
 static void ArmReadback(uint32_t *pDest)
 {
 	if (nullptr == s_ctx || nullptr == pDest || nullptr != s_composeTarget || s_pipelined)
@@ -706,7 +707,7 @@ void Tunnelscape_Draw(uint32_t *pDest, float time, float delta)
 	p.step_v = Rocket::getf(trackStarsStepV);
 	p.speed = Rocket::getf(trackStarsSpeed);
 	p.blur = Rocket::getf(trackStarsBlur);
-	Finish(ckd_tunnelscape_draw(s_ctx, &p, time, Target()), pDest, "Tunnelscape_Draw");
+	Finish(ckd_tunnelscape_draw(s_ctx, &p, time, Target(pDest)), pDest, "Tunnelscape_Draw");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -786,7 +787,7 @@ void Ball_Draw(uint32_t *pDest, float time, float delta)
 	p.beams2 = Rocket::getf(trackBallBeams2);
 	p.beams3 = Rocket::getf(trackBallBeams3);
 	p.low_beams = Rocket::geti(trackBallLowBeams);
-	Finish(ckd_ball_draw(s_ctx, &p, time, Target()), pDest, "Ball_Draw");
+	Finish(ckd_ball_draw(s_ctx, &p, time, Target(pDest)), pDest, "Ball_Draw");
 }
 
 bool Ball_HasBeams() { return Rocket::geti(trackBallHasBeams) != 0; } // ball.cpp:521-524
@@ -820,7 +821,7 @@ void Twister_Draw(uint32_t *pDest, float time, float delta)
 	p.speed = Rocket::getf(trackTwisterSpeed);
 	p.shear_speed = Rocket::getf(trackTwisterShearSpeed);
 	p.blur = Rocket::getf(trackTwisterBlur);
-	Finish(ckd_twister_draw(s_ctx, &p, time, Target()), pDest, "Twister_Draw");
+	Finish(ckd_twister_draw(s_ctx, &p, time, Target(pDest)), pDest, "Twister_Draw");
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -68,8 +68,9 @@ int ckd_download(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes); /*
 int ckd_copy(ckd_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);       /* device to device, async on the stream (the compositor's memcpy, demo.cpp:407-449) */
 
 /* banded read-back for synchronous callers: arms the NEXT effect draw with the caller's page-locked frame buffer.  A draw that
- * ends in raymarch + Fx_Blit_2x2 (Plasma, Sinuses, Laura, Spikey without its mix-blur chain, Nautilus without blur) then
- * renders in `bands` row bands and copies each finished band to h_dest while the next one renders; every other draw, and
+ * ends in raymarch + Fx_Blit_2x2 (Plasma, Sinuses, Laura, Spikey without its mix-blur chain, Nautilus without blur) or in a
+ * polar remap (Tunnelscape without blur, Ball, Twister) then issues those stages in `bands` row bands and copies each finished
+ * band to h_dest while the next one renders; every other draw, and
  * pageable h_dest, leave the arm unused.  ckd_finish_readback waits for the band copies and sets *out_done to 1 when the
  * frame is in h_dest, to 0 when the caller still has to copy it (ckd_download). */
 int ckd_arm_readback(ckd_ctx *ctx, void *h_dest, int bands);

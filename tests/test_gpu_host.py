@@ -181,7 +181,7 @@ def test_effect_created_from_image_files(host_and_ref, tmp_path):
 
 
 @pytest.mark.parametrize("effect,row", [("plasma", 2600), ("sinuses", 7800), ("laura", 8900), ("spikey_distant", 3600), ("spikey_close", 6800),
-                                        ("nautilus", 5700), ("tunnel", 4500), ("ball", 1500)])
+                                        ("nautilus", 5700), ("tunnel", 4500), ("ball", 1500), ("ball", 2060), ("twister", 2008), ("tunnelscape", 4300), ("landscape", 500)])
 def test_banded_readback_delivers_the_same_frame(host_and_ref, effect, row):
     """CkdHost_SetReadbackBands: a synchronous X_Draw into a page-locked buffer renders and copies in row bands (raymarchers
     without a post chain) or falls back to one copy (everything else): the frame in pDest is the same, bit for bit"""
