@@ -1,0 +1,80 @@
+"""examples/headless_demo.cpp: the reference's main loop written against include/ckd_host.h with the reference's own names only.
+CPU: it compiles and links against the library (the drop-in claim at the source level).  GPU: run next to a target/ directory
+with real image FILES and the Rocket project, its frames equal the reference's Demo_Draw."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import MAX_LSB, MIN_EXACT_PCT, pixel_stats
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_example(out_dir):
+    from cookiedough_b200 import capi
+    exe = os.path.join(str(out_dir), "headless_demo")
+    lib_dir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), os.path.join(REPO, "examples", "headless_demo.cpp"),
+                           "-L", lib_dir, "-lckd_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe])
+    return exe
+
+
+def test_example_compiles_and_fails_loudly_without_a_gpu(tmp_path):
+    exe = build_example(tmp_path)
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if not have_gpu:
+        r = subprocess.run([exe, "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=str(tmp_path))
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_example_renders_the_reference_frames_from_files(tmp_path):
+    from PIL import Image
+    from oracle import ref as oref
+    if not oref.available(720):
+        pytest.skip("oracle/_ref not built")
+    from cookiedough_b200 import sink
+    from cookiedough_b200.assets import Assets
+    assets = Assets(1280, 720)
+    R = oref.Reference.get(720, assets, demo=True)
+
+    # a target/ directory like the reference's: every image the demo loads as a FILE (PNG streams: lossless, so both sides
+    # see the same pixels; the decoder goes by content, so .jpg names work too) + the Rocket project
+    target = tmp_path / "target"
+    for path in assets.paths(demo=True):
+        arr = assets[path]
+        out = target / path
+        out.parent.mkdir(parents=True, exist_ok=True)
+        if arr.dtype == np.uint8:
+            img = Image.fromarray(arr, "L")
+        else:
+            bgra = arr.view(np.uint8).reshape(arr.shape[0], arr.shape[1], 4)
+            img = Image.fromarray(np.ascontiguousarray(bgra[..., [2, 1, 0, 3]]), "RGBA")
+        with open(out, "wb") as f:
+            img.save(f, "PNG", compress_level=1)
+    shutil.copyfile(os.path.join(oref.DATA_DIR, "directors-cut.rocket"), target / "directors-cut.rocket")
+
+    exe = build_example(tmp_path)
+    stream = tmp_path / "out.ckdf"
+    start, fps, frames = 50.0, 0.0625, 10       # t = 50, 66, ..., 194 s (exact in binary): ten frames across the parts of the timeline
+    r = subprocess.run([exe, str(frames / fps), str(fps), str(stream), str(start)], cwd=str(target), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert sink.read_header(str(stream))[:2] == (1280, 720)
+
+    failures = []
+    for i in range(frames):
+        t = start + i / fps
+        R.set_time(float(np.float32(t)))
+        ref = R.demo_draw().copy()
+        got = sink.read_frame(str(stream), i)
+        exact, max_delta = pixel_stats(got, ref)  # the compositor's tolerance (tests/test_gpu_demo.py): the float effect underneath
+        if exact < MIN_EXACT_PCT or max_delta > MAX_LSB:
+            failures.append(f"t={t}: {exact:.4f}% exact, max delta {max_delta} LSB")
+    assert not failures, "\n".join(failures)
