@@ -85,7 +85,7 @@ static bool DecodeIntoRegistry(const char *path, int bpp)
 {
 	HostImage img;
 	img.bpp = bpp;
-	if (!ckdhost::DecodeImageFile(path, bpp, img.pixels, img.width, img.height))
+	if (nullptr == s_ctx || !ckdhost::DecodeImageForResolution(path, bpp, ckd_res_x(s_ctx), ckd_res_y(s_ctx), img.pixels, img.width, img.height))
 		return false;
 	s_images[path] = std::move(img);
 	return true;

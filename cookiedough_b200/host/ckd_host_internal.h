@@ -18,6 +18,9 @@ namespace ckdhost
 
 	// host/ckd_image.cpp: decode `path` (PNG or JPEG, relative to the asset root) to BGRA (bpp 4) or L8 (bpp 1)
 	bool DecodeImageFile(const char *path, int bpp, std::vector<uint8_t> &pixels, int &width, int &height);
+	// ... and brought to the output resolution by the rules of SURVEY 8 f3 (output-sized art, FX-map sized maps, the ribbon
+	// strip; the missing tunnelscape colour map synthesised from the landscape's)
+	bool DecodeImageForResolution(const char *path, int bpp, int resX, int resY, std::vector<uint8_t> &pixels, int &width, int &height);
 
 	// While composing, X_Draw(pDest, ...) renders into d_frame and leaves it on the device (pDest is ignored):
 	// the compositor downloads the finished frame once.

@@ -882,7 +882,74 @@ namespace ckdhost
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// resolution rules ("deterministic 4K resampling rules"; the Python twin is cookiedough_b200/assets.py)
+// ---------------------------------------------------------------------------------------------------------------
+// The reference's art is made for 1280x720.  For any other output resolution: art of exactly the native output size is
+// nearest-resampled to the output size, the two 644x364 blur maps (native FX-map size) to the FX-map size, the 2160x720
+// ribbon strip scales with resY/720 (the part-12 strided read stays inside it); textures, sprites and the
+// 1280x568 credit logos keep their size.  Nearest means source index = (i*srcSize)/dstSize.  The tunnelscape colour map
+// is listed in the reference's .MISSING_LARGE_BLOBS: when the file is absent it is the landscape colour map at twice the
+// size, at every resolution (the stand-in both sides of the parity harness use).
+
+namespace {
+
+void NearestResize(std::vector<uint8_t> &pixels, int &width, int &height, int bpp, int newW, int newH)
+{
+	if (newW == width && newH == height)
+		return;
+	std::vector<uint8_t> out(size_t(newW)*newH*bpp);
+	for (int y = 0; y < newH; ++y)
+	{
+		const uint8_t *srcRow = &pixels[size_t((int64_t(y)*height)/newH)*width*bpp];
+		uint8_t *dstRow = &out[size_t(y)*newW*bpp];
+		for (int x = 0; x < newW; ++x)
+			memcpy(dstRow + size_t(x)*bpp, srcRow + size_t((int64_t(x)*width)/newW)*bpp, size_t(bpp));
+	}
+	pixels.swap(out);
+	width = newW; height = newH;
+}
+
+} // namespace
+
+namespace ckdhost
+{
+	bool DecodeImageForResolution(const char *path, int bpp, int resX, int resY, std::vector<uint8_t> &pixels, int &width, int &height)
+	{
+		static const char kMissingMap[] = "assets/scape/tscape-C7W-edit.png", kStandIn[] = "assets/scape/C17W-edit.png";
+		if (!DecodeImageFile(path, bpp, pixels, width, height))
+		{
+			if (0 != strcmp(path, kMissingMap) || !DecodeImageFile(kStandIn, bpp, pixels, width, height))
+				return false;
+			NearestResize(pixels, width, height, bpp, width*2, height*2);
+		}
+		constexpr int kNativeX = 1280, kNativeY = 720, kNativeFxX = kNativeX/2 + 4, kNativeFxY = kNativeY/2 + 4;
+		if (width == kNativeX && height == kNativeY)
+			NearestResize(pixels, width, height, bpp, resX, resY);
+		else if (width == kNativeFxX && height == kNativeFxY)
+			NearestResize(pixels, width, height, bpp, resX/2 + 4, resY/2 + 4);
+		else if (0 == strcmp(path, "assets/demo/ribbons.png"))
+			NearestResize(pixels, width, height, bpp, width*resY/kNativeY, height*resY/kNativeY);
+		return true;
+	}
+}
+
 extern "C" {
+
+// ctypes hook: decode a file for an output resolution (rules above) into a malloc'ed buffer (ckdhost_image_free)
+void *ckdhost_image_load_for_resolution(const char *path, int grayscale, int resX, int resY, int *width, int *height)
+{
+	std::vector<uint8_t> pixels;
+	int w = 0, h = 0;
+	if (!ckdhost::DecodeImageForResolution(path, grayscale ? 1 : 4, resX, resY, pixels, w, h))
+		return nullptr;
+	void *p = malloc(pixels.size() + 16);
+	if (nullptr == p) return nullptr;
+	memcpy(p, pixels.data(), pixels.size());
+	if (width) *width = w;
+	if (height) *height = h;
+	return p;
+}
 
 // ctypes hook: decode a file; returns a malloc'ed buffer the caller releases with ckdhost_image_free (or null)
 void *ckdhost_image_load(const char *path, int grayscale, int *width, int *height) { return Load(path, 0 != grayscale, width, height, true); }

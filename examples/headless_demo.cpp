@@ -19,7 +19,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-constexpr unsigned kResX = 1280, kResY = 720; // main.h:37-38
+// main.h:37-38 -- compile-time constants in the reference; here CKD_RES_X / CKD_RES_Y may override them (3840 x 2160 renders
+// the demo at 4K from the same 1280x720 art: the library resamples it by the rules of host/ckd_image.cpp)
+static unsigned kResX = 1280, kResY = 720;
 
 int main(int argc, char **argv)
 {
@@ -28,6 +30,7 @@ int main(int argc, char **argv)
 	const char *outPath = (argc > 3 && argv[3][0]) ? argv[3] : nullptr;
 	const double startSeconds = argc > 4 ? atof(argv[4]) : 0.0;
 	const char *rocket = getenv("CKD_ROCKET") ? getenv("CKD_ROCKET") : "directors-cut.rocket";
+	if (getenv("CKD_RES_X") && getenv("CKD_RES_Y")) { kResX = unsigned(atoi(getenv("CKD_RES_X"))); kResY = unsigned(atoi(getenv("CKD_RES_Y"))); }
 
 	if (!CkdHost_Create(kResX, kResY, 0))
 	{

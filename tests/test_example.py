@@ -78,3 +78,15 @@ def test_example_renders_the_reference_frames_from_files(tmp_path):
         if exact < MIN_EXACT_PCT or max_delta > MAX_LSB:
             failures.append(f"t={t}: {exact:.4f}% exact, max delta {max_delta} LSB")
     assert not failures, "\n".join(failures)
+
+    # the same directory of 1280x720 art rendered at 3840x2160: the host layer resamples what it decodes (the rules are pinned
+    # against the harness on the CPU, tests/test_image_decode.py; 4K compositor parity with those pixels: test_gpu_demo.py)
+    stream4k = tmp_path / "out4k.ckdf"
+    env = dict(os.environ, CKD_RES_X="3840", CKD_RES_Y="2160")
+    r = subprocess.run([exe, "32", "0.0625", str(stream4k), "66"], cwd=str(target), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert sink.read_header(str(stream4k)) == (3840, 2160, 2)
+    # (a 4K frame is not an upscale of the 720p one -- the casters get more columns / a wider view, SURVEY 8d -- so the check
+    #  here is only that a real picture arrived; what it must look like is the 4K reference build's business)
+    big = sink.read_frame(str(stream4k), 0)
+    assert len(np.unique(big)) > 1000 and len(np.unique(sink.read_frame(str(stream4k), 1))) > 1000

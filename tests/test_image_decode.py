@@ -116,3 +116,67 @@ def test_mutated_files_decode_or_fail_cleanly(lib, tmp_path):
                 else:
                     decoded += 1
     assert decoded > 50 and failed > 50
+
+
+def decode_for(L, path, gray, res_x, res_y):
+    L.ckdhost_image_load_for_resolution.restype = C.c_void_p
+    L.ckdhost_image_load_for_resolution.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    w, h = C.c_int(), C.c_int()
+    p = L.ckdhost_image_load_for_resolution(path.encode(), int(gray), res_x, res_y, C.byref(w), C.byref(h))
+    if not p:
+        return None
+    try:
+        buf = (C.c_uint8 * (w.value * h.value * (1 if gray else 4))).from_address(p)
+        return np.frombuffer(buf, dtype=np.uint8 if gray else np.uint32).reshape(h.value, w.value).copy()
+    finally:
+        L.ckdhost_image_free(p)
+
+
+def test_resolution_rules_on_files(lib, tmp_path):
+    """the 4K rules of the host layer against their Python twin (cookiedough_b200/assets.py): output-sized art,
+    FX-map sized maps and the ribbon strip are nearest-resampled, everything else keeps its size, and the tunnelscape colour
+    map the reference's checkout lacks is the landscape's at twice the size"""
+    from PIL import Image
+    from cookiedough_b200.assets import _nearest_resize
+
+    def write(path, arr):
+        out = tmp_path / path
+        out.parent.mkdir(parents=True, exist_ok=True)
+        bgra = arr.view(np.uint8).reshape(arr.shape[0], arr.shape[1], 4)
+        Image.fromarray(np.ascontiguousarray(bgra[..., [2, 1, 0, 3]]), "RGBA").save(out, "PNG", compress_level=1)
+
+    rng = np.random.default_rng(5)
+    files = {"assets/x/layer.png": (720, 1280), "assets/x/blurmap.png": (364, 644), "assets/demo/ribbons.png": (720, 2160),
+             "assets/x/credits.png": (568, 1280), "assets/x/sprite.png": (128, 128), "assets/scape/C17W-edit.png": (64, 64)}
+    arrays = {p: rng.integers(0, 2**32, size=hw, dtype=np.uint64).astype(np.uint32) for p, hw in files.items()}
+    for p, a in arrays.items():
+        write(p, a)
+    lib.ckdhost_set_asset_root(str(tmp_path).encode())
+    for res_x, res_y in ((1280, 720), (1920, 1080), (3840, 2160), (2560, 1080)):
+        fx_x, fx_y = res_x // 2 + 4, res_y // 2 + 4
+        want = {"assets/x/layer.png": _nearest_resize(arrays["assets/x/layer.png"], res_y, res_x),
+                "assets/x/blurmap.png": _nearest_resize(arrays["assets/x/blurmap.png"], fx_y, fx_x),
+                "assets/demo/ribbons.png": _nearest_resize(arrays["assets/demo/ribbons.png"], 720 * res_y // 720, 2160 * res_y // 720),
+                "assets/x/credits.png": arrays["assets/x/credits.png"], "assets/x/sprite.png": arrays["assets/x/sprite.png"],
+                "assets/scape/tscape-C7W-edit.png": _nearest_resize(arrays["assets/scape/C17W-edit.png"], 128, 128)}
+        for p, ref in want.items():
+            got = decode_for(lib, p, False, res_x, res_y)
+            assert got is not None, lib.ckdhost_last_error().decode()
+            assert got.shape == ref.shape and np.array_equal(got, ref), f"{p} at {res_x}x{res_y}"
+    assert decode_for(lib, "assets/x/absent.png", False, 3840, 2160) is None
+
+
+def test_every_reference_asset_at_4k_matches_the_harness(lib):
+    target = os.path.join(os.environ.get("CKD_REFERENCE", "/root/reference"), "target")
+    npz_path = os.path.join(REPO, "refdata", "assets.npz")
+    if not os.path.isdir(os.path.join(target, "assets")) or not os.path.exists(npz_path):
+        pytest.skip("reference tree not present on this machine")
+    from cookiedough_b200.assets import SPEC, Assets
+    lib.ckdhost_set_asset_root(target.encode())
+    assets = Assets(3840, 2160)
+    for path, spec in SPEC.items():
+        got = decode_for(lib, path, bool(spec[2]), 3840, 2160)
+        assert got is not None, lib.ckdhost_last_error().decode()
+        want = assets[path]
+        assert got.shape == want.shape and np.array_equal(got, want), path
+        assets.drop(path)
