@@ -47,6 +47,8 @@ SUITE = [
 ]
 PIXELS_PER_STEP = len(SUITE) * RES_X * RES_Y
 
+# (The counts were taken on the exact-lookup kernels, i.e. they are the reference's own operations -- lutcosf with its two
+#  conversions included; the conversion-free lookup executes one FP instruction more per call, which is NOT credited.)
 # FP operations per FX-map pixel at the pinned rows (SURVEY.md 8d asks for the measured mean, not the <= bound): MEASURED on
 # the B200 as executed thread-level FP instructions of one 4K launch of each kernel (tools/count_fp_ops.py ->
 # profiles/r01_fp_ops.json).  The kernels execute the reference's float operations one for one (no FMA contraction), so this
@@ -495,7 +497,7 @@ def run_ours(args):
                        "l2": f"no explicit flush: one step streams ~{working_set_mb:.0f} MB (frames, render targets, polar maps, textures) through the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                     "api": "X_Draw(uint32_t *pDest, float time, float delta) of include/ckd_host.h, pinned host pDest, synchronous (drop-in semantics)",
-                    "readback": "automatic (CkdHost_SetReadbackBands(-1)): the raymarched frames without a post chain render in 4 row bands and every finished band is copied while the next one renders; the other frames are copied whole",
+                    "readback": "automatic (CkdHost_SetReadbackBands(-1)): frames that end in raymarch + Fx_Blit_2x2 or in a polar remap without a whole-frame post chain render those stages in 4 row bands and every finished band is copied while the next one renders; the other frames are copied whole",
                     "unbanded_value": e2e_unbanded,
                     "pipelined_value": e2e_pipelined,
                     "pipelined_note": "same calls with CkdHost_SetPipelined(true): two device frame buffers, copy stream; pDest valid after CkdHost_Flush()"},
