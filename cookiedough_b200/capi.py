@@ -172,6 +172,18 @@ def load():
         "ckd_ball_draw": ([VP, C.POINTER(BallParams), F, VP], _I),
         "ckd_twister_draw": ([VP, C.POINTER(TwisterParams), F, VP], _I),
         "ckd_launch_count": ([VP], C.c_ulonglong),
+        "ckd_set_fast_cos_table": ([VP, VP], _I), "ckd_get_fast_cos_table": ([VP, VP], _I),
+        "ckd_fastcos": ([VP, VP, VP, SZ, _I], _I),
+        "ckd_set_frame_independent": ([VP, _I], _I),
+        "ckd_gather_create": ([VP, _I, C.POINTER(VP)], _I), "ckd_gather_export": ([VP, VP], _I),
+        "ckd_gather_open": ([VP, VP, C.POINTER(VP)], _I), "ckd_gather_destroy": ([VP], None),
+        "ckd_gather_set_timeout_ms": ([VP, U], _I),
+        "ckd_gather_acquire": ([VP, C.POINTER(VP)], _I), "ckd_gather_push": ([VP, VP, C.c_ulonglong], _I),
+        "ckd_gather_pop": ([VP, C.c_ulonglong, _I, VP], _I), "ckd_gather_wait_pop": ([VP, C.c_ulonglong], _I),
+        "ckd_gather_flush": ([VP], _I), "ckd_gather_status": ([VP], _I),
+        "ckd_gather_checksums": ([VP, C.c_ulonglong, U, C.POINTER(C.c_ulonglong)], _I),
+        "ckd_gather_peer_bytes": ([VP], C.c_ulonglong), "ckd_gather_slots": ([VP], _I),
+        "ckd_frame_checksum": ([VP, VP, C.POINTER(C.c_ulonglong)], _I),
         "ckd_profile_begin": ([VP], _I),
         "ckd_profile_end": ([VP, C.POINTER(KernelStat), _I, C.POINTER(_I)], _I),
     }
@@ -372,6 +384,32 @@ class Context:
         return {stats[i].name.decode(): {"launches": int(stats[i].launches), "total_ms": float(stats[i].total_ms), "algo_bytes": float(stats[i].algo_bytes)}
                 for i in range(count.value)}
 
+    # -- helpers / frame gather -----------------------------------------------------------------
+    def fastcos(self, x, sine=False):
+        """fastcosf / fastsinf (fast-cosine.h:17-53) of a float64 array, evaluated on the device"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        d_x = self.to_device(x, pad_elems=0)
+        d_out = self.malloc(max(4, x.size * 4))
+        self._check(self.L.ckd_fastcos(self.h, C.c_void_p(d_out), C.c_void_p(d_x), x.size, int(bool(sine))))
+        out = self.download(d_out, x.shape, dtype=np.float32)
+        self.free(d_x)
+        self.free(d_out)
+        return out
+
+    def fast_cos_table(self):
+        tab = np.zeros(1025, dtype=np.float64)
+        self._check(self.L.ckd_get_fast_cos_table(self.h, tab.ctypes.data))
+        return tab
+
+    def set_frame_independent(self, enabled):
+        self._check(self.L.ckd_set_frame_independent(self.h, int(bool(enabled))))
+
+    def frame_checksum(self, d_ptr=None):
+        """sum_i pixel[i]*(2i+1) mod 2^64 of a device frame (the checksum the gather's collector computes)"""
+        out = C.c_ulonglong()
+        self._check(self.L.ckd_frame_checksum(self.h, C.c_void_p(d_ptr or self.frame()), C.byref(out)))
+        return int(out.value)
+
     def malloc_host(self, nbytes):
         p = C.c_void_p()
         self._check(self.L.ckd_malloc_host(C.byref(p), nbytes))
@@ -387,3 +425,71 @@ class Context:
         ms = C.c_float()
         self._check(self.L.ckd_timer_stop_ms(self.h, C.byref(ms)))
         return ms.value
+
+
+GATHER_CHECKSUM, GATHER_TO_HOST = 1, 2
+GATHER_HANDLE_BYTES = 128
+
+
+def frame_checksum_host(frame):
+    """the gather's frame checksum computed on the host: sum_i pixel[i]*(2i+1) mod 2^64"""
+    px = np.ascontiguousarray(frame).reshape(-1).astype(np.uint64)
+    w = np.arange(px.size, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    with np.errstate(over="ignore"):
+        return int((px * w).sum(dtype=np.uint64))
+
+
+class Gather:
+    """ckd_gather: the slot ring in the collector's HBM that the producers fill with peer copies (include/ckd.h).
+    Gather(ctx, slots=8) creates it (collector); Gather(ctx, handle=bytes) maps it from another process (producer)."""
+
+    def __init__(self, ctx, slots=8, handle=None):
+        self.L, self.ctx = ctx.L, ctx
+        g = C.c_void_p()
+        if handle is None:
+            ctx._check(self.L.ckd_gather_create(ctx.h, slots, C.byref(g)))
+        else:
+            buf = C.create_string_buffer(bytes(handle), GATHER_HANDLE_BYTES)
+            ctx._check(self.L.ckd_gather_open(ctx.h, buf, C.byref(g)))
+        self.g = g
+
+    def export(self):
+        buf = C.create_string_buffer(GATHER_HANDLE_BYTES)
+        self.ctx._check(self.L.ckd_gather_export(self.g, buf))
+        return bytes(buf.raw)
+
+    def set_timeout_ms(self, ms):
+        self.ctx._check(self.L.ckd_gather_set_timeout_ms(self.g, int(ms)))
+
+    def acquire(self):
+        p = C.c_void_p()
+        self.ctx._check(self.L.ckd_gather_acquire(self.g, C.byref(p)))
+        return p.value
+
+    def push(self, seq, d_frame=None):
+        self.ctx._check(self.L.ckd_gather_push(self.g, C.c_void_p(d_frame), seq))
+
+    def pop(self, seq, mode=0, h_dest=None):
+        self.ctx._check(self.L.ckd_gather_pop(self.g, seq, mode, C.c_void_p(h_dest)))
+
+    def wait_pop(self, seq):
+        self.ctx._check(self.L.ckd_gather_wait_pop(self.g, seq))
+
+    def flush(self):
+        self.ctx._check(self.L.ckd_gather_flush(self.g))
+
+    def status(self):
+        self.ctx._check(self.L.ckd_gather_status(self.g))
+
+    def checksums(self, first_seq, count):
+        out = (C.c_ulonglong * count)()
+        self.ctx._check(self.L.ckd_gather_checksums(self.g, first_seq, count, out))
+        return [int(v) for v in out]
+
+    def peer_bytes(self):
+        return int(self.L.ckd_gather_peer_bytes(self.g))
+
+    def close(self):
+        if self.g:
+            self.L.ckd_gather_destroy(self.g)
+            self.g = None

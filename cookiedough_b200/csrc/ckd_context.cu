@@ -90,6 +90,13 @@ static void ProbeHostRsqrt(std::vector<uint32_t> &table, int &log2Bin)
 		table[i] = full[i << log2Bin];
 }
 
+// InitializeFastCosine, fast-cosine.cpp:11-17 (host cos, double)
+static void BuildFastCosTable(double *table)
+{
+	for (unsigned iPhase = 0; iPhase < 1024+1; ++iPhase)
+		table[iPhase] = cos(double(iPhase)*(ckdh::k2PI/1024));
+}
+
 // CalculateMaps, polar.cpp:18-59 (host sqrtf/atan2f, like the reference)
 static void BuildPolarMaps(int32_t *pDest, int32_t *pInvDest, unsigned srcResX, unsigned srcResY, unsigned destResX, unsigned destResY)
 {
@@ -144,6 +151,28 @@ extern "C" int ckd_set_cos_lut(ckd_ctx *ctx, const float *lut2049)
 	for (int i = 0; i < kCkdCosTabSize; ++i)
 		pairs[i] = make_float2(lut2049[i], lut2049[i+1] - lut2049[i]); // b-a of lerpf (Math.h:52-56), same float subtraction
 	CKD_CUDA(cudaMemcpy(ctx->d_cosLUT2, pairs.data(), pairs.size()*sizeof(float2), cudaMemcpyHostToDevice));
+	return CKD_OK;
+}
+
+extern "C" int ckd_set_fast_cos_table(ckd_ctx *ctx, const double *table1025)
+{
+	CKD_REQUIRE(ctx && table1025, "null argument");
+	memcpy(ctx->h_fastCosTab, table1025, sizeof(ctx->h_fastCosTab));
+	CKD_CUDA(cudaMemcpy(ctx->d_fastCosTab, table1025, sizeof(ctx->h_fastCosTab), cudaMemcpyHostToDevice));
+	return CKD_OK;
+}
+
+extern "C" int ckd_get_fast_cos_table(ckd_ctx *ctx, double *out_table1025)
+{
+	CKD_REQUIRE(ctx && out_table1025, "null argument");
+	memcpy(out_table1025, ctx->h_fastCosTab, sizeof(ctx->h_fastCosTab));
+	return CKD_OK;
+}
+
+extern "C" int ckd_set_frame_independent(ckd_ctx *ctx, int enabled)
+{
+	CKD_REQUIRE(ctx, "null context");
+	ctx->frameIndependent = 0 != enabled;
 	return CKD_OK;
 }
 
@@ -267,6 +296,7 @@ extern "C" int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device)
 	const size_t offBallB = carve(ballMapPixels*4 + 4096);
 	const size_t offMap = carve(mapBytes), offInvMap = carve(mapBytes);
 	const size_t offCos = carve(kCkdCosTabSize*sizeof(float2));
+	const size_t offFastCos = carve(1025*sizeof(double));
 	const size_t offVox = carve(8192*sizeof(int));
 	const size_t offRay = carve(size_t(res_y)*8*sizeof(float) + 4096);
 	const size_t offCounters = carve(256);
@@ -287,6 +317,7 @@ extern "C" int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device)
 	ctx->d_polarMap = reinterpret_cast<int32_t *>(base + offMap);
 	ctx->d_polarInvMap = reinterpret_cast<int32_t *>(base + offInvMap);
 	ctx->d_cosLUT2 = reinterpret_cast<float2 *>(base + offCos);
+	ctx->d_fastCosTab = reinterpret_cast<double *>(base + offFastCos);
 	ctx->d_voxelTables = reinterpret_cast<int *>(base + offVox);
 	ctx->d_rayParams = reinterpret_cast<float *>(base + offRay);
 	ctx->d_tileCounters = reinterpret_cast<unsigned *>(base + offCounters);
@@ -300,6 +331,10 @@ extern "C" int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device)
 		float lut[kCkdCosTabSize+1];
 		BuildCosLUT(lut);
 		if (CKD_OK != (rc = ckd_set_cos_lut(ctx, lut))) break;
+
+		double fastCos[1025];
+		BuildFastCosTable(fastCos);
+		if (CKD_OK != (rc = ckd_set_fast_cos_table(ctx, fastCos))) break;
 
 		std::vector<uint32_t> rsqrtTab;
 		int log2Bin = 0;
@@ -331,6 +366,7 @@ extern "C" void ckd_destroy(ckd_ctx *ctx)
 		if (slot.d_pixels) cudaFree(slot.d_pixels);
 	if (ctx->d_rsqrtTab) cudaFree(ctx->d_rsqrtTab);
 	if (ctx->d_polarMap2x2) cudaFree(ctx->d_polarMap2x2);
+	if (ctx->d_checksumWork) cudaFree(ctx->d_checksumWork);
 	free(ctx->h_rsqrtTab);
 	for (auto &e : ctx->profEntries) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
 	for (int i = 0; i < 2; ++i)
@@ -624,4 +660,49 @@ extern "C" const void *ckd_get_image(ckd_ctx *ctx, ckd_image slot)
 {
 	if (!ctx || slot < 0 || slot >= CKD_IMG_COUNT) return nullptr;
 	return ctx->images[slot].d_pixels;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fastcosf / fastsinf -- fast-cosine.h:17-53
+// ---------------------------------------------------------------------------------------------------------------
+
+// The phase 1 + |x|/2pi is kept in double: its exponent says how far the mantissa has to be shifted so that the bits below the
+// binary point line up as a 32-bit fraction of a turn; the top 10 of those index the table, the other 22 interpolate.
+__device__ __forceinline__ float fastcos_eval(const double *table, double x)
+{
+	x = fabs(x);
+	const double phaseScale = double(1.f/ckdh::k2PI);        // a float constant in the reference (fast-cosine.h:23)
+	const double phase = 1.0 + x*phaseScale;
+	const unsigned long long phaseBits = (unsigned long long) __double_as_longlong(phase);
+	const int exponent = int(phaseBits >> 52) - 1023;
+	// x86 shifts by the low 6 bits of the count (huge and non-finite arguments: "quality degrades", but the bits are defined)
+	const unsigned significand = unsigned((phaseBits << (unsigned(exponent) & 63u)) >> (52-32));
+	const unsigned index = significand >> 22;
+	const double left = table[index], right = table[index+1];
+	const double t = double(significand & 0x3fffffu)*(1.0/4194304.0);
+	return float(left + (right-left)*t);
+}
+
+__global__ void __launch_bounds__(256) fastcos_kernel(float *__restrict__ pOut, const double *__restrict__ pIn, size_t n, const double *__restrict__ table, int sine)
+{
+	__shared__ double s_table[1025];
+	for (int i = threadIdx.x; i < 1025; i += blockDim.x)
+		s_table[i] = table[i];
+	__syncthreads();
+	const size_t stride = size_t(gridDim.x)*blockDim.x;
+	for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += stride)
+		pOut[i] = fastcos_eval(s_table, sine ? pIn[i] - 0.25 : pIn[i]); // fastsinf, fast-cosine.h:51-53
+}
+
+extern "C" int ckd_fastcos(ckd_ctx *ctx, float *d_out, const double *d_x, size_t n, int sine)
+{
+	CKD_REQUIRE(ctx && d_out && d_x, "null argument");
+	if (0 == n)
+		return CKD_OK;
+	CKD_CUDA(cudaSetDevice(ctx->device));
+	const unsigned blocks = unsigned(std::max<size_t>(1, std::min<size_t>(size_t(ctx->numSMs)*8, ckd_div_up(n, 256))));
+	ckd_prof_begin(ctx, "fastcos", 12.0*double(n));
+	fastcos_kernel<<<blocks, 256, 0, ctx->stream>>>(d_out, d_x, n, ctx->d_fastCosTab, sine);
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
 }

@@ -54,6 +54,8 @@ struct ckd_ctx {
 	// tables
 	float h_cosLUT[kCkdCosTabSize+1];
 	float2 *d_cosLUT2 = nullptr;      // [i] = (LUT[i], LUT[i+1]-LUT[i]) so one 8-byte load feeds the lerp
+	double h_fastCosTab[1025];        // g_fastCosTab (fast-cosine.cpp:9)
+	double *d_fastCosTab = nullptr;
 	uint32_t *d_rsqrtTab = nullptr;   // host RSQRTPS table
 	uint32_t *h_rsqrtTab = nullptr;
 	int rsqrtLog2Bin = 13;
@@ -64,6 +66,8 @@ struct ckd_ctx {
 	float *d_rayParams = nullptr;     // per-ray host-computed parameters (ball fan deltas, twister origins)
 	unsigned *d_tileCounters = nullptr; // two alternating work-queue counters of the raymarch kernels
 	unsigned long long tileLaunches = 0;
+	unsigned long long *d_checksumWork = nullptr; // ckd_frame_checksum scratch, allocated on first use
+	bool frameIndependent = false;    // ckd_set_frame_independent: no pixel of a frame may depend on an earlier frame
 
 	ckd_image_slot images[CKD_IMG_COUNT];
 

@@ -431,6 +431,7 @@ struct BallFrame
 	unsigned beamAtten;       // s_beamAtten
 	float beamAlphaMin;       // s_beamAlphaMin
 	unsigned lowLight;
+	int clearLastPixel;       // ckd_set_frame_independent: the pixel the beam path never writes starts from 0 instead of history
 };
 
 // tables: heightProj[1024], projNorm0[1024], projNorm1[1024], projNorm2[1024] (ball.cpp:61-62)
@@ -445,6 +446,13 @@ __global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest,
 	if (iRay >= unsigned(f.resY))
 		return;
 	uint32_t *line = pDest + size_t(iRay)*f.resX;
+	if (BEAMS && f.clearLastPixel)
+	{
+		// the extrusion stops one pixel short of the row (ball.cpp:186) and nothing clears the target (ball.cpp:352-363): that
+		// pixel is whatever an earlier frame left there unless a span reaches it
+		if (0 == lane) line[f.resX-1] = 0;
+		__syncwarp();
+	}
 
 	const int dX = rayDeltas[iRay*2], dY = rayDeltas[iRay*2+1];
 	const int *heightProj = tables, *projNorm0 = tables + 1024, *projNorm1 = tables + 2048, *projNorm2 = tables + 3072;
@@ -838,6 +846,7 @@ extern "C" int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time,
 	f.beamAtten = unsigned(ckdh::clampi(0, 255, p->beam_atten));
 	f.beamAlphaMin = ckdh::clampf(0.f, 255.f, p->beam_alpha_min);
 	f.lowLight = unsigned(ckdh::clampi(0, 255, p->low_beams));
+	f.clearLastPixel = ctx->frameIndependent ? 1 : 0;
 
 	const float timeScale = float(rayLength)*(0.25f/1024);
 	const float fMapDim = 1024.f, fMapHalf = fMapDim*0.5f;

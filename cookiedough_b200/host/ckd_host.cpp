@@ -13,6 +13,7 @@
 #include <string.h>
 #include <ctype.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -349,6 +350,9 @@ void CkdHost_SetPipelined(bool enabled)
 }
 
 static uint32_t *s_composeTarget = nullptr;     // non-null while Demo_Draw composes a frame on the device
+static uint32_t *s_deviceTarget = nullptr;      // CkdHost_SetDeviceTarget: where a draw with pDest == nullptr leaves its frame
+
+void CkdHost_SetDeviceTarget(uint32_t *d_frame) { s_deviceTarget = d_frame; }
 static int s_readbackBands = -1;                // -1: automatic (4 bands for frames of 8 MB and more), 0/1: off, n: n bands
 
 void CkdHost_SetReadbackBands(int bands) { s_readbackBands = bands; }
@@ -373,6 +377,8 @@ static uint32_t *Target(uint32_t *pDestToStreamTo = nullptr)
 	ArmReadback(pDestToStreamTo);
 	if (nullptr != s_composeTarget)
 		return s_composeTarget;
+	if (nullptr != s_deviceTarget && nullptr == pDestToStreamTo)
+		return s_deviceTarget;
 	if (!s_pipelined)
 		return ckd_frame(s_ctx);
 	Check(ckd_wait_download(s_ctx, s_slot), "X_Draw"); // the copy that last read this buffer must have finished
@@ -847,10 +853,13 @@ struct Staged
 		if (destPixels > cap || srcPixels > cap) { SetLastError("buffer larger than the output resolution"); return; }
 		d_dest = ckd_render_target(s_ctx, 2);
 		if (destIsInput && !Check(ckd_upload(s_ctx, d_dest, pDest, destBytes), "upload")) return;
-		if (pSrc == pDest || nullptr == pSrc)
+		if (nullptr == pSrc || (pSrc == pDest && destIsInput))
 			d_src = d_dest;
 		else
 		{
+			// also when pSrc == pDest for an op that does not read its destination (TapeWarp32, Polar_Blit, Fx_Blit_2x2 ...):
+			// those gather from anywhere in the source, so the source gets its own device copy and the call behaves like the
+			// out-of-place one instead of reading whatever render target 2 held
 			uint32_t *d = ckd_render_target(s_ctx, 3);
 			if (!Check(ckd_upload(s_ctx, d, pSrc, srcPixels*4), "upload")) return;
 			d_src = d;
@@ -1134,6 +1143,33 @@ void Shared_Destroy()
 	s_nytrikTPB.clear(); s_xboxLogoTPB.clear();
 }
 
+// fast-cosine.cpp:9-17: the table is the context's (built by ckd_create with the host's cos(), as InitializeFastCosine does)
+double g_fastCosTab[kFastCosTabSize+1];
+
+void InitializeFastCosine()
+{
+	if (nullptr == s_ctx) { SetLastError("CkdHost_Create() has not been called"); return; }
+	Check(ckd_get_fast_cos_table(s_ctx, g_fastCosTab), "InitializeFastCosine");
+}
+
+static bool FastCosArray(float *pDest, const double *pX, size_t numValues, int sine, const char *what)
+{
+	if (nullptr == s_ctx) { SetLastError("CkdHost_Create() has not been called"); return false; }
+	if (0 == numValues) return true;
+	void *d_x = nullptr, *d_out = nullptr;
+	bool ok = Check(ckd_malloc(s_ctx, &d_x, numValues*sizeof(double)), what) && Check(ckd_malloc(s_ctx, &d_out, numValues*sizeof(float)), what);
+	ok = ok && Check(ckd_upload(s_ctx, d_x, pX, numValues*sizeof(double)), what)
+		&& Check(ckd_fastcos(s_ctx, static_cast<float *>(d_out), static_cast<const double *>(d_x), numValues, sine), what)
+		&& Check(ckd_download(s_ctx, pDest, d_out, numValues*sizeof(float)), what)
+		&& Check(ckd_sync(s_ctx), what);
+	if (d_x) ckd_free(s_ctx, d_x);
+	if (d_out) ckd_free(s_ctx, d_out);
+	return ok;
+}
+
+bool fastcosf(float *pDest, const double *pX, size_t numValues) { return FastCosArray(pDest, pX, numValues, 0, "fastcosf"); }
+bool fastsinf(float *pDest, const double *pX, size_t numValues) { return FastCosArray(pDest, pX, numValues, 1, "fastsinf"); }
+
 void TapeWarp32(uint32_t *pDest, const uint32_t *pSrc, unsigned xRes, unsigned yRes, float strength, float speed)
 {
 	Staged s(pDest, size_t(xRes)*yRes, pSrc, size_t(xRes)*yRes, false);
@@ -1285,6 +1321,15 @@ int ckdhost_post(int op, uint32_t *pDest, const uint32_t *pSrc, unsigned a, unsi
 	}
 	return s_lastError.empty() ? 0 : -2;
 }
+
+int ckdhost_fastcos(float *pDest, const double *pX, size_t numValues, int sine)
+{
+	s_lastError.clear();
+	InitializeFastCosine();
+	return ((sine ? fastsinf(pDest, pX, numValues) : fastcosf(pDest, pX, numValues)) && s_lastError.empty()) ? 0 : -2;
+}
+
+const double *ckdhost_fast_cos_tab() { return g_fastCosTab; }
 
 // module set-up names: 0 Polar, 1 BoxBlur, 2 FxBlitter, 3 Shared; create != 0 calls X_Create, else X_Destroy
 int ckdhost_module(int module, int create)

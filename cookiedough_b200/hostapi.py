@@ -46,6 +46,10 @@ def _lib():
     L.ckdhost_demo_create.argtypes = []
     L.ckdhost_demo_draw.argtypes = [C.c_void_p, C.c_double, C.c_float]
     L.ckdhost_demo_destroy.argtypes = []
+    L.ckdhost_timeline_render.argtypes = [C.POINTER(C.c_double), C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_int,
+                                          C.POINTER(C.c_void_p), C.c_uint, C.c_ulonglong, C.c_float]
+    L.ckdhost_fastcos.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.ckdhost_fast_cos_tab.restype = C.POINTER(C.c_double)
     L._host_bound = True
     return L
 
@@ -156,6 +160,29 @@ class Host:
         if rc < 0:
             raise capi.CkdError(f"Demo_Draw: {self.L.ckdhost_last_error().decode()}")
         return rc == 1
+
+    def timeline_render(self, times, rank=0, world=1, gather=None, passes=1, pop_mode=0, host_ring=None, seq_base=0, delta=1.6667):
+        """CkdTimeline_Render: Demo_Draw for the frames i % world == rank of `times`, each published to `gather` (capi.Gather);
+        rank 0 also consumes every frame in order (pop_mode: capi.GATHER_CHECKSUM / GATHER_TO_HOST into host_ring, a list of
+        page-locked buffer addresses, or into the open sink when host_ring is None)"""
+        assert self.demo
+        arr = (C.c_double * len(times))(*times)
+        ring = (C.c_void_p * len(host_ring))(*host_ring) if host_ring else None
+        rc = self.L.ckdhost_timeline_render(arr, len(times), passes, rank, world, gather.g if gather is not None else None, pop_mode,
+                                            ring, len(host_ring) if host_ring else 0, seq_base, C.c_float(delta))
+        if rc != 0:
+            raise capi.CkdError(f"CkdTimeline_Render: {self.L.ckdhost_last_error().decode()}")
+
+    def fastcos(self, x, sine=False):
+        """InitializeFastCosine + fastcosf / fastsinf over an array (ckd_host.h)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(x.shape, dtype=np.float32)
+        if self.L.ckdhost_fastcos(out.ctypes.data, x.ctypes.data, x.size, int(bool(sine))) != 0:
+            raise capi.CkdError(f"fastcosf: {self.L.ckdhost_last_error().decode()}")
+        return out
+
+    def fast_cos_tab(self):
+        return np.ctypeslib.as_array(self.L.ckdhost_fast_cos_tab(), shape=(1025,)).copy()
 
     def post(self, op, dst, src, a=0, b=0, f0=0.0, f1=0.0, u=0):
         rc = self.L.ckdhost_post(POST_IDS[op], dst.ctypes.data, src.ctypes.data if src is not None else None, a, b, C.c_float(f0), C.c_float(f1), u)

@@ -30,7 +30,8 @@ typedef enum ckd_status {
 	CKD_ERR_CUDA = -1,          /* CUDA runtime/driver error (message in ckd_last_error) */
 	CKD_ERR_INVALID = -2,       /* bad argument */
 	CKD_ERR_MISSING_INPUT = -3, /* an image / table the effect needs has not been uploaded */
-	CKD_ERR_UNIMPLEMENTED = -4
+	CKD_ERR_UNIMPLEMENTED = -4,
+	CKD_ERR_TIMEOUT = -5        /* a device-side wait of the frame gather gave up (ckd_gather_status) */
 } ckd_status;
 
 /* ---- context (replaces the module globals allocated by Shared_Create / FxBlitter_Create / Polar_Create /
@@ -98,6 +99,22 @@ int ckd_set_rsqrt_table(ckd_ctx *ctx, const uint32_t *table, int log2_bin);
 int ckd_get_rsqrt_table(ckd_ctx *ctx, uint32_t *out_table, size_t max_entries, int *out_log2_bin, size_t *out_entries);
 int ckd_set_polar_maps(ckd_ctx *ctx, const int32_t *map, const int32_t *inv_map); /* s_pMap/s_pInvMap (polar.cpp:13-14), 2 ints/px */
 int ckd_get_polar_maps(ckd_ctx *ctx, int32_t *out_map, int32_t *out_inv_map);
+
+/* g_fastCosTab (fast-cosine.cpp:11-17): 1025 doubles cos(i*2pi/1024), built by ckd_create with the host's cos() like
+ * InitializeFastCosine does; the getter returns the host copy. */
+int ckd_set_fast_cos_table(ckd_ctx *ctx, const double *table1025);
+int ckd_get_fast_cos_table(ckd_ctx *ctx, double *out_table1025);
+/* fastcosf (fast-cosine.h:17-49) / fastsinf (:51-53) over n arguments on the device: d_out[i] = fastcosf(d_x[i]).  The table is
+ * staged in shared memory once per CTA.  No effect of the demo calls fastcosf; the entry exists so the helper is available
+ * (and testable) on the device side of the boundary like lutcosf is. */
+int ckd_fastcos(ckd_ctx *ctx, float *d_out, const double *d_x, size_t n, int sine);
+
+/* Frame independence.  Ball_Draw with beams leaves the last pixel of every ray row of g_renderTarget[0] untouched
+ * (ball.cpp:168-203 fills up to kTargetResX-1, and :352-363 does not clear), so that column -- and, through the in-place
+ * blur, its neighbourhood -- carries over from whatever frame was rendered before.  With enabled != 0 that column is cleared
+ * to 0 before the rays are cast, which makes every frame a pure function of (time, tracks, assets): required when frames
+ * are sharded over GPUs, where "the frame before" differs with the GPU count.  Default 0 = the reference's behaviour. */
+int ckd_set_frame_independent(ckd_ctx *ctx, int enabled);
 
 /* ---- images (replace Image_Load32 / Image_Load8 results held in file statics) -------------------------------------- */
 typedef enum ckd_image {
@@ -293,6 +310,43 @@ typedef struct ckd_twister_params {      /* torus-twister.cpp:100-101,173 */
 	float speed, shear_speed, blur; /* twister:Speed, twister::ShearSpeed (sic), twister:Blur */
 } ckd_twister_params;
 int ckd_twister_draw(ckd_ctx *ctx, const ckd_twister_params *p, float time, uint32_t *d_dest); /* Twister_Draw torus-twister.cpp:166 */
+
+/* ---- frame gather over peer memory (frames shard over the GPUs of a box, frame i -> rank i mod N, one process
+ *      per GPU; the finished frames meet on one GPU before they go where the reference hands them to Display::Update,
+ *      display.cpp:66-82).  A ring of frame slots in the collector's HBM, written by the producers with peer copies over
+ *      NVLink (CUDA IPC mapping, copy engines) and flag-signalled on the device: no NCCL, no host round trip per frame.
+ *      Frames carry a global sequence number and are pushed / popped in the order 0, 1, 2, ...                          ---- */
+typedef struct ckd_gather ckd_gather;
+#define CKD_GATHER_HANDLE_BYTES 128
+#define CKD_GATHER_CHECKSUM 1   /* ckd_gather_pop: fold the frame into the checksum table (sum_i pixel[i]*(2i+1) mod 2^64) */
+#define CKD_GATHER_TO_HOST  2   /* ckd_gather_pop: copy the frame to h_dest */
+/* collector (the process whose GPU receives the frames): allocates `slots` (2..64) frame slots of the context's resolution */
+int ckd_gather_create(ckd_ctx *ctx, int slots, ckd_gather **out_gather);
+/* collector: writes CKD_GATHER_HANDLE_BYTES bytes that another process hands to ckd_gather_open (over any channel) */
+int ckd_gather_export(ckd_gather *gather, void *out_handle);
+/* producer in another process (same or another GPU of the box): maps the collector's ring */
+int ckd_gather_open(ckd_ctx *ctx, const void *handle, ckd_gather **out_gather);
+void ckd_gather_destroy(ckd_gather *gather);
+int ckd_gather_set_timeout_ms(ckd_gather *gather, unsigned timeout_ms); /* device-side waits give up after this long (default 20 s) */
+/* producer: a local device frame to render the next frame into (three are handed out in turn; the context's stream waits,
+ * on the device, for the copy that last read it) */
+int ckd_gather_acquire(ckd_gather *gather, uint32_t **out_d_frame);
+/* producer: publish a frame as sequence number seq, ordered after everything enqueued on the context's stream so far.
+ * d_frame == NULL: the frame of the last ckd_gather_acquire; otherwise any device frame that stays untouched until
+ * ckd_gather_flush + ckd_sync.  Waits on the device (not the host) until the collector has drained slot seq % slots. */
+int ckd_gather_push(ckd_gather *gather, const uint32_t *d_frame, unsigned long long seq);
+/* collector: consume sequence number seq (call in order).  mode: 0 release the slot, CKD_GATHER_CHECKSUM, CKD_GATHER_TO_HOST
+ * (h_dest page-locked), or both.  Enqueued on the gather's consumer stream. */
+int ckd_gather_pop(ckd_gather *gather, unsigned long long seq, int mode, void *h_dest);
+int ckd_gather_wait_pop(ckd_gather *gather, unsigned long long seq); /* host blocks until that pop is done (one of the last 16) */
+/* the context's stream waits for everything pushed / popped so far (so an event recorded on it afterwards covers the gather) */
+int ckd_gather_flush(ckd_gather *gather);
+int ckd_gather_status(ckd_gather *gather); /* synchronises; CKD_OK or CKD_ERR_TIMEOUT */
+int ckd_gather_checksums(ckd_gather *gather, unsigned long long first_seq, unsigned count, unsigned long long *out_sums);
+unsigned long long ckd_gather_peer_bytes(const ckd_gather *gather); /* bytes this process has copied into the collector's memory */
+int ckd_gather_slots(const ckd_gather *gather);
+/* the same checksum for a frame in this context's memory (synchronises) */
+int ckd_frame_checksum(ckd_ctx *ctx, const uint32_t *d_frame, unsigned long long *out_sum);
 
 /* number of CUDA kernels this library launched on this context so far (bench.py's gpu_launches) */
 unsigned long long ckd_launch_count(const ckd_ctx *ctx);

@@ -65,6 +65,30 @@ void CkdHost_Flush();
 // Extension to every X_Draw / Demo_Draw below: pDest == nullptr renders the frame and leaves it on the device
 // (ckd_frame(CkdHost_Context()), or the current ckd_frame_slot while pipelined) instead of copying it to the host.
 
+// ... or, after CkdHost_SetDeviceTarget(d_frame), in that device buffer (resX*resY pixels + 4 guard rows; nullptr restores the
+// default).  This is how the timeline runner below renders straight into the staging frames of the gather.
+void CkdHost_SetDeviceTarget(uint32_t *d_frame);
+
+// ---- timeline rendering, frame-sharded over the GPUs of one box (BASELINE config 5).  One process per GPU calls
+//      this with its rank: it renders the frames i with i % world == rank through Demo_Draw -- times[i] is what the reference
+//      would get from the audio stream position, audio.cpp:175-178 -- and publishes each to the gather (ckd.h: a slot ring in
+//      the collector's HBM, peer copies over NVLink); rank 0 also consumes all frames in order.  Every frame of every pass has
+//      the sequence number seqBase + pass*numFrames + i.  The context is put into frame-independent mode for the duration
+//      (ckd_set_frame_independent), so the frames -- and their checksums -- do not depend on `world`. -------------------------
+struct CkdTimelineJob
+{
+	const double *times;            // seconds, one per frame
+	unsigned numFrames, passes;
+	unsigned rank, world;
+	ckd_gather *gather;             // nullptr: no exchange, every frame stays on the GPU that rendered it
+	int popMode;                    // rank 0: CKD_GATHER_CHECKSUM / CKD_GATHER_TO_HOST bits for ckd_gather_pop
+	uint32_t *const *hostRing;      // CKD_GATHER_TO_HOST: page-locked frame buffers used in turn (2..8), or nullptr to
+	unsigned hostRingFrames;        //   deliver into the open frame sink (CkdSink_Acquire / CkdSink_Commit by frame index)
+	unsigned long long seqBase;
+	float delta;                    // Demo_Draw's delta argument
+};
+bool CkdTimeline_Render(const CkdTimelineJob *job);
+
 // ---- frame sink (replaces Display::Update, display.cpp:66-82, for headless rendering): a raw stream file
 //      ("CKDF" header + numFrames ARGB8888 frames) fed through a ring of host buffers by a writer thread.  Acquire a buffer,
 //      let X_Draw / Demo_Draw fill it, commit it with its frame index; frames land by index, so several processes (one per
@@ -163,6 +187,16 @@ extern uint32_t *g_pXboxLogoTPB;
 // Same 16-byte layout as the reference's __m128i array; filled by Shared_Create.
 struct alignas(16) ckd_unp16 { uint16_t lane[8]; };
 extern ckd_unp16 g_gradientUnp16[kNumGradients];
+
+// fast (co)sine, fast-cosine.h:9-53 / fast-cosine.cpp:9-17.  g_fastCosTab is filled by InitializeFastCosine() from the
+// context's table (ckd_get_fast_cos_table: cos(i*2pi/1024) in double, what the reference computes).  fastcosf / fastsinf over
+// an array run on the device with the table staged in shared memory (no effect of the demo calls them -- they exist for PLLs
+// in the audio code -- so there is no per-scalar entry: one value per call is not work for a GPU).
+constexpr unsigned kFastCosTabSize = 1024;
+extern double g_fastCosTab[kFastCosTabSize+1];
+void InitializeFastCosine();
+bool fastcosf(float *pDest, const double *pX, size_t numValues);
+bool fastsinf(float *pDest, const double *pX, size_t numValues);
 
 void Polar_Blit(uint32_t *pDest, const uint32_t *pSrc, bool inverse = false);
 void Polar_BlitA(uint32_t *pDest, const uint32_t *pSrc, bool inverse = false);

@@ -227,3 +227,59 @@ def test_pinning_the_callers_frame_buffer(host_and_ref):
         assert rate(pinned) <= rate(plain) * 1.25  # never slower (typically 1.5-3x faster at 4K; 720p frames are small)
     finally:
         host.unpin(pinned)
+
+
+def _fastcos_inputs():
+    rng = np.random.default_rng(1234)
+    edges = np.arange(0, 1025, dtype=np.float64) * (2.0 * np.pi / 1024.0)       # the table's phase boundaries ...
+    near = np.concatenate([edges - 1e-9, edges, edges + 1e-9, np.nextafter(edges, np.inf), np.nextafter(edges, -np.inf)])
+    return np.concatenate([
+        near, -near, near + 2.0 * np.pi * 1000.0,
+        rng.uniform(-1e6, 1e6, 200000), rng.uniform(-8.0, 8.0, 100000), rng.uniform(-1.0, 1.0, 50000),
+        np.array([0.0, -0.0, 1.0, -1.0, 0.25, 1e-300, 5e-324, 1e9, -1e9, 1e12, 2.0**40, 2.0**52, 2.0**53 + 2, 1e15]),
+    ])
+
+
+@pytest.mark.parametrize("sine", [False, True], ids=["fastcosf", "fastsinf"])
+def test_fastcosf_matches_reference(host_and_ref, sine):
+    """fast-cosine.h:17-53 on the device (table in shared memory) against the reference's inline function, bit for bit:
+    +-1e6, the PLL domain, every table edge and its neighbours, and arguments large enough that the exponent shift wraps"""
+    host, R = host_and_ref
+    x = _fastcos_inputs()
+    got = host.fastcos(x, sine=sine)
+    arg = x - 0.25 if sine else x
+    want = np.array([R.lib.ref_fastcosf(float(v)) for v in arg], dtype=np.float32)
+    bad = np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
+    assert bad.size == 0, f"{bad.size} of {x.size} differ, first x={x[bad[0]]!r}: {got[bad[0]]!r} vs {want[bad[0]]!r}"
+    # the C ABI entry directly (device arrays) gives the same values
+    assert np.array_equal(host.context().fastcos(x[:4096], sine=sine).view(np.uint32), want[:4096].view(np.uint32))
+
+
+def test_fast_cos_table_is_the_reference_table(host_and_ref):
+    host, R = host_and_ref
+    host.fastcos(np.zeros(1))                        # InitializeFastCosine
+    ref_tab = np.ctypeslib.as_array(R.lib.ref_fast_cos_tab(), shape=(1025,))
+    assert np.array_equal(host.fast_cos_tab().view(np.uint64), ref_tab.view(np.uint64))
+    assert np.array_equal(host.context().fast_cos_table().view(np.uint64), ref_tab.view(np.uint64))
+
+
+def test_post_ops_in_place_on_one_host_buffer(host_and_ref):
+    """ops that do not read their destination (TapeWarp32, Polar_Blit, Fx_Blit_2x2) called with pSrc == pDest must work
+    on the caller's pixels (not on stale staging memory): the result equals the out-of-place call"""
+    host, R = host_and_ref
+    import post_cases as pc
+    from oracle.ref import aligned_u32
+    n = R.res_x * R.res_y
+    src = pc.seeded(n, "noise")
+
+    def buf(init):
+        a = aligned_u32(n, pad=4 * R.res_x); a[:] = init
+        return a
+
+    for op, kw in (("TapeWarp32", dict(a=R.res_x, b=R.res_y, f0=0.5, f1=1.0)), ("Polar_Blit", dict(u=1)), ("Polar_Blit", dict(u=0))):
+        want = buf(0)
+        host.post(op, want, buf(src), **kw)
+        host.post("MixSrc32", buf(pc.seeded(n, "mix")), buf(pc.seeded(n, "mix")), n)   # leaves other content in the staging targets
+        got = buf(src)
+        host.post(op, got, got, **kw)
+        assert_bit_exact(got, want, f"{op} in place")
