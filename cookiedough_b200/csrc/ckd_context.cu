@@ -287,6 +287,7 @@ extern "C" int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device)
 	size_t total = 0;
 	auto carve = [&](size_t bytes) { size_t off = total; total += AlignUp(bytes, 256); return off; };
 	const size_t offFrame = carve(outBytes);
+	const size_t offFrame2 = carve(outBytes); // ckd_frame_slot(ctx, 1): its own image, no effect or blur scratch aliases it
 	size_t offRT[kCkdNumRenderTargets], offFx[kCkdNumFxMaps], offScratch[2];
 	for (auto &o : offRT) o = carve(outBytes);
 	for (auto &o : offFx) o = carve(fxBytes);
@@ -308,6 +309,7 @@ extern "C" int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device)
 
 	uint8_t *base = static_cast<uint8_t *>(ctx->d_pool);
 	ctx->d_frame = reinterpret_cast<uint32_t *>(base + offFrame);
+	ctx->d_frame2 = reinterpret_cast<uint32_t *>(base + offFrame2);
 	for (int i = 0; i < kCkdNumRenderTargets; ++i) ctx->d_renderTarget[i] = reinterpret_cast<uint32_t *>(base + offRT[i]);
 	for (int i = 0; i < kCkdNumFxMaps; ++i) ctx->d_fxMap[i] = reinterpret_cast<uint32_t *>(base + offFx[i]);
 	for (int i = 0; i < 2; ++i) ctx->d_scratch[i] = reinterpret_cast<uint32_t *>(base + offScratch[i]);
@@ -475,7 +477,7 @@ extern "C" int ckd_download(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t
 extern "C" uint32_t *ckd_frame_slot(ckd_ctx *ctx, int slot)
 {
 	if (!ctx || slot < 0 || slot > 1) return nullptr;
-	return slot ? ctx->d_scratch[1] : ctx->d_frame; // the second blur scratch image is only used by ckd_new_blur
+	return slot ? ctx->d_frame2 : ctx->d_frame;
 }
 
 int ckd_ensure_copy_stream(ckd_ctx *ctx)

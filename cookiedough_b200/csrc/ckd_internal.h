@@ -43,6 +43,7 @@ struct ckd_ctx {
 
 	// device twins of the reference's global buffers (all carved out of one allocation, with guard rows)
 	uint32_t *d_frame = nullptr;
+	uint32_t *d_frame2 = nullptr;   // second frame buffer of the overlapped read-back (ckd_frame_slot(ctx, 1))
 	uint32_t *d_fxMap[kCkdNumFxMaps] = {};
 	uint32_t *d_renderTarget[kCkdNumRenderTargets] = {};
 	uint32_t *d_scratch[2] = {};    // blur / effect scratch, output sized (+guard)

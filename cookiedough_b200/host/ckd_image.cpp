@@ -625,12 +625,13 @@ struct JpegDecoder
 					t.Build();
 				}
 				break;
-			case 0xdd: restartInterval = int(Be16(seg)); break;
+			case 0xdd: if (length < 4) return Fail(path, "bad JPEG restart interval segment"); restartInterval = int(Be16(seg)); break;
 			case 0xee: if (length >= 14 && 0 == memcmp(seg, "Adobe", 5)) adobeTransform = seg[11]; break;
 			case 0xc0: case 0xc1: case 0xc2: // SOF0/1 (sequential Huffman), SOF2 (progressive Huffman)
 			{
 				if (haveFrame) return Fail(path, "more than one JPEG frame");
 				progressive = 0xc2 == marker;
+				if (length < 8) return Fail(path, "truncated JPEG frame header");
 				if (8 != seg[0]) return Fail(path, "only 8-bit JPEG samples are supported");
 				height = int(Be16(seg + 1)); width = int(Be16(seg + 3));
 				const int n = seg[5];
@@ -661,6 +662,7 @@ struct JpegDecoder
 			case 0xda: // SOS
 			{
 				if (!haveFrame) return Fail(path, "JPEG scan before the frame header");
+				if (length < 3) return Fail(path, "bad JPEG scan header");
 				const int n = seg[0];
 				if (n < 1 || n > int(comps.size()) || length < size_t(6 + 2*n)) return Fail(path, "bad JPEG scan header");
 				std::vector<int> scanComps;

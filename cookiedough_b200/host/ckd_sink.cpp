@@ -124,6 +124,22 @@ bool CkdSink_Open(const char *path, unsigned resX, unsigned resY, unsigned numFr
 		}
 	}
 
+	else
+	{
+		// attaching: the stream must be the one this process is about to write into
+		uint32_t header[8] = { 0 };
+		const int rfd = open(path, O_RDONLY);
+		const bool readOk = rfd >= 0 && pread(rfd, header, sizeof(header), 0) == ssize_t(sizeof(header));
+		if (rfd >= 0) close(rfd);
+		if (!readOk || 0x46444b43u != header[0] || 1u != header[1] || resX != header[2] || resY != header[3] || numFrames != header[4])
+		{
+			SetLastError(std::string("CkdSink_Open: ") + path + " is not a CKDF stream of this resolution and frame count");
+			close(sink->fd);
+			delete sink;
+			return false;
+		}
+	}
+
 	for (unsigned i = 0; i < ringFrames; ++i)
 	{
 		void *p = nullptr;
@@ -170,15 +186,24 @@ uint32_t *CkdSink_Acquire()
 bool CkdSink_Commit(uint32_t *frame, unsigned frameIndex)
 {
 	Sink *sink = s_sink;
-	if (nullptr == sink || nullptr == frame || frameIndex >= sink->numFrames)
+	if (nullptr == sink || nullptr == frame)
 	{
 		SetLastError("CkdSink_Commit: invalid argument");
 		return false;
 	}
 	std::lock_guard<std::mutex> lock(sink->mutex);
+	if (frameIndex >= sink->numFrames || !sink->error.empty())
+	{
+		// a rejected frame's buffer goes back to the ring (otherwise ringFrames rejections would block CkdSink_Acquire for good)
+		if (frameIndex >= sink->numFrames) SetLastError("CkdSink_Commit: frame index past the end of the stream");
+		else SetLastError(sink->error);
+		sink->freeList.push_back(frame);
+		sink->freed.notify_all();
+		return false;
+	}
 	sink->pending.emplace_back(frame, frameIndex);
 	sink->queued.notify_one();
-	return sink->error.empty();
+	return true;
 }
 
 // waits for all committed frames, closes the file; false when any write failed

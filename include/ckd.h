@@ -38,7 +38,11 @@ typedef enum ckd_status {
  *      BoxBlur_Create: shared-resources.cpp:14-37, fx-blitter.cpp:10-20, polar.cpp:61-72, boxblur.cpp:23-28;
  *      and CalculateCosLUT / InitializeFastCosine: sincos-lut.cpp:9-16, fast-cosine.cpp:10-17) ------------------- */
 
-/* resX/resY replace the compile-time kResX/kResY (main.h:37-38); both must be multiples of 8. */
+/* resX/resY replace the compile-time kResX/kResY (main.h:37-38); both must be multiples of 8.
+ * ckd_create makes `device` the calling thread's current CUDA device and the context lives there.  The other ckd_* calls do
+ * not switch devices (they are launch-rate sensitive): a process drives ONE device -- the deployment model is one process
+ * per GPU (bench.py, tools/render_demo.py) -- or the caller makes the context's device current (cudaSetDevice) before using
+ * a context that lives on another one.  ckd_last_error() is one string per process, overwritten by the latest failure. */
 int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device);
 void ckd_destroy(ckd_ctx *ctx);
 const char *ckd_last_error(void);
@@ -79,7 +83,7 @@ int ckd_finish_readback(ckd_ctx *ctx, int *out_done);
 
 /* overlapped read-back for frame pipelines: the copy of a finished frame runs on the context's copy stream while the
  * compute stream already renders the next one.  slot = 0/1 selects one of two in-flight copies; ckd_frame_slot(ctx, slot)
- * are two device frame buffers to alternate between.  ckd_download_overlapped() orders the copy after everything enqueued
+ * are two device frame buffers to alternate between (images of their own: no effect, blur or gather uses them as scratch).  ckd_download_overlapped() orders the copy after everything enqueued
  * on the compute stream so far; ckd_wait_download() blocks the host until that slot's copy has landed. */
 uint32_t *ckd_frame_slot(ckd_ctx *ctx, int slot);
 int ckd_download_overlapped(ckd_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, int slot);

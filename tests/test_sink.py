@@ -63,5 +63,16 @@ def test_sink_rejects_bad_use(tmp_path):
     ptr = out.acquire()
     with pytest.raises(capi.CkdError):
         out.commit(ptr, 2)  # frame index out of range
+    # the rejected buffer went back to the one-frame ring: acquiring again does not block
+    ptr = out.acquire()
+    out.view(ptr)[:] = _frame(1, 16, 16)
     out.commit(ptr, 1)
     out.close()
+    assert np.array_equal(sink.read_frame(tmp_path / "ok.ckdf", 1), _frame(1, 16, 16))
+    # attaching checks the header of the existing stream: resolution and frame count must match
+    with pytest.raises(capi.CkdError):
+        sink.Sink(tmp_path / "ok.ckdf", 32, 16, 2, ring_frames=1, pinned=False, create=False)
+    with pytest.raises(capi.CkdError):
+        sink.Sink(tmp_path / "ok.ckdf", 16, 16, 3, ring_frames=1, pinned=False, create=False)
+    again = sink.Sink(tmp_path / "ok.ckdf", 16, 16, 2, ring_frames=1, pinned=False, create=False)
+    again.close()
