@@ -526,6 +526,8 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 	const unsigned total = len + edgeSpan;           // step t adds pixel t (while t < len) and emits output t - edgeSpan
 	const unsigned mainEnd = len - edgeSpan;         // outputs [kM, mainEnd) are the full-weight main pass
 	const unsigned fullDiv = s.fullDiv, fullDivHi = fullDiv << 16;
+	// fast path of a steady block: every accumulator within [0, fastLimit] <=> no clamp anywhere (b <= 255 in every step)
+	const unsigned fastLimit = min(65535u - 255u, fullDiv ? ((256u << 16) - 1u)/fullDiv : 0u);
 
 	// this lane's share of every block: steps [s0, s0 + cnt) of the block, cnt is QT or QT - 1 (the host picks QT = ceil(kM/P))
 	const unsigned s0 = (part*kM) >> LOG2P;
@@ -580,8 +582,7 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 			pxs[q] = int(v);
 		}
 
-		int d[QT], h[QT];
-		int D = 0, L = 0, H = 65535;
+		int d[QT], bq[QT];
 		int prevPx = 0, prevS = 0;
 		if (SUBEDGES)
 		{
@@ -605,48 +606,95 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 			if (SUBEDGES && q == QT-1) { a *= m; b *= m; }   // the pending remainders belong to the next lane's first step
 			prevPx = px; prevS = spx;
 			d[q] = a - b;
-			h[q] = 65535 - b;
-			D += d[q];
-			L = __viaddmin_s32_relu(L, d[q], h[q]);
-			H = __viaddmin_s32_relu(H, d[q], h[q]);
+			bq[q] = b;
 		}
 
-		// 2. inclusive scan over the parts: (D, L, H) becomes the composition of parts 0..part
-		#pragma unroll
-		for (unsigned round = 0; round < unsigned(LOG2P); ++round)
-		{
-			const unsigned delta = C << round;
-			const int De = __shfl_up_sync(0xffffffffu, D, delta), Le = __shfl_up_sync(0xffffffffu, L, delta), He = __shfl_up_sync(0xffffffffu, H, delta);
-			if (part >= (1u << round))
-			{
-				// x -> clamp(clamp(x + De, Le, He) + D, L, H) == clamp(x + De + D, clamp(Le + D, L, H), clamp(He + D, L, H))
-				const int Ln = max(__viaddmin_s32(Le, D, H), L), Hn = max(__viaddmin_s32(He, D, H), L);
-				D += De; L = Ln; H = Hn;
-			}
-		}
-		const int accEnd = max(__viaddmin_s32(x0, D, H), L);           // accumulator after this lane's share
-		int acc = __shfl_up_sync(0xffffffffu, accEnd, C);               // ... and before it
-		if (part == 0) acc = x0;
-		x0 = __shfl_sync(0xffffffffu, accEnd, srcLast);                 // the next block starts where the last part ends
-
-		// 3. replay with the real accumulator, emit outputs (Div, deprecated/boxblur.cpp:39-42).  A step past the lane's share
-		//    computes garbage that nothing reads: its slot of outPrev is masked when it is used.
 		int o[QT];
-		#pragma unroll
-		for (int q = 0; q < QT; ++q)
+		bool done = false;
+		if (kSteady)
 		{
-			const unsigned t = t0 + q;
-			acc = __viaddmin_s32_relu(acc, d[q], h[q]);
-			if (kSteady)
-				o[q] = int(min(__umulhi(unsigned(acc), fullDivHi), 255u)); // the full-weight divisor is <= 32768: see the staged kernel
-			else
+			// Fast path.  While no clamp of the recurrence is active the accumulator is a plain running sum: the parts exchange
+			// one integer (a prefix sum of their shares' totals) instead of a (D, L, H) triple and replay with additions.  The
+			// replayed values prove the premise: every step stayed within [0, fastLimit], fastLimit <= 65535 - max(b) (neither
+			// the saturating add nor the saturating subtract of deprecated/boxblur.cpp:17-36 could have clamped, by induction
+			// over the steps) and <= the largest accumulator whose quotient still is <= 255 (packuswb would not clamp either).
+			// One vote per warp; a warp with any step out of range redoes the block on the exact path below.
+			int Ds = 0;
+			#pragma unroll
+			for (int q = 0; q < QT; ++q) Ds += d[q];
+			#pragma unroll
+			for (unsigned round = 0; round < unsigned(LOG2P); ++round)
 			{
-				const unsigned oi = (t >= edgeSpan && t < total) ? t - edgeSpan : 0;
-				const unsigned div = (oi < kM) ? s_divTab[oi] : (oi < mainEnd) ? fullDiv : s_divTab[len - 1 - oi];
-				o[q] = int(old_div(unsigned(acc), div));
+				const int up = __shfl_up_sync(0xffffffffu, Ds, C << round);
+				if (part >= (1u << round)) Ds += up;
 			}
-			outPrev[q] = o[q];
+			const int endF = x0 + Ds;
+			int accF = __shfl_up_sync(0xffffffffu, endF, C);
+			if (part == 0) accF = x0;
+			const int x0F = __shfl_sync(0xffffffffu, endF, srcLast);
+			unsigned worst = 0;
+			#pragma unroll
+			for (int q = 0; q < QT; ++q)
+			{
+				accF += d[q];
+				worst = max(worst, unsigned(accF));              // a negative accumulator reads as a huge unsigned one
+				o[q] = int(__umulhi(unsigned(accF), fullDivHi));
+			}
+			done = __all_sync(0xffffffffu, worst <= fastLimit);
+			if (done) x0 = x0F;
 		}
+
+		if (!done)
+		{
+			// Exact path: the (D, L, H) triple of the composition of this lane's clamped steps, h = 65535 - b.
+			// A step past the lane's share reads as zero pixels: d = 0, h = 65535, the identity.
+			int D = 0, L = 0, H = 65535;
+			#pragma unroll
+			for (int q = 0; q < QT; ++q)
+			{
+				const int h = 65535 - bq[q];
+				D += d[q];
+				L = __viaddmin_s32_relu(L, d[q], h);
+				H = __viaddmin_s32_relu(H, d[q], h);
+			}
+
+			// 2. inclusive scan over the parts: (D, L, H) becomes the composition of parts 0..part
+			#pragma unroll
+			for (unsigned round = 0; round < unsigned(LOG2P); ++round)
+			{
+				const unsigned delta = C << round;
+				const int De = __shfl_up_sync(0xffffffffu, D, delta), Le = __shfl_up_sync(0xffffffffu, L, delta), He = __shfl_up_sync(0xffffffffu, H, delta);
+				if (part >= (1u << round))
+				{
+					// x -> clamp(clamp(x + De, Le, He) + D, L, H) == clamp(x + De + D, clamp(Le + D, L, H), clamp(He + D, L, H))
+					const int Ln = max(__viaddmin_s32(Le, D, H), L), Hn = max(__viaddmin_s32(He, D, H), L);
+					D += De; L = Ln; H = Hn;
+				}
+			}
+			const int accEnd = max(__viaddmin_s32(x0, D, H), L);           // accumulator after this lane's share
+			int acc = __shfl_up_sync(0xffffffffu, accEnd, C);               // ... and before it
+			if (part == 0) acc = x0;
+			x0 = __shfl_sync(0xffffffffu, accEnd, srcLast);                 // the next block starts where the last part ends
+
+			// 3. replay with the real accumulator, emit outputs (Div, deprecated/boxblur.cpp:39-42).  A step past the lane's share
+			//    computes garbage that nothing reads: its slot of outPrev is masked when it is used.
+			#pragma unroll
+			for (int q = 0; q < QT; ++q)
+			{
+				const unsigned t = t0 + q;
+				acc = __viaddmin_s32_relu(acc, d[q], 65535 - bq[q]);
+				if (kSteady)
+					o[q] = int(min(__umulhi(unsigned(acc), fullDivHi), 255u)); // the full-weight divisor is <= 32768: see the staged kernel
+				else
+				{
+					const unsigned oi = (t >= edgeSpan && t < total) ? t - edgeSpan : 0;
+					const unsigned div = (oi < kM) ? s_divTab[oi] : (oi < mainEnd) ? fullDiv : s_divTab[len - 1 - oi];
+					o[q] = int(old_div(unsigned(acc), div));
+				}
+			}
+		}
+		#pragma unroll
+		for (int q = 0; q < QT; ++q) outPrev[q] = o[q];
 		if (SUBEDGES)
 		{
 			lastOut2 = lastOut1;

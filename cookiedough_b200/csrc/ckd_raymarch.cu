@@ -201,6 +201,7 @@ struct SpikeyFrame
 	float xOffs, yOffs, zTerm; // close: dir.z = 1+zOffsFinal; distant: origin.z = -2.614+zOffs
 	float normalGrain;
 	float warmup;
+	float totalSafe;          // distant, FAST kernel: while |total| < totalSafe both LUT angles are provably within the fast lookup's range
 };
 
 template <bool GOLDEN_ANGLE, class Lut>
@@ -259,6 +260,25 @@ struct SpikeyCloseEffect
 	}
 };
 
+// The distant variant marches up to 48 steps of 0.314*(|p| - radius): rays that miss the ball run away geometrically and do
+// reach angles past the fast lookup's range (the reference's aliased lookups out there are part of the picture).  The march
+// total bounds the sample position (|p| <= |origin| + |dir|*|total|), so the FAST kernel guards every distance evaluation
+// with one comparison: |total| < totalSafe (host: SpikeyTotalSafe) -> conversion-free lookups, else the exact ones.  A NaN
+// total fails the comparison.  Rays that hit (and the first ~20 steps of those that miss) never leave the fast side.
+template <class Lut> struct SpikeyGuard
+{
+	static __device__ __forceinline__ float eval(const Lut &lut, const SpikeyFrame &f, float, float px, float py, float pz) { return fSpikey<false>(lut, f, px, py, pz); }
+};
+template <> struct SpikeyGuard<CosLutFast>
+{
+	static __device__ __forceinline__ float eval(const CosLutFast &lut, const SpikeyFrame &f, float total, float px, float py, float pz)
+	{
+		if (fabsf(total) < f.totalSafe)
+			return fSpikey<false>(lut, f, px, py, pz);
+		return fSpikey<false>(CosLut(lut.handle), f, px, py, pz);
+	}
+};
+
 struct SpikeyDistantEffect
 {
 	SpikeyFrame f;
@@ -273,23 +293,25 @@ struct SpikeyDistantEffect
 		fast_norm3(e.rsqrt, dir);
 
 		float hx = 0.f, hy = 0.f, hz = 0.f;
-		float march = 1.f, total = 0.f;
+		float march = 1.f, total = 0.f, lastTotal = 0.f;
 		#pragma unroll 1
 		for (int iStep = 0; march > 0.001f && iStep < 48; ++iStep)
 		{
 			hx = ox + dir.x*total;
 			hy = oy + dir.y*total;
 			hz = oz + dir.z*total;
-			march = fSpikey<false>(e.lut, f, hx, hy, hz);
+			march = SpikeyGuard<Lut>::eval(e.lut, f, total, hx, hy, hz);
+			lastTotal = total;
 			march *= 0.314f;
 			total += march;
 		}
 
+		// the taps sit at the last sampled position (+ nOffs, which SpikeyTotalSafe accounts for): guarded by that step's total
 		constexpr float nOffs = kPI*0.02f;
 		vec3 normal = {
-			march-fSpikey<false>(e.lut, f, hx+nOffs, hy, hz),
-			march-fSpikey<false>(e.lut, f, hx, hy+nOffs, hz),
-			march-fSpikey<false>(e.lut, f, hx, hy, hz+nOffs) };
+			march-SpikeyGuard<Lut>::eval(e.lut, f, lastTotal, hx+nOffs, hy, hz),
+			march-SpikeyGuard<Lut>::eval(e.lut, f, lastTotal, hx, hy+nOffs, hz),
+			march-SpikeyGuard<Lut>::eval(e.lut, f, lastTotal, hx, hy, hz+nOffs) };
 		fast_norm3(e.rsqrt, normal);
 
 		const float diffuse = stdmax(0.f, normal.z*0.8f + normal.y*0.2f);
@@ -833,6 +855,34 @@ extern "C" int ckd_nautilus_draw(ckd_ctx *ctx, const ckd_nautilus_params *p, flo
 }
 
 // Spikey_Draw, shadertoy.cpp:661-733
+// Range proof of the close and the specular-only variants (fixed step budgets, slow growth).  March: |fSpikey| <= |p| + 1.35 +
+// 2*scale while every table value so far is within [-1, 1] (the induction of LutRangeProof); |p| <= |origin| + |dir|*|total|
+// with |dir| <= 1.002 (RSQRTPS error); total grows by |march|*stepScale per step.  The recursion is evaluated in double with
+// every constant rounded up; the taps add nOffs.  Close: 32 steps of 0.157 -> |total| <= ~270 for the shipped parameters,
+// angles <= 22*272 + |gx|: far inside the range.  Anything non-finite fails LutRangeProof::holds().
+static LutRangeProof SpikeyFixedProof(const SpikeyFrame &f, double originLen, double stepScale, int steps, double nOffs)
+{
+	double total = 0.0;
+	for (int i = 0; i < steps; ++i)
+		total += stepScale*1.001*((originLen + 1.002*total) + 1.35 + 0.5);
+	const double pMax = originLen + 1.002*total + fabs(nOffs);
+	LutRangeProof proof;
+	proof.add(fabs(double(f.gy))*pMax + fabs(double(f.gx)));
+	proof.add(fabs(double(f.gz))*pMax + fabs(double(f.gx)));
+	return proof;
+}
+
+// Largest |total| for which both angles of fSpikey (gy*py - gx, gz*px + gx) stay below LutRangeProof's threshold at every
+// position origin + dir*total (+ nOffs on one axis), |dir| <= 1.002.  <= 0 or NaN: no fast side (the exact kernel is launched).
+static float SpikeyTotalSafe(const SpikeyFrame &f, double originLen, double nOffs)
+{
+	const double g = std::max(fabs(double(f.gy)), fabs(double(f.gz)));
+	if (!(g > 0.0))
+		return 0.f;
+	const double safe = ((20000.0 - fabs(double(f.gx)))/g - originLen - fabs(nOffs))/1.002;
+	return (safe > 1.0 && safe < 1e30) ? float(safe*0.999) : 0.f;
+}
+
 extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float time, int close, uint32_t *d_dest)
 {
 	CKD_REQUIRE(ctx && p && d_dest, "null argument");
@@ -860,10 +910,12 @@ extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float t
 		f.zTerm = 1.f + zOffsFinal;
 		f.normalGrain = p->close_normal_grain;
 		SpikeyCloseEffect fx = { f };
+		// origin (0.2, 0, -2.23), 32 steps of march*(0.05*pi), taps at +normalGrain (shadertoy.cpp:460-492)
+		const LutRangeProof proof = SpikeyFixedProof(f, 2.24, 0.05*3.14159266, 32, double(f.normalGrain));
 		const float mbOpacity = ckdh::saturatef(p->mix_blur_opacity);
 		if (!(mbOpacity > 0.f))
-			return RaymarchAndBlit(ctx, fx, "raymarch_spikey_close", nullptr, d_dest);
-		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_close"));
+			return RaymarchAndBlit(ctx, fx, "raymarch_spikey_close", &proof, d_dest);
+		CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_close", &proof));
 		{
 			// shadertoy.cpp:672-707
 			const float mbMap = ckdh::clampf(0, 1.f, p->mix_blur_map);
@@ -903,15 +955,21 @@ extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float t
 		f.xOffs = p->dist_x;
 		f.yOffs = p->dist_y;
 		f.zTerm = -2.614f + p->dist_z;
+		// origin (0, 0, zTerm), taps at +pi*0.02 (shadertoy.cpp:546-575): the FAST kernel guards each evaluation with totalSafe
+		f.totalSafe = SpikeyTotalSafe(f, fabs(double(f.zTerm)), 3.14159266*0.02);
+		LutRangeProof guarded;
+		guarded.add(f.totalSafe > 0.f ? 0.0 : 1e30);
 		SpikeyDistantEffect fx = { f };
-		return RaymarchAndBlit(ctx, fx, "raymarch_spikey_distant", nullptr, d_dest);
+		return RaymarchAndBlit(ctx, fx, "raymarch_spikey_distant", &guarded, d_dest);
 	}
 
 	// RenderSpikeyMap_2x2_Distant_SpecularOnly(…, 1.f+warmup), shadertoy.cpp:600-608, 727-729
 	f.gx = p->speed*time; f.gy = 8.f; f.gz = 16.f;
 	f.warmup = 1.f+warmup;
 	SpikeySpecOnlyEffect fx = { f };
-	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_spec"));
+	// origin (0, 0, -3.314), 36 steps of march*0.075*golden ratio, taps at +0.01 (shadertoy.cpp:610-640)
+	const LutRangeProof proof = SpikeyFixedProof(f, 3.314, 0.075*1.6180340, 36, 0.01);
+	CKD_TRY(LaunchRaymarch(ctx, fx, ctx->d_fxMap[0], "raymarch_spikey_spec", &proof));
 	CKD_TRY(ckd_old_blur_h(ctx, ctx->d_fxMap[0], ctx->d_fxMap[0], unsigned(ctx->fxX), unsigned(ctx->fxY), ckdh::BoxBlurScale(1.f+warmup)));
 	return ckd_fx_blit_2x2(ctx, d_dest, ctx->d_fxMap[0]);
 }

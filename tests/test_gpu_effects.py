@@ -42,15 +42,12 @@ def test_every_golden_effect_case(ctx_synth, golden_effects):
             out = _draw(ctx_synth, case)
             if sha256_u32(out) == case["sha256"]:
                 continue
-            if case["effect"] in INTEGER_EFFECTS:
-                failures.append(f"{label}: integer path not bit-exact")
-                continue
-            # float path: fall back to the pinned crop with the north-star tolerance
+            # the pins were generated with the same RSQRTPS table and assets: every case, float paths included, reproduces its
+            # frame bit for bit (the north star's 2-LSB tolerance is only needed against a reference on another CPU: the live tests)
             c = case["crop"]
             ref_crop = np.frombuffer(bytes.fromhex(c["hex"]), dtype="<u4").reshape(c["h"], c["w"])
             exact, max_delta = pixel_stats(out[c["y"]:c["y"] + c["h"], c["x"]:c["x"] + c["w"]], ref_crop)
-            if max_delta > 2 or exact < 97.0:  # 288-pixel crop: a few 1-LSB pixels are within the tolerance
-                failures.append(f"{label}: crop {exact:.2f}% exact, max delta {max_delta}")
+            failures.append(f"{label}: frame differs from its pin (pinned crop: {exact:.2f}% exact, max delta {max_delta})")
     assert not failures, "\n".join(failures)
 
 
@@ -79,6 +76,10 @@ LIVE_ROWS = [
     ("landscape", "landscape", None, 40), ("landscape", "landscape", None, 1040), ("ball", "ball", None, 1200),
     ("ball", "ball", None, 1750), ("nautilus", "nautilus", None, 5510), ("tunnel", "tunnel", None, 5236),
     ("spikey_close", "spikey", True, 7100), ("spikey_distant", "spikey", False, 7080), ("tunnelscape", "tunnelscape", None, 4710),
+    # ball:Radius > 1280 (2000 / 2200 / 1800 at these rows; 1200, 1500 and 1750 above have 1800 too): at 720p the reference's
+    # spans run past their 1280-pixel row into the next one, this implementation clips them to the row.
+    # The spill is overwritten by the next row's own span before anything reads it, so the frames must still be identical.
+    ("ball", "ball", None, 1100), ("ball", "ball", None, 1490), ("ball", "ball", None, 1410),
 ]
 
 
