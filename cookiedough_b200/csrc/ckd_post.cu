@@ -542,6 +542,48 @@ template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel_1
 	pDest[i] = out;
 }
 
+// persistent variant: a grid that fits the machine once walks the quads with a grid stride and requests the map entries (and
+// the destination pixels) of its NEXT quad before it gathers the texels of the current one, so the two dependent round trips
+// of a quad (map, then texels) of consecutive iterations overlap
+template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel_pf(uint32_t *pDest, const uint32_t *__restrict__ pSrc, const int4 *__restrict__ pMap, unsigned numQuads, unsigned resX)
+{
+	const unsigned stride = gridDim.x*blockDim.x;
+	unsigned q = blockIdx.x*blockDim.x + threadIdx.x;
+	if (q >= numQuads)
+		return;
+	int4 m0 = __ldg(pMap + size_t(q)*2), m1 = __ldg(pMap + size_t(q)*2 + 1);
+	uint4 d = make_uint4(0, 0, 0, 0);
+	if (ALPHA) d = reinterpret_cast<const uint4 *>(pDest)[q];
+	for (;;)
+	{
+		const unsigned qn = q + stride;
+		const bool more = qn < numQuads;
+		int4 n0 = m0, n1 = m1;
+		uint4 dn = d;
+		if (more)
+		{
+			n0 = __ldg(pMap + size_t(qn)*2); n1 = __ldg(pMap + size_t(qn)*2 + 1);
+			if (ALPHA) dn = reinterpret_cast<const uint4 *>(pDest)[qn];
+		}
+		uint4 out;
+		out.x = polar_fetch(pSrc, m0.x, m0.y, resX);
+		out.y = polar_fetch(pSrc, m0.z, m0.w, resX);
+		out.z = polar_fetch(pSrc, m1.x, m1.y, resX);
+		out.w = polar_fetch(pSrc, m1.z, m1.w, resX);
+		if (ALPHA)
+		{
+			out.x = polar_blend(d.x, out.x);
+			out.y = polar_blend(d.y, out.y);
+			out.z = polar_blend(d.z, out.z);
+			out.w = polar_blend(d.w, out.w);
+		}
+		reinterpret_cast<uint4 *>(pDest)[q] = out;
+		if (!more)
+			break;
+		q = qn; m0 = n0; m1 = n1; d = dn;
+	}
+}
+
 static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse, bool alpha)
 {
 	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
@@ -560,6 +602,15 @@ static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, in
 			polar_blit_kernel_1px<true><<<ckd_div_up(numPixels, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap2, numPixels, unsigned(ctx->resX));
 		else
 			polar_blit_kernel_1px<false><<<ckd_div_up(numPixels, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap2, numPixels, unsigned(ctx->resX));
+	}
+	else if (variant >= 2)
+	{
+		const unsigned perSM = unsigned(variant >= 4 ? variant : 6); // CTAs of 256 threads per SM
+		const unsigned grid = std::min<unsigned>(blocks, unsigned(ctx->numSMs)*perSM);
+		if (alpha)
+			polar_blit_kernel_pf<true><<<grid, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
+		else
+			polar_blit_kernel_pf<false><<<grid, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
 	}
 	else if (alpha)
 		polar_blit_kernel<true><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));

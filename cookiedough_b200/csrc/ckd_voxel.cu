@@ -273,17 +273,24 @@ __global__ void __launch_bounds__(kScapeColsPerBlock*32) landscape_kernel(uint32
 			carryLastColor = unpack16(__ldg(colorMap + (U|V)));
 		}
 
+		// the samples of a chunk do not depend on the carry: the gathers of the NEXT chunk are issued before this chunk's scan
+		// and span stores (see tunnelscape_kernel), so their L2 latency overlaps the emission instead of heading every iteration
+		RawSample next = fetch_sample(heightMap, colorMap, fogGradient, lane, int(unsigned(f.fpX1) + (lane+1)*unsigned(fpDX)), int(unsigned(f.fpY1) + (lane+1)*unsigned(fpDY)), 1023u, 10u);
+
 		for (unsigned base = 0; base < kScapeRayLength; base += 32)
 		{
 			const unsigned iStep = base + lane;
-			const int curX = int(unsigned(f.fpX1) + (iStep+1)*unsigned(fpDX));
-			const int curY = int(unsigned(f.fpY1) + (iStep+1)*unsigned(fpDY));
+			const RawSample raw = next;
+			if (base + 32 < kScapeRayLength)
+			{
+				const unsigned nStep = iStep + 32;
+				next = fetch_sample(heightMap, colorMap, fogGradient, nStep, int(unsigned(f.fpX1) + (nStep+1)*unsigned(fpDX)), int(unsigned(f.fpY1) + (nStep+1)*unsigned(fpDY)), 1023u, 10u);
+			}
 
-			const TexCoords t = prep_uvs(curX, curY, 1023u, 10u);
-			const unsigned mapHeight = sample_u8(heightMap, t);
-			Color16 color = unpack16(sample_argb(colorMap, t));
+			const unsigned mapHeight = bilerp_u8(raw.h[0], raw.h[1], raw.h[2], raw.h[3], int(raw.fu), int(raw.fv));
+			Color16 color = unpack16(bilerp_argb(raw.c[0], raw.c[1], raw.c[2], raw.c[3], raw.fu, raw.fv));
 
-			const Color16 fog = unpack16(__ldg(fogGradient + (iStep >> 1)));
+			const Color16 fog = unpack16(raw.fog);
 			#pragma unroll
 			for (int i = 0; i < 4; ++i) color.c[i] = subs16(color.c[i], fog.c[i]);
 

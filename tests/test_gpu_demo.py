@@ -123,7 +123,7 @@ def test_demo_draw_4k_child_process():
 
 
 def test_render_demo_stream_matches_demo_draw(tmp_path):
-    """tools/render_demo.py (f4: device frame -> pinned ring -> writer thread) writes the frames Demo_Draw produces"""
+    """tools/render_demo.py (e + f4: CkdTimeline_Render -> ckd_gather ring -> sink's pinned ring -> writer thread) writes the frames Demo_Draw produces"""
     from oracle import ref as oref
     if not oref.available(720):
         pytest.skip("oracle/_ref not built")
@@ -137,6 +137,7 @@ def test_render_demo_stream_matches_demo_draw(tmp_path):
     assert sink.read_header(path) == (1280, 720, frames)
     host = hostapi.Host(1280, 720, 0, Assets(1280, 720), demo=True)
     try:
+        host.context().set_frame_independent(True)   # what CkdTimeline_Render renders with (frames must not depend on the sharding)
         out = np.zeros((720, 1280), dtype=np.uint32)
         times = sharding.timeline_times(frames)
         for i in range(frames):

@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
-"""Render the demo timeline to a raw frame stream (SURVEY.md section 8 rows f1 + f4): Demo_Draw on every GPU of the box, the
-frames gathered to rank 0 over NCCL (device to device, NVLink), copied into a pinned host ring and written by the sink's
-writer thread.
+"""Render the demo timeline to a raw frame stream (SURVEY.md section 8 rows e + f1 + f4): Demo_Draw on every GPU of the box
+(CkdTimeline_Render, include/ckd_host.h), every frame pushed into the slot ring in rank 0's HBM by the library's peer-memory
+gather (ckd_gather_*, include/ckd.h: CUDA IPC mapping, copy-engine peer copies over NVLink, device-side flags -- no NCCL on
+the data path; torch.distributed only carries the 128-byte ring handle), drained in frame order into the sink's pinned host
+ring and written by its writer thread.
 
     python tools/render_demo.py --out /tmp/demo.ckdf --frames 600 [--res 2160]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/render_demo.py --out ... --frames 600
@@ -12,29 +14,23 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-class DeviceFrame:
-    """__cuda_array_interface__ view of a device frame owned by the renderer's context"""
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
     ap.add_argument("--frames", type=int, default=600)
     ap.add_argument("--res", type=int, default=2160)
     ap.add_argument("--ring", type=int, default=6)
+    ap.add_argument("--slots", type=int, default=8, help="frames of the gather's slot ring in rank 0's HBM")
     args = ap.parse_args()
 
     import torch
     import torch.distributed as dist
-    from cookiedough_b200 import hostapi, sharding, sink
+    from cookiedough_b200 import capi, hostapi, sharding, sink
     from cookiedough_b200.assets import Assets
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     res_y = args.res; res_x = res_y * 16 // 9
     n = res_x * res_y
@@ -43,59 +39,53 @@ def main():
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     times = sharding.timeline_times(args.frames)
 
+    # the ring lives on rank 0; its handle travels once over the control plane
+    if rank == 0:
+        gather = capi.Gather(ctx, slots=args.slots)
+        handle = gather.export()
+    else:
+        gather, handle = None, bytes(capi.GATHER_HANDLE_BYTES)
+    if world > 1:
+        t = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, src=0)
+        if rank != 0:
+            gather = capi.Gather(ctx, handle=bytes(t.cpu().tolist()))
+    gather.set_timeout_ms(60000)
+
     out = sink.Sink(args.out, res_x, res_y, args.frames, ring_frames=args.ring, pinned=True, create=True) if rank == 0 else None
-    frame_dev = torch.as_tensor(DeviceFrame(ctx.frame(), n), device="cuda")      # the context's device frame, zero-copy
-    recv = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(2)] if rank == 0 else None
-    copy_stream = torch.cuda.Stream() if rank == 0 else None
 
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    pending = []  # rank 0: (event, buffer address, frame index) of device->host copies in flight
-    for i in range(args.frames):
-        owner = i % world
-        if owner == rank:
-            host.demo_draw(0, times[i])                      # composed frame stays on the device
-        if rank == 0:
-            if owner == 0:
-                src = frame_dev
-            else:
-                src = recv[i & 1]
-                dist.recv(src, src=owner)
-            ptr = out.acquire()                              # pinned host buffer of the sink's ring
-            dst = torch.from_numpy(out.view(ptr).reshape(-1).view(np.int32))
-            copy_stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(copy_stream):
-                dst.copy_(src, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record()
-            torch.cuda.current_stream().wait_stream(copy_stream)   # src (device frame / receive buffer) is reused by what follows
-            pending.append((ev, ptr, i))
-            while len(pending) > 2:
-                e, p, k = pending.pop(0)
-                e.synchronize()
-                out.commit(p, k)
-        elif owner == rank:
-            dist.send(frame_dev, dst=0)
+    # rank r renders the frames i % world == r and pushes them; rank 0 pops every frame in order into the open sink
+    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=1, pop_mode=capi.GATHER_CHECKSUM | capi.GATHER_TO_HOST, host_ring=None)
+    ctx.sync()
+    gather.status()
     if rank == 0:
-        for e, p, k in pending:
-            e.synchronize()
-            out.commit(p, k)
         out.close()
-    torch.cuda.synchronize()
     elapsed = time.perf_counter() - t0
+    peer_bytes = gather.peer_bytes()
     if world > 1:
-        t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
+        t = torch.tensor([elapsed, float(peer_bytes)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        elapsed, peer_bytes = float(t[0].item()), float(t[1].item())
     if rank == 0:
         print(json.dumps({"tool": "render_demo", "frames": args.frames, "res": [res_x, res_y], "n_gpus": world, "seconds": elapsed,
                           "fps": args.frames / elapsed, "mpixel_s": args.frames * n / elapsed / 1e6, "gbytes_written": args.frames * n * 4 / 1e9,
-                          "out": args.out, "gather": "NCCL send/recv to rank 0, pinned ring, writer thread" if world > 1 else "single rank"}))
-    host.close()
+                          "out": args.out, "nvlink_gbytes": peer_bytes / 1e9,
+                          "gather": "ckd_gather_* (slot ring in rank 0's HBM, peer copies, device-side flags) -> sink's pinned ring -> writer thread"}))
+    if world > 1:
+        dist.barrier()          # the ring may only go away after every producer has unmapped it: producers close first
+    if rank != 0:
+        gather.close()
     if world > 1:
         dist.barrier()
+    if rank == 0:
+        gather.close()
+    host.close()
+    if world > 1:
         dist.destroy_process_group()
 
 
