@@ -20,6 +20,7 @@ struct OldBlurSetup
 {
 	unsigned edgeSpan, kernelMedian, remainderShift, startWeight, fullPassLen, fullDiv;
 	int subEdges;
+	int noFastPath;           // CKD_BLUR_NOFAST (A/B measurements): the blocked kernel never tries its plain-sum fast path
 };
 
 // WeightToDiv, deprecated/boxblur.cpp:11-14; the value lands in 16-bit lanes (_mm_set1_epi16): keep the low 16 bits
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 	const unsigned mainEnd = len - edgeSpan;         // outputs [kM, mainEnd) are the full-weight main pass
 	const unsigned fullDiv = s.fullDiv, fullDivHi = fullDiv << 16;
 	// fast path of a steady block: every accumulator within [0, fastLimit] <=> no clamp anywhere (b <= 255 in every step)
-	const unsigned fastLimit = min(65535u - 255u, fullDiv ? ((256u << 16) - 1u)/fullDiv : 0u);
+	const unsigned fastLimit = s.noFastPath ? 0u : min(65535u - 255u, fullDiv ? ((256u << 16) - 1u)/fullDiv : 0u); // 0: every block takes the exact path
 
 	// this lane's share of every block: steps [s0, s0 + cnt) of the block, cnt is QT or QT - 1 (the host picks QT = ceil(kM/P))
 	const unsigned s0 = (part*kM) >> LOG2P;
@@ -600,9 +601,10 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 				if (t >= len) px = 0;
 				if (t < span || t >= total) spx = 0;
 			}
-			a = (prevPx >> sh) + (px - (px >> sh));
+			// odd kernels shift the remainder out entirely (bytes >> 8 == 0): a = px, b = spx
+			a = SUBEDGES ? (prevPx >> sh) + (px - (px >> sh)) : px;
 			if (!kSteady && t > len) a = 0;                  // t == len: the pending remainder, deprecated/boxblur.cpp:113-115
-			int b = (prevS >> sh) + (spx - (spx >> sh));
+			int b = SUBEDGES ? (prevS >> sh) + (spx - (spx >> sh)) : spx;
 			if (SUBEDGES && q == QT-1) { a *= m; b *= m; }   // the pending remainders belong to the next lane's first step
 			prevPx = px; prevS = spx;
 			d[q] = a - b;
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 
 		int o[QT];
 		bool done = false;
-		if (kSteady)
+		if (kSteady && fastLimit != 0)
 		{
 			// Fast path.  While no clamp of the recurrence is active the accumulator is a plain running sum: the parts exchange
 			// one integer (a prefix sum of their shares' totals) instead of a (D, L, H) triple and replay with additions.  The
@@ -788,7 +790,13 @@ static cudaError_t LaunchBlocked(ckd_ctx *ctx, uint8_t *p, unsigned numLines, un
 	// parts that keep QT <= 8 win: every extra scan round costs more than the warps it adds hide (two parts up to a median of
 	// 13, four up to 32, ...).
 	const unsigned blocks = ckd_div_up(numLines, 8), kM = s.kernelMedian;
-	const unsigned log2P = (kM <= 13) ? 1 : (kM <= 32) ? 2 : (kM <= 64) ? 3 : 4;
+	unsigned log2P = (kM <= 13) ? 1 : (kM <= 32) ? 2 : (kM <= 64) ? 3 : 4;
+	static const int forcedLog2P = getenv("CKD_BLUR_LOG2P") ? atoi(getenv("CKD_BLUR_LOG2P")) : 0; // tuning sweeps: 1..4 where the shape allows it
+	if (forcedLog2P >= 1 && forcedLog2P <= 4)
+	{
+		const unsigned q = (kM + (1u << forcedLog2P) - 1) >> forcedLog2P;
+		if (q >= 2 && q <= 8) log2P = unsigned(forcedLog2P);
+	}
 	const int qt = int((kM + (1u << log2P) - 1) >> log2P); // every lane then owns qt or qt - 1 steps
 
 	const size_t smem = 2*kRingBytes;
@@ -856,6 +864,8 @@ static int OldBlurPass(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, un
 	CKD_REQUIRE(lineLen >= s.kernelMedian + s.edgeSpan, "image smaller than the blur kernel (the reference would run off the buffer)");
 	s.fullPassLen = lineLen - (s.kernelMedian + s.edgeSpan);
 	s.fullDiv = WeightToDiv16(kernelSpan << 4);
+	static const bool noFast = nullptr != getenv("CKD_BLUR_NOFAST");
+	s.noFastPath = noFast ? 1 : 0;
 
 	const bool vert = (stepStride != 1);
 	const unsigned pitch = unsigned(vert ? stepStride : lineStride); // pixels per image row

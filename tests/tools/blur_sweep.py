@@ -24,6 +24,8 @@ images = {
     "blocks": np.where(((xx // 97 + yy // 61) % 3) == 0, np.uint32(0xffffffff), np.uint32(0)).astype(np.uint32).reshape(-1),
     "gradient": ((xx * 255 // res_x) | ((yy * 255 // res_y) << 8) | (((xx + yy) * 255 // (res_x + res_y)) << 16) | (0xff << 24)).astype(np.uint32).reshape(-1),
 }
+if os.environ.get("CKD_SWEEP_IMAGES"):
+    images = {k: v for k, v in images.items() if k in os.environ["CKD_SWEEP_IMAGES"].split(",")}
 d_a = ctx.to_device(images["noise"], pad_elems=4 * res_x)
 print(f"{'K':>4} {'img':>9} {'h us':>8} {'v us':>8}  parity")
 for K in KS:
