@@ -204,7 +204,10 @@ def bind_to_gpu_numa(local):
 
 
 def dist_setup(n_gpus):
-    # NCCL_DEBUG is left as the caller set it; NCCL logs to stderr and stdout carries exactly one JSON line
+    # NCCL_DEBUG is left as the caller set it.  Without one, NCCL still prints its version banner on stdout, where this script owes
+    # exactly one JSON line: the banner is sent to stderr (NCCL_DEBUG_FILE), not switched off.
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -201,7 +201,6 @@ struct SpikeyFrame
 	float xOffs, yOffs, zTerm; // close: dir.z = 1+zOffsFinal; distant: origin.z = -2.614+zOffs
 	float normalGrain;
 	float warmup;
-	float totalSafe;          // distant, FAST kernel: while |total| < totalSafe both LUT angles are provably within the fast lookup's range
 };
 
 template <bool GOLDEN_ANGLE, class Lut>
@@ -260,25 +259,6 @@ struct SpikeyCloseEffect
 	}
 };
 
-// The distant variant marches up to 48 steps of 0.314*(|p| - radius): rays that miss the ball run away geometrically and do
-// reach angles past the fast lookup's range (the reference's aliased lookups out there are part of the picture).  The march
-// total bounds the sample position (|p| <= |origin| + |dir|*|total|), so the FAST kernel guards every distance evaluation
-// with one comparison: |total| < totalSafe (host: SpikeyTotalSafe) -> conversion-free lookups, else the exact ones.  A NaN
-// total fails the comparison.  Rays that hit (and the first ~20 steps of those that miss) never leave the fast side.
-template <class Lut> struct SpikeyGuard
-{
-	static __device__ __forceinline__ float eval(const Lut &lut, const SpikeyFrame &f, float, float px, float py, float pz) { return fSpikey<false>(lut, f, px, py, pz); }
-};
-template <> struct SpikeyGuard<CosLutFast>
-{
-	static __device__ __forceinline__ float eval(const CosLutFast &lut, const SpikeyFrame &f, float total, float px, float py, float pz)
-	{
-		if (fabsf(total) < f.totalSafe)
-			return fSpikey<false>(lut, f, px, py, pz);
-		return fSpikey<false>(CosLut(lut.handle), f, px, py, pz);
-	}
-};
-
 struct SpikeyDistantEffect
 {
 	SpikeyFrame f;
@@ -293,25 +273,23 @@ struct SpikeyDistantEffect
 		fast_norm3(e.rsqrt, dir);
 
 		float hx = 0.f, hy = 0.f, hz = 0.f;
-		float march = 1.f, total = 0.f, lastTotal = 0.f;
+		float march = 1.f, total = 0.f;
 		#pragma unroll 1
 		for (int iStep = 0; march > 0.001f && iStep < 48; ++iStep)
 		{
 			hx = ox + dir.x*total;
 			hy = oy + dir.y*total;
 			hz = oz + dir.z*total;
-			march = SpikeyGuard<Lut>::eval(e.lut, f, total, hx, hy, hz);
-			lastTotal = total;
+			march = fSpikey<false>(e.lut, f, hx, hy, hz);
 			march *= 0.314f;
 			total += march;
 		}
 
-		// the taps sit at the last sampled position (+ nOffs, which SpikeyTotalSafe accounts for): guarded by that step's total
 		constexpr float nOffs = kPI*0.02f;
 		vec3 normal = {
-			march-SpikeyGuard<Lut>::eval(e.lut, f, lastTotal, hx+nOffs, hy, hz),
-			march-SpikeyGuard<Lut>::eval(e.lut, f, lastTotal, hx, hy+nOffs, hz),
-			march-SpikeyGuard<Lut>::eval(e.lut, f, lastTotal, hx, hy, hz+nOffs) };
+			march-fSpikey<false>(e.lut, f, hx+nOffs, hy, hz),
+			march-fSpikey<false>(e.lut, f, hx, hy+nOffs, hz),
+			march-fSpikey<false>(e.lut, f, hx, hy, hz+nOffs) };
 		fast_norm3(e.rsqrt, normal);
 
 		const float diffuse = stdmax(0.f, normal.z*0.8f + normal.y*0.2f);
@@ -872,17 +850,6 @@ static LutRangeProof SpikeyFixedProof(const SpikeyFrame &f, double originLen, do
 	return proof;
 }
 
-// Largest |total| for which both angles of fSpikey (gy*py - gx, gz*px + gx) stay below LutRangeProof's threshold at every
-// position origin + dir*total (+ nOffs on one axis), |dir| <= 1.002.  <= 0 or NaN: no fast side (the exact kernel is launched).
-static float SpikeyTotalSafe(const SpikeyFrame &f, double originLen, double nOffs)
-{
-	const double g = std::max(fabs(double(f.gy)), fabs(double(f.gz)));
-	if (!(g > 0.0))
-		return 0.f;
-	const double safe = ((20000.0 - fabs(double(f.gx)))/g - originLen - fabs(nOffs))/1.002;
-	return (safe > 1.0 && safe < 1e30) ? float(safe*0.999) : 0.f;
-}
-
 extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float time, int close, uint32_t *d_dest)
 {
 	CKD_REQUIRE(ctx && p && d_dest, "null argument");
@@ -955,12 +922,12 @@ extern "C" int ckd_spikey_draw(ckd_ctx *ctx, const ckd_spikey_params *p, float t
 		f.xOffs = p->dist_x;
 		f.yOffs = p->dist_y;
 		f.zTerm = -2.614f + p->dist_z;
-		// origin (0, 0, zTerm), taps at +pi*0.02 (shadertoy.cpp:546-575): the FAST kernel guards each evaluation with totalSafe
-		f.totalSafe = SpikeyTotalSafe(f, fabs(double(f.zTerm)), 3.14159266*0.02);
-		LutRangeProof guarded;
-		guarded.add(f.totalSafe > 0.f ? 0.0 : 1e30);
+		// 48 steps of 0.314*(|p| - radius): rays that miss the ball run away geometrically (x 1.314 per step) and do reach angles
+		// past the fast lookup's range -- the reference's aliased lookups out there are part of the picture -- so this variant
+		// always runs the exact kernel.  (A per-evaluation guard on the march total that switches lookups inside the FAST
+		// kernel was measured: 186.6 us against 175.7 us at 4K, profiles/r02_notes.md.)
 		SpikeyDistantEffect fx = { f };
-		return RaymarchAndBlit(ctx, fx, "raymarch_spikey_distant", &guarded, d_dest);
+		return RaymarchAndBlit(ctx, fx, "raymarch_spikey_distant", nullptr, d_dest);
 	}
 
 	// RenderSpikeyMap_2x2_Distant_SpecularOnly(…, 1.f+warmup), shadertoy.cpp:600-608, 727-729
