@@ -103,7 +103,7 @@ LIMITER = {
     "raymarch": "instruction issue: FMUL/FADD chains without FMA contraction (bit parity) + the non-FP instructions of every LUT lookup",
     "old_blur": "integer ALU pipe + the dependent chain of the saturating in-place recurrence; DRAM traffic = algorithmic bytes",
     "voxel": "L2 gather latency of the height/colour map samples (warp per ray)",
-    "polar_blit": "dependent map -> texel gather chain; DRAM traffic = algorithmic bytes",
+    "polar_blit": "L1TEX: 16 four-byte texel gathers per thread fill the LSU queue (l1tex 75 %, lg/mio throttle; profiles/r02_notes.md); DRAM traffic = algorithmic bytes",
     "fx_blit_2x2": "L2 write-back of the 33 MB frame",
     "blend": "HBM / L2 bandwidth",
     "rect_blit": "HBM / L2 bandwidth (small rectangles: launch latency)",
@@ -355,7 +355,8 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
 
     frame_bytes = RES_X * RES_Y * 4
     times = sharding.timeline_times(frames)
-    slots = 8
+    skip = sharding.default_collector_skip(world)      # the library's default (hostapi passes it on when collector_skip is None)
+    slots = min(64, max(8, 4 * world))   # every producer may run four frames ahead of the collector (33 MB per 4K slot in rank 0's HBM)
 
     # the ring lives on rank 0; its CUDA IPC handle travels once, over the control plane (torch.distributed)
     if rank == 0:
@@ -377,7 +378,7 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
 
     seq = 0
     # warm-up pass (also the first list of checksums)
-    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=1, pop_mode=capi.GATHER_CHECKSUM, seq_base=seq)
+    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=1, pop_mode=capi.GATHER_CHECKSUM, seq_base=seq, collector_skip=skip)
     ctx.sync()
     gather.status()
     warm_sums = gather.checksums(seq, frames) if rank == 0 else None
@@ -387,7 +388,7 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=passes, pop_mode=capi.GATHER_CHECKSUM, seq_base=seq)
+    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=passes, pop_mode=capi.GATHER_CHECKSUM, seq_base=seq, collector_skip=skip)
     ev1.record()                        # CkdTimeline_Render ends with ckd_gather_flush: the stream waits for every push and pop
     torch.cuda.synchronize()
     gather.status()
@@ -403,7 +404,7 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
     barrier()
     t0 = time.perf_counter()
     host.timeline_render(times, rank=rank, world=world, gather=gather, passes=1, pop_mode=capi.GATHER_CHECKSUM | capi.GATHER_TO_HOST,
-                         host_ring=ring, seq_base=seq)
+                         host_ring=ring, seq_base=seq, collector_skip=skip)
     ctx.sync()
     e2e_s = reduce_max(dist, time.perf_counter() - t0)
     gather.status()
@@ -427,11 +428,13 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
         rec = {
             "config": {"workload": "timeline-4k", "frames": frames, "res": [RES_X, RES_Y], "api": "Demo_Draw via CkdTimeline_Render (include/ckd_host.h)"},
             "scaling": "strong", "n_gpus": world, "passes": passes,
-            "sharding": "frame i -> rank i mod N; every frame pushed to a slot ring in rank 0's HBM (ckd_gather_*: CUDA IPC mapping, copy-engine peer copies over NVLink, device-side ready/drained flags), checksummed there in order; no NCCL on the data path",
+            "sharding": ("frame i -> rank i mod N" if skip <= 1 else f"weighted round-robin (CkdTimeline_Owner, collector_skip = {skip}): rank 0, which collects and checksums every frame, renders 1 frame per {skip} rounds of the other ranks ({len(sharding.frames_for_rank(frames, 0, world, skip))} of {frames} frames)")
+                        + "; every frame pushed to a slot ring in rank 0's HBM (ckd_gather_*: CUDA IPC mapping, copy-engine peer copies over NVLink, device-side ready/drained flags), checksummed there in order; no NCCL on the data path",
+            "collector_skip": skip,
             "gathered_to_rank0_fps": fps, "value": px * passes / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_pass": ms / passes,
             "no_gather_fps": frames / (nogather_ms * 1e-3),
             "nvlink_bytes_per_frame": peer_bytes_timed / (frames * passes), "nvlink_gbs": peer_bytes_timed / (ms * 1e-3) / 1e9,
-            "nvlink_note": "frames rendered on rank 0 are copied inside its own HBM; the others cross NVLink once (rank 0 ingest limit: 900 GB/s nominal = 27 100 4K frames/s)",
+            "nvlink_note": "frames rendered on rank 0 are copied inside its own HBM; the others cross NVLink once; rank 0 ingests at most what one GPU's NVLink takes: 770 GB/s measured peer copy (900 nominal) = 23 200 4K frames/s over the wire",
             "e2e": {"fps": frames / e2e_s, "value": px / e2e_s / 1e6, "unit": "Mpixel/s", "d2h_bytes_per_pass": frames * frame_bytes, "h2d_bytes_per_pass": 0,
                     "note": "every gathered frame copied to a pinned host ring on rank 0 inside the timed region; one PCIe link (rank 0's) carries all frames: that link is the ceiling at every N"},
             "gpu_launches": int(launches), "ring_slots": slots,

@@ -506,12 +506,17 @@ __device__ __forceinline__ uint32_t polar_blend(uint32_t d, uint32_t s)
 	return lerp8x2(d & 0x00ff00ffu, s & 0x00ff00ffu, a) | (lerp8x2((d >> 8) & 0x00ff00ffu, (s >> 8) & 0x00ff00ffu, a) << 8);
 }
 
-template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel(uint32_t *pDest, const uint32_t *__restrict__ pSrc, const int4 *__restrict__ pMap, unsigned numQuads, unsigned resX)
+// HALO: SoftLight32A(pDest, pHalo) (util.cpp:274-346) applied to the remapped pixel before it is stored -- the ball's halo layer
+// (ball.cpp:357-361) in the same pass instead of a second read-modify-write of the frame
+template <bool ALPHA, bool HALO> __global__ void __launch_bounds__(256) polar_blit_kernel(uint32_t *pDest, const uint32_t *__restrict__ pSrc, const int4 *__restrict__ pMap, unsigned numQuads, unsigned resX,
+	const uint4 *__restrict__ pHalo)
 {
 	const unsigned q = blockIdx.x*blockDim.x + threadIdx.x;
 	if (q >= numQuads)
 		return;
 	const int4 m0 = __ldg(pMap + size_t(q)*2), m1 = __ldg(pMap + size_t(q)*2 + 1);
+	uint4 halo = make_uint4(0, 0, 0, 0);
+	if (HALO) halo = __ldg(pHalo + q);
 	uint4 out;
 	out.x = polar_fetch(pSrc, m0.x, m0.y, resX);
 	out.y = polar_fetch(pSrc, m0.z, m0.w, resX);
@@ -524,6 +529,14 @@ template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel(u
 		out.y = polar_blend(d.y, out.y);
 		out.z = polar_blend(d.z, out.z);
 		out.w = polar_blend(d.w, out.w);
+	}
+	if (HALO)
+	{
+		const BlendParams none = { 0u, 0u };
+		out.x = blend_px<CKD_SOFTLIGHT32A>(out.x, halo.x, none);
+		out.y = blend_px<CKD_SOFTLIGHT32A>(out.y, halo.y, none);
+		out.z = blend_px<CKD_SOFTLIGHT32A>(out.z, halo.z, none);
+		out.w = blend_px<CKD_SOFTLIGHT32A>(out.w, halo.w, none);
 	}
 	reinterpret_cast<uint4 *>(pDest)[q] = out;
 }
@@ -540,48 +553,6 @@ template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel_1
 	if (ALPHA)
 		out = polar_blend(pDest[i], out);
 	pDest[i] = out;
-}
-
-// persistent variant: a grid that fits the machine once walks the quads with a grid stride and requests the map entries (and
-// the destination pixels) of its NEXT quad before it gathers the texels of the current one, so the two dependent round trips
-// of a quad (map, then texels) of consecutive iterations overlap
-template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel_pf(uint32_t *pDest, const uint32_t *__restrict__ pSrc, const int4 *__restrict__ pMap, unsigned numQuads, unsigned resX)
-{
-	const unsigned stride = gridDim.x*blockDim.x;
-	unsigned q = blockIdx.x*blockDim.x + threadIdx.x;
-	if (q >= numQuads)
-		return;
-	int4 m0 = __ldg(pMap + size_t(q)*2), m1 = __ldg(pMap + size_t(q)*2 + 1);
-	uint4 d = make_uint4(0, 0, 0, 0);
-	if (ALPHA) d = reinterpret_cast<const uint4 *>(pDest)[q];
-	for (;;)
-	{
-		const unsigned qn = q + stride;
-		const bool more = qn < numQuads;
-		int4 n0 = m0, n1 = m1;
-		uint4 dn = d;
-		if (more)
-		{
-			n0 = __ldg(pMap + size_t(qn)*2); n1 = __ldg(pMap + size_t(qn)*2 + 1);
-			if (ALPHA) dn = reinterpret_cast<const uint4 *>(pDest)[qn];
-		}
-		uint4 out;
-		out.x = polar_fetch(pSrc, m0.x, m0.y, resX);
-		out.y = polar_fetch(pSrc, m0.z, m0.w, resX);
-		out.z = polar_fetch(pSrc, m1.x, m1.y, resX);
-		out.w = polar_fetch(pSrc, m1.z, m1.w, resX);
-		if (ALPHA)
-		{
-			out.x = polar_blend(d.x, out.x);
-			out.y = polar_blend(d.y, out.y);
-			out.z = polar_blend(d.z, out.z);
-			out.w = polar_blend(d.w, out.w);
-		}
-		reinterpret_cast<uint4 *>(pDest)[q] = out;
-		if (!more)
-			break;
-		q = qn; m0 = n0; m1 = n1; d = dn;
-	}
 }
 
 static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse, bool alpha)
@@ -603,19 +574,10 @@ static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, in
 		else
 			polar_blit_kernel_1px<false><<<ckd_div_up(numPixels, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap2, numPixels, unsigned(ctx->resX));
 	}
-	else if (variant >= 2)
-	{
-		const unsigned perSM = unsigned(variant >= 4 ? variant : 6); // CTAs of 256 threads per SM
-		const unsigned grid = std::min<unsigned>(blocks, unsigned(ctx->numSMs)*perSM);
-		if (alpha)
-			polar_blit_kernel_pf<true><<<grid, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
-		else
-			polar_blit_kernel_pf<false><<<grid, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
-	}
 	else if (alpha)
-		polar_blit_kernel<true><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
+		polar_blit_kernel<true, false><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX), nullptr);
 	else
-		polar_blit_kernel<false><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX));
+		polar_blit_kernel<false, false><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX), nullptr);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
 }
@@ -628,13 +590,24 @@ int ckd_polar_tail(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int in
 	void *h_dest = ctx->rbHost;
 	ctx->rbHost = nullptr;
 	const unsigned numPixels = unsigned(ctx->resX)*unsigned(ctx->resY);
+	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap : ctx->d_polarMap);
+	// the halo rides in the remap kernel when the shapes allow it (alpha remap, 16-byte aligned layers)
+	const bool fuseHalo = nullptr != d_softLightSrc && alpha && 0 == (ctx->resX & 3) && 0 == ((reinterpret_cast<uintptr_t>(d_softLightSrc) | reinterpret_cast<uintptr_t>(d_dest)) & 15);
 	if (nullptr == h_dest || 0 != (ctx->resX & 3))
 	{
+		if (fuseHalo)
+		{
+			CKD_REQUIRE(d_dest != d_src, "polar blit cannot run in place");
+			const unsigned numQuads = numPixels/4;
+			ckd_prof_begin(ctx, "polar_blit_a_halo", 24.0*numPixels);
+			polar_blit_kernel<true, true><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX), reinterpret_cast<const uint4 *>(d_softLightSrc));
+			CKD_CHECK_LAUNCH(ctx);
+			return CKD_OK;
+		}
 		CKD_TRY(LaunchPolar(ctx, d_dest, d_src, inverse, alpha));
 		return d_softLightSrc ? ckd_blend(ctx, CKD_SOFTLIGHT32A, d_dest, d_softLightSrc, numPixels, 0.f, 0) : CKD_OK;
 	}
 	CKD_REQUIRE(d_dest != d_src, "polar blit cannot run in place");
-	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap : ctx->d_polarMap);
 	const int bands = ctx->rbBands;
 	for (int k = 0; k < bands; ++k)
 	{
@@ -643,13 +616,15 @@ int ckd_polar_tail(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int in
 			continue;
 		const size_t offset = size_t(y0)*ctx->resX, count = size_t(y1 - y0)*ctx->resX;
 		const unsigned numQuads = unsigned(count/4);
-		ckd_prof_begin(ctx, alpha ? "polar_blit_a" : "polar_blit", (alpha ? 20.0 : 16.0)*double(count));
-		if (alpha)
-			polar_blit_kernel<true><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX));
+		ckd_prof_begin(ctx, fuseHalo ? "polar_blit_a_halo" : alpha ? "polar_blit_a" : "polar_blit", (fuseHalo ? 24.0 : alpha ? 20.0 : 16.0)*double(count));
+		if (fuseHalo)
+			polar_blit_kernel<true, true><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX), reinterpret_cast<const uint4 *>(d_softLightSrc + offset));
+		else if (alpha)
+			polar_blit_kernel<true, false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX), nullptr);
 		else
-			polar_blit_kernel<false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX));
+			polar_blit_kernel<false, false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX), nullptr);
 		CKD_CHECK_LAUNCH(ctx);
-		if (d_softLightSrc)
+		if (d_softLightSrc && !fuseHalo)
 			CKD_TRY(ckd_blend(ctx, CKD_SOFTLIGHT32A, d_dest + offset, d_softLightSrc + offset, unsigned(count), 0.f, 0));
 		CKD_CUDA(cudaEventRecord(ctx->evBand[k], ctx->stream));
 		CKD_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evBand[k], 0));
@@ -672,7 +647,7 @@ extern "C" int ckd_polar_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t
 	const unsigned numQuads = unsigned(size_t(ctx->fxX)*ctx->fxY/4); // fxResX is a multiple of 4 (fx-blitter.h:18)
 	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap2x2 : ctx->d_polarMap2x2);
 	ckd_prof_begin(ctx, "polar_blit_2x2", 16.0*ctx->fxX*ctx->fxY);
-	polar_blit_kernel<false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->fxX));
+	polar_blit_kernel<false, false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->fxX), nullptr);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
 }

@@ -524,6 +524,8 @@ struct TileQueue { unsigned *counter; unsigned *nextCounter; int tilesX; unsigne
 
 __device__ __forceinline__ bool next_tile(const TileQueue &q, unsigned &iX, unsigned &iY)
 {
+	// (requesting the next tile's number one tile ahead, so that the atomic's round trip overlaps the shading, was measured
+	//  and made every kernel 2-6 % slower -- profiles/r02_notes.md)
 	const unsigned lane = threadIdx.x;
 	unsigned tile = 0;
 	if (lane == 0)
@@ -682,8 +684,9 @@ TileQueue MakeQueue(ckd_ctx *ctx, const FrameGeom &geom, int row0 = 0, int row1 
 // scaled angle < 2^23, i.e. |angle| < 25735.9 rad).  It exists for the four effects whose distance function is BOUNDED --
 // a sum of table values, each within [-1, 1] -- so the march total, hence every sample position, is bounded by the step
 // count alone; what remains are the frame's own parameters (time offsets, origins), which 'add' folds in.  The spikey
-// variants march |p| - radius, which grows geometrically on rays that miss (their background pixels do reach such
-// angles, and the reference's aliased lookups there are part of the picture): they always run the exact kernel.
+// variants march |p| - radius, which grows geometrically: the close and the specular-only variant stay in range within their
+// step budgets (SpikeyFixedProof); on the distant one rays that miss do reach such angles (and the reference's aliased
+// lookups there are part of the picture), so it always runs the exact kernel.
 // The induction behind the bound: while every angle so far was in range, every table value so far is within [-1, 1] (a
 // lerp between two entries), so the next position obeys the bound, so the next angle is in range.  NaN/inf parameters fail
 // the comparison and select the exact kernel.

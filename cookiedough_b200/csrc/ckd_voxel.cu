@@ -130,7 +130,10 @@ __device__ __forceinline__ uint32_t span_pixel(const SpanRamp &r, unsigned j)
 	return px;
 }
 
-constexpr unsigned kShortSpan = 6; // spans up to this length are drawn by their own lane, longer ones by the whole warp
+// spans up to this length are drawn by their own lane, longer ones by the whole warp (tuned on B200, profiles/r02_notes.md;
+// CKD_SHORT_SPAN overrides it for sweeps)
+__constant__ unsigned c_shortSpan = 24;
+#define kShortSpan c_shortSpan
 
 // Emits the spans of one 32-step chunk into a line buffer.  Lane parameters: visible, pos (index of the span's first
 // pixel in the line), dir (+1/-1 index increment), length/drawLength and the two colours; 'limit' clips writes to the line.
@@ -468,22 +471,37 @@ __global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest,
 	Color16 carryLastColor = unpack16(sample_argb(colorMap, prep_uvs(f.fromX, f.fromY, 1023u, 10u)));
 	int beamCarry[4] = { 0, 0, 0, 0 };
 
+	// the height / colour (/ beam) texels of a chunk do not depend on the carry: those of the NEXT chunk are requested before this
+	// chunk's scan and span stores (see tunnelscape_kernel).  Steps past the ray's end sample wrapped coordinates that nothing uses.
+	struct BallRaw { int h[4]; uint32_t c[4]; uint32_t b[4]; uint32_t fu, fv; };
+	auto fetchRaw = [&](unsigned iStep) -> BallRaw
+	{
+		const TexCoords t = prep_uvs(int(unsigned(f.fromX) - (iStep+1)*unsigned(dX)), int(unsigned(f.fromY) - (iStep+1)*unsigned(dY)), 1023u, 10u);
+		BallRaw r;
+		r.h[0] = __ldg(heightMap + t.i00); r.h[1] = __ldg(heightMap + t.i10); r.h[2] = __ldg(heightMap + t.i01); r.h[3] = __ldg(heightMap + t.i11);
+		r.c[0] = __ldg(colorMap + t.i00); r.c[1] = __ldg(colorMap + t.i10); r.c[2] = __ldg(colorMap + t.i01); r.c[3] = __ldg(colorMap + t.i11);
+		if (BEAMS) { r.b[0] = __ldg(auxMap + t.i00); r.b[1] = __ldg(auxMap + t.i10); r.b[2] = __ldg(auxMap + t.i01); r.b[3] = __ldg(auxMap + t.i11); }
+		r.fu = t.fu; r.fv = t.fv;
+		return r;
+	};
+	BallRaw next = fetchRaw(lane);
+
 	for (unsigned base = 0; base < f.rayLength; base += 32)
 	{
 		const unsigned iStep = base + lane;
 		const bool active = iStep < f.rayLength;
 		const unsigned tabIdx = active ? iStep : 0;
 
-		const int curX = int(unsigned(f.fromX) - (iStep+1)*unsigned(dX));
-		const int curY = int(unsigned(f.fromY) - (iStep+1)*unsigned(dY));
-		const TexCoords t = prep_uvs(curX, curY, 1023u, 10u);
-		const unsigned mapHeight = sample_u8(heightMap, t);
-		Color16 color = unpack16(sample_argb(colorMap, t));
+		const BallRaw raw = next;
+		if (base + 32 < f.rayLength)
+			next = fetchRaw(iStep + 32);
+		const unsigned mapHeight = bilerp_u8(raw.h[0], raw.h[1], raw.h[2], raw.h[3], int(raw.fu), int(raw.fv));
+		Color16 color = unpack16(bilerp_argb(raw.c[0], raw.c[1], raw.c[2], raw.c[3], raw.fu, raw.fv));
 
 		if (BEAMS)
 		{
 			// vball_ray_beams, ball.cpp:113-140
-			Color16 beam = unpack16(sample_argb(auxMap, t));
+			Color16 beam = unpack16(bilerp_argb(raw.b[0], raw.b[1], raw.b[2], raw.b[3], raw.fu, raw.fv));
 			const unsigned heightNorm = (mapHeight*unsigned(__ldg(projNorm0 + tabIdx))) >> 8;
 			const unsigned heightNorm2 = (mapHeight*unsigned(__ldg(projNorm1 + tabIdx))) >> 8;
 			const unsigned diffuse = heightNorm + ((unsigned(int(heightNorm2-heightNorm))*f.lowLight) >> 8);
@@ -692,8 +710,24 @@ template <class K> int EnsureSmem(K kernel, size_t bytes)
 } // namespace
 
 // Landscape_Draw, landscape.cpp:228-243
+// CKD_SHORT_SPAN=n: tuning override of the lane-parallel / cooperative span threshold (once per process)
+static int ApplyShortSpanOverride()
+{
+	static bool done = false;
+	if (done)
+		return CKD_OK;
+	done = true;
+	if (const char *env = getenv("CKD_SHORT_SPAN"))
+	{
+		const unsigned v = unsigned(atoi(env));
+		CKD_CUDA(cudaMemcpyToSymbol(c_shortSpan, &v, sizeof(v)));
+	}
+	return CKD_OK;
+}
+
 extern "C" int ckd_landscape_draw(ckd_ctx *ctx, const ckd_landscape_params *p, float time, uint32_t *d_dest)
 {
+	CKD_TRY(ApplyShortSpanOverride());
 	(void)time;
 	CKD_REQUIRE(ctx && p && d_dest, "null argument");
 	CKD_TRY(RequireImage(ctx, CKD_IMG_SCAPE_HEIGHT, 1024, 1024, 1, "landscape height map (assets/scape/D17.png)"));
@@ -744,6 +778,7 @@ extern "C" int ckd_landscape_draw(ckd_ctx *ctx, const ckd_landscape_params *p, f
 // Tunnelscape_Draw, tunnelscape.cpp:168-186
 extern "C" int ckd_tunnelscape_draw(ckd_ctx *ctx, const ckd_tunnelscape_params *p, float time, uint32_t *d_dest)
 {
+	CKD_TRY(ApplyShortSpanOverride());
 	CKD_REQUIRE(ctx && p && d_dest, "null argument");
 	CKD_TRY(RequireImage(ctx, CKD_IMG_TSCAPE_HEIGHT, 2048, 2048, 1, "tunnelscape height map (assets/scape/tscape-D7-edit.png)"));
 	CKD_TRY(RequireImage(ctx, CKD_IMG_TSCAPE_COLOR, 2048, 2048, 4, "tunnelscape colour map (assets/scape/tscape-C7W-edit.png)"));
@@ -789,6 +824,7 @@ extern "C" int ckd_tunnelscape_draw(ckd_ctx *ctx, const ckd_tunnelscape_params *
 // Ball_Draw, ball.cpp:452-514
 extern "C" int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time, uint32_t *d_dest)
 {
+	CKD_TRY(ApplyShortSpanOverride());
 	CKD_REQUIRE(ctx && p && d_dest, "null argument");
 	for (int i = 0; i < 5; ++i)
 		CKD_TRY(RequireImage(ctx, ckd_image(CKD_IMG_BALL_HEIGHT0 + i), 1024, 1024, 1, "ball height map"));
@@ -909,6 +945,7 @@ extern "C" int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time,
 // Twister_Draw, torus-twister.cpp:166-188
 extern "C" int ckd_twister_draw(ckd_ctx *ctx, const ckd_twister_params *p, float time, uint32_t *d_dest)
 {
+	CKD_TRY(ApplyShortSpanOverride());
 	CKD_REQUIRE(ctx && p && d_dest, "null argument");
 	CKD_TRY(RequireImage(ctx, CKD_IMG_TWISTER_HEIGHT, 1024, 1024, 1, "twister height map"));
 	CKD_TRY(RequireImage(ctx, CKD_IMG_TWISTER_COLOR, 1024, 1024, 4, "twister colour map"));

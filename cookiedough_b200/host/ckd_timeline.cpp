@@ -22,6 +22,19 @@ bool Ok(int rc, const char *what) { return ckdhost::Check(rc, what); }
 
 } // namespace
 
+unsigned CkdTimeline_Owner(unsigned frame, unsigned world, unsigned collectorSkip)
+{
+	if (world <= 1)
+		return 0;
+	if (collectorSkip <= 1)
+		return frame % world;
+	const unsigned cycle = collectorSkip*(world - 1) + 1;
+	const unsigned c = frame % cycle;
+	return (0 == c) ? 0 : 1 + (c - 1) % (world - 1);
+}
+
+unsigned CkdTimeline_DefaultCollectorSkip(unsigned world) { return (world >= 4) ? 2 : 1; }
+
 bool CkdTimeline_Render(const CkdTimelineJob *job)
 {
 	ckd_ctx *ctx = CkdHost_Context();
@@ -71,7 +84,7 @@ bool CkdTimeline_Render(const CkdTimelineJob *job)
 		for (unsigned i = 0; ok && i < job->numFrames; ++i)
 		{
 			const unsigned long long seq = job->seqBase + (unsigned long long)(pass)*job->numFrames + i;
-			if (i % job->world == job->rank)
+			if (CkdTimeline_Owner(i, job->world, job->collectorSkip) == job->rank)
 			{
 				uint32_t *d_frame = nullptr;
 				if (nullptr != gather)
@@ -129,10 +142,12 @@ extern "C" {
 
 // ctypes hook: the job as plain arguments
 int ckdhost_timeline_render(const double *times, unsigned numFrames, unsigned passes, unsigned rank, unsigned world, void *gather, int popMode,
-	uint32_t *const *hostRing, unsigned hostRingFrames, unsigned long long seqBase, float delta)
+	uint32_t *const *hostRing, unsigned hostRingFrames, unsigned long long seqBase, float delta, unsigned collectorSkip)
 {
-	CkdTimelineJob job = { times, numFrames, passes, rank, world, static_cast<ckd_gather *>(gather), popMode, hostRing, hostRingFrames, seqBase, delta };
+	CkdTimelineJob job = { times, numFrames, passes, rank, world, static_cast<ckd_gather *>(gather), popMode, hostRing, hostRingFrames, seqBase, delta, collectorSkip };
 	return CkdTimeline_Render(&job) ? 0 : -1;
 }
+unsigned ckdhost_timeline_owner(unsigned frame, unsigned world, unsigned collectorSkip) { return CkdTimeline_Owner(frame, world, collectorSkip); }
+unsigned ckdhost_timeline_default_skip(unsigned world) { return CkdTimeline_DefaultCollectorSkip(world); }
 
 } // extern "C"

@@ -1,7 +1,8 @@
 """Frame-parallel sharding of a timeline across the GPUs of one box.
 
 Every X_Draw is a pure function of (time, Rocket row, assets), so a timeline shards by frame index with no data-path
-collective: frame i goes to rank i mod N.  The only communication is bookkeeping (barrier, max-over-ranks time, gathering
+collective: frame i goes to rank i mod N (or, when rank 0 also collects the frames, to a weighted round-robin that gives rank 0
+fewer turns: frame_owner).  The only communication is bookkeeping (barrier, max-over-ranks time, gathering
 per-frame checksums to rank 0) and runs over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
 import zlib
 
@@ -22,11 +23,28 @@ def timeline_times(num_frames=600):
     return [i * total / num_frames for i in range(num_frames)]
 
 
-def frames_for_rank(num_frames, rank, world_size):
-    """frame i -> rank i mod N"""
+def frame_owner(frame, world_size, collector_skip=1):
+    """which rank renders frame i (the rule of CkdTimeline_Owner, host/ckd_timeline.cpp): i mod N, or, with collector_skip = k > 1,
+    cycles of k*(N-1) + 1 frames whose first frame goes to rank 0 -- the rank that also collects every frame -- and whose other
+    frames go round-robin over the ranks 1..N-1"""
+    if world_size <= 1:
+        return 0
+    if collector_skip <= 1:
+        return frame % world_size
+    c = frame % (collector_skip * (world_size - 1) + 1)
+    return 0 if c == 0 else 1 + (c - 1) % (world_size - 1)
+
+
+def default_collector_skip(world_size):
+    """CkdTimeline_DefaultCollectorSkip: rank 0 renders a full share up to 3 GPUs, one frame per two rounds from 4 GPUs on"""
+    return 2 if world_size >= 4 else 1
+
+
+def frames_for_rank(num_frames, rank, world_size, collector_skip=1):
+    """the frames rank `rank` renders (frame i -> rank i mod N by default)"""
     if not (0 <= rank < world_size):
         raise ValueError("rank out of range")
-    return list(range(rank, num_frames, world_size))
+    return [i for i in range(num_frames) if frame_owner(i, world_size, collector_skip) == rank]
 
 
 def frame_checksum(frame):

@@ -86,8 +86,17 @@ struct CkdTimelineJob
 	unsigned hostRingFrames;        //   deliver into the open frame sink (CkdSink_Acquire / CkdSink_Commit by frame index)
 	unsigned long long seqBase;
 	float delta;                    // Demo_Draw's delta argument
+	unsigned collectorSkip;         // 0 or 1: frame i -> rank i % world.  k > 1: rank 0, which also collects (and checksums / copies
+	                                //   out) every frame of every rank, renders only one frame per k rounds of the other ranks:
+	                                //   CkdTimeline_Owner(i, world, k).  Every rank must pass the same value.
 };
 bool CkdTimeline_Render(const CkdTimelineJob *job);
+// which rank renders frame i: cycles of k*(world-1) + 1 frames, the first of a cycle goes to rank 0, the others round-robin over
+// the ranks 1..world-1 (k <= 1 or world == 1: i % world)
+unsigned CkdTimeline_Owner(unsigned frame, unsigned world, unsigned collectorSkip);
+// the default for a box: 1 up to 3 GPUs, 2 from 4 GPUs on (measured on B200: at 8 GPUs the collector's own share of the
+// rendering plus the per-frame checksum of all eight streams made it the slowest rank)
+unsigned CkdTimeline_DefaultCollectorSkip(unsigned world);
 
 // ---- frame sink (replaces Display::Update, display.cpp:66-82, for headless rendering): a raw stream file
 //      ("CKDF" header + numFrames ARGB8888 frames) fed through a ring of host buffers by a writer thread.  Acquire a buffer,

@@ -66,3 +66,27 @@ def test_timeline_times_match_config5():
     assert len(t) == 600 and t[0] == 0.0
     assert abs(t[1] - 0.369828) < 1e-6   # t_i = i * 0.369828 s
     assert t[-1] < 10296 / sharding.ROW_RATE
+
+
+def test_weighted_sharding_matches_the_library_and_covers_every_frame():
+    """frame_owner (python) == CkdTimeline_Owner (C++), every frame has exactly one owner, and with collector_skip = k rank 0
+    renders one frame per k rounds of the others"""
+    from cookiedough_b200 import hostapi
+    L = hostapi._lib() if hasattr(hostapi, "_lib") else None
+    for world in (1, 2, 3, 4, 8):
+        for skip in (0, 1, 2, 3):
+            owners = [sharding.frame_owner(i, world, skip) for i in range(600)]
+            assert all(0 <= o < world for o in owners)
+            if L is not None:
+                assert owners == [L.ckdhost_timeline_owner(i, world, skip) for i in range(600)]
+            per_rank = [sharding.frames_for_rank(600, r, world, skip) for r in range(world)]
+            assert sorted(i for fr in per_rank for i in fr) == list(range(600))
+            if world > 1 and skip > 1:
+                cycle = skip * (world - 1) + 1
+                assert abs(len(per_rank[0]) - 600 / cycle) <= 1
+                assert all(abs(len(fr) - 600 * skip / cycle) <= skip for fr in per_rank[1:])
+            elif world > 1:
+                assert owners == [i % world for i in range(600)]
+    assert sharding.default_collector_skip(2) == 1 and sharding.default_collector_skip(8) == 2
+    if L is not None:
+        assert [L.ckdhost_timeline_default_skip(w) for w in (1, 2, 3, 4, 8)] == [sharding.default_collector_skip(w) for w in (1, 2, 3, 4, 8)]

@@ -37,7 +37,9 @@ def bench_name(kernel):
     if "ball_kernel" in kernel:
         return "voxel_ball_beams" if re.search(r"ball_kernel<\(bool\)1>|ball_kernel<true>|ball_kernel<1>", kernel) else "voxel_ball"
     if "polar_blit" in kernel:
-        return "polar_blit_a" if re.search(r"<\(bool\)1>|<true>|<1>", kernel) else "polar_blit"
+        if re.search(r"<\(bool\)1, \(bool\)1>|<true, true>|<1, 1>", kernel):
+            return "polar_blit_a_halo"
+        return "polar_blit_a" if re.search(r"<\(bool\)1[,>]|<true[,>]|<1[,>]", kernel) else "polar_blit"
     if "old_blur" in kernel:
         vert = re.search(r"old_blur_\w+_kernel<\(bool\)(\d)|old_blur_\w+_kernel<(\d)", kernel)
         flag = (vert.group(1) or vert.group(2)) if vert else "0"
@@ -71,7 +73,12 @@ def launches(path):
 
 
 def full(rep, summary_path, traffic_path):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    # `rep` is the capture itself or its raw page exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x_raw.csv`: the
+    # reports embed the whole module and do not fit gpurun_out/ once there are several)
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--frames", type=int, default=600)
     ap.add_argument("--res", type=int, default=2160)
     ap.add_argument("--ring", type=int, default=6)
-    ap.add_argument("--slots", type=int, default=8, help="frames of the gather's slot ring in rank 0's HBM")
+    ap.add_argument("--slots", type=int, default=0, help="frames of the gather's slot ring in rank 0's HBM (0: 4 per rank, at least 8)")
     args = ap.parse_args()
 
     import torch
@@ -41,7 +41,7 @@ def main():
 
     # the ring lives on rank 0; its handle travels once over the control plane
     if rank == 0:
-        gather = capi.Gather(ctx, slots=args.slots)
+        gather = capi.Gather(ctx, slots=args.slots or min(64, max(8, 4 * world)))
         handle = gather.export()
     else:
         gather, handle = None, bytes(capi.GATHER_HANDLE_BYTES)
