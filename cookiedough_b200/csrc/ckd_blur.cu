@@ -158,7 +158,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 
 template <bool B> struct BoolTag { static constexpr bool value = B; };
 
-// KM: the kernel median when it is < 8 and the blur runs in place (trailing edge from registers); 0: any width (from the ring)
+// KM: the kernel median when it is <= 8 and the blur runs in place (trailing edge from registers); 0: any width (from the ring)
 template <bool VERT, bool INPLACE, bool SUBEDGES, int KM>
 __global__ void __launch_bounds__(kBlurWarps*32) old_blur_staged_kernel(uint8_t *pDest, const uint8_t *pSrc, unsigned numLines, unsigned len, unsigned pitch, OldBlurSetup s)
 {
@@ -820,7 +820,7 @@ static cudaError_t LaunchStaged(ckd_ctx *ctx, uint8_t *pDest, const uint8_t *pSr
 {
 	const unsigned blocks = ckd_div_up(numLines, 8*kBlurWarps);
 	const size_t smem = size_t(kBlurWarps)*2*kRingBytes;
-	bool &attrSet = ctx->blurAttrSet[(((VERT ? 1 : 0)*2 + (INPLACE ? 1 : 0))*2 + (SUBEDGES ? 1 : 0))*8 + KM];
+	bool &attrSet = ctx->blurAttrSet[(((VERT ? 1 : 0)*2 + (INPLACE ? 1 : 0))*2 + (SUBEDGES ? 1 : 0))*9 + KM];
 	if (!attrSet)
 	{
 		const cudaError_t err = cudaFuncSetAttribute(old_blur_staged_kernel<VERT, INPLACE, SUBEDGES, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -844,6 +844,7 @@ static cudaError_t LaunchStagedInPlace(ckd_ctx *ctx, uint8_t *p, unsigned numLin
 	case 5: return LaunchStaged<VERT, true, SUBEDGES, 5>(ctx, p, p, numLines, len, pitch, s);
 	case 6: return LaunchStaged<VERT, true, SUBEDGES, 6>(ctx, p, p, numLines, len, pitch, s);
 	case 7: return LaunchStaged<VERT, true, SUBEDGES, 7>(ctx, p, p, numLines, len, pitch, s);
+	case 8: return LaunchStaged<VERT, true, SUBEDGES, 8>(ctx, p, p, numLines, len, pitch, s);
 	default: return LaunchStaged<VERT, true, SUBEDGES, 0>(ctx, p, p, numLines, len, pitch, s);
 	}
 }
@@ -882,7 +883,11 @@ static int OldBlurPass(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, un
 		const int variant = (vert ? 4 : 0) | (inPlace ? 2 : 0) | (s.subEdges ? 1 : 0);
 		// The serial walk runs one warp per 8 lines; once that alone puts three warps on every SM (vertical passes at 4K) it holds
 		// its own against the scan up to medium kernels.  Measured on B200, see profiles/r01_notes.md.
-		const unsigned blockedFrom = (numLines/8 >= 3u*unsigned(ctx->numSMs)) ? 24 : 8;
+		// medians up to 8 keep their trailing edge in registers (staged walk); an odd kernel of median 9 is still better off on the
+		// staged walk than on a two-part scan (profiles/r02_blur_dispatch_sweep.txt)
+		unsigned blockedFrom = (numLines/8 >= 3u*unsigned(ctx->numSMs)) ? 24 : (s.subEdges ? 9 : 10);
+		static const int forcedFrom = getenv("CKD_BLUR_BLOCKED_FROM") ? atoi(getenv("CKD_BLUR_BLOCKED_FROM")) : 0; // tuning sweeps
+		if (forcedFrom >= 9) blockedFrom = unsigned(forcedFrom);
 		if (inPlace && s.kernelMedian >= blockedFrom)
 		{
 			if (vert) err = s.subEdges ? LaunchBlocked<true, true>(ctx, pDest, numLines, lineLen, pitch, s) : LaunchBlocked<true, false>(ctx, pDest, numLines, lineLen, pitch, s);

@@ -38,7 +38,7 @@ struct ckd_ctx {
 	bool rbIssued = false;                          // band copies are on the copy stream
 	cudaEvent_t evBand[kMaxBands] = {};
 	bool newBlurAttrSet = false;                   // opt-in shared-memory size set for new_blur_line_kernel on this device
-	bool blurAttrSet[64] = {};                     // opt-in shared-memory size set for the staged blur variants on this device
+	bool blurAttrSet[72] = {};                     // opt-in shared-memory size set for the staged blur variants on this device
 	unsigned long long launches = 0;
 
 	// device twins of the reference's global buffers (all carved out of one allocation, with guard rows)
