@@ -132,7 +132,7 @@ __device__ __forceinline__ uint32_t span_pixel(const SpanRamp &r, unsigned j)
 
 // spans up to this length are drawn by their own lane, longer ones by the whole warp (tuned on B200, profiles/r02_notes.md;
 // CKD_SHORT_SPAN overrides it for sweeps)
-__constant__ unsigned c_shortSpan = 24;
+__constant__ unsigned c_shortSpan = 48;
 #define kShortSpan c_shortSpan
 
 // Emits the spans of one 32-step chunk into a line buffer.  Lane parameters: visible, pos (index of the span's first
@@ -144,17 +144,47 @@ __device__ __forceinline__ void emit_spans(uint32_t *line, int limit, bool visib
 	if (visible)
 		ramp = span_setup(length, drawLength, A, B);
 
+	// A ramp whose two end points -- evaluated without the 32-bit wrap-around -- lie within [0, 2^24) cannot wrap or leave that
+	// range in between (it is linear): every channel value is then byte 2 of its accumulator, the packusdw / packuswb clamps of
+	// span_pixel cannot act, and a pixel costs four additions (or multiply-adds) and three byte permutes.  Anything else (the
+	// ball's over-bright colours, the pmaddwd quirks of steep ramps) takes the literal path.
+	bool plain = visible;
+	if (visible)
+	{
+		#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			const long long last = (long long)(ramp.from[i]) + (long long)(drawLength - 1)*(long long)(ramp.step[i]);
+			plain = plain && ramp.from[i] < (1u << 24) && last >= 0 && last < (1ll << 24);
+		}
+	}
+
 	if (visible && drawLength <= kShortSpan)
 	{
-		for (unsigned j = 0; j < drawLength; ++j)
+		if (plain)
 		{
-			const int idx = pos + int(j)*dir;
-			if (idx >= 0 && idx < limit)
-				line[idx] = span_pixel(ramp, j);
+			uint32_t c0 = ramp.from[0], c1 = ramp.from[1], c2 = ramp.from[2], c3 = ramp.from[3];
+			int idx = pos;
+			for (unsigned j = 0; j < drawLength; ++j, idx += dir)
+			{
+				if (idx >= 0 && idx < limit)
+					line[idx] = __byte_perm(__byte_perm(c0, c1, 0x0062), __byte_perm(c2, c3, 0x0062), 0x5410);
+				c0 += uint32_t(ramp.step[0]); c1 += uint32_t(ramp.step[1]); c2 += uint32_t(ramp.step[2]); c3 += uint32_t(ramp.step[3]);
+			}
+		}
+		else
+		{
+			for (unsigned j = 0; j < drawLength; ++j)
+			{
+				const int idx = pos + int(j)*dir;
+				if (idx >= 0 && idx < limit)
+					line[idx] = span_pixel(ramp, j);
+			}
 		}
 	}
 
 	unsigned longMask = __ballot_sync(kFull, visible && drawLength > kShortSpan);
+	const unsigned plainMask = __ballot_sync(kFull, plain);
 	while (longMask)
 	{
 		const int src = __ffs(longMask) - 1;
@@ -168,11 +198,24 @@ __device__ __forceinline__ void emit_spans(uint32_t *line, int limit, bool visib
 		}
 		const int p = __shfl_sync(kFull, pos, src);
 		const unsigned len = __shfl_sync(kFull, drawLength, src);
-		for (unsigned j = lane; j < len; j += 32)
+		if ((plainMask >> src) & 1u)
 		{
-			const int idx = p + int(j)*dir;
-			if (idx >= 0 && idx < limit)
-				line[idx] = span_pixel(r, j);
+			for (unsigned j = lane; j < len; j += 32)
+			{
+				const int idx = p + int(j)*dir;
+				if (idx >= 0 && idx < limit)
+					line[idx] = __byte_perm(__byte_perm(r.from[0] + j*uint32_t(r.step[0]), r.from[1] + j*uint32_t(r.step[1]), 0x0062),
+						__byte_perm(r.from[2] + j*uint32_t(r.step[2]), r.from[3] + j*uint32_t(r.step[3]), 0x0062), 0x5410);
+			}
+		}
+		else
+		{
+			for (unsigned j = lane; j < len; j += 32)
+			{
+				const int idx = p + int(j)*dir;
+				if (idx >= 0 && idx < limit)
+					line[idx] = span_pixel(r, j);
+			}
 		}
 	}
 }
@@ -507,22 +550,28 @@ __global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest,
 			const unsigned diffuse = heightNorm + ((unsigned(int(heightNorm2-heightNorm))*f.lowLight) >> 8);
 			const int litWhite = int(diffuse & 0xffffu); // _mm_set1_epi16
 
-			int beamIncl[4];
+			// paddusw prefix: all terms are >= 0, so the saturating running sum is min(65535, exact prefix sum).  A term is at most
+			// 255, a warp's prefix at most 8160: two channels share one 32-bit word through the scan (16 bits each, no carry between)
+			int lit[4];
 			#pragma unroll
 			for (int i = 0; i < 4; ++i)
 			{
 				const int b = ((beam.c[i]*int(f.beamAtten)) & 0xffff) >> 8;
-				int lit = ((b*litWhite) & 0xffff) >> 8;
-				if (!active) lit = 0;
-				// paddusw prefix: all terms are >= 0, so the saturating running sum is min(65535, exact prefix sum)
-				int incl = lit;
-				#pragma unroll
-				for (int d = 1; d < 32; d <<= 1)
-				{
-					const int o = __shfl_up_sync(kFull, incl, d);
-					if (lane >= d) incl += o;
-				}
-				beamIncl[i] = min(beamCarry[i] + incl, 65535);
+				lit[i] = active ? (((b*litWhite) & 0xffff) >> 8) : 0;
+			}
+			unsigned incl01 = unsigned(lit[0]) | (unsigned(lit[1]) << 16), incl23 = unsigned(lit[2]) | (unsigned(lit[3]) << 16);
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const unsigned o01 = __shfl_up_sync(kFull, incl01, d), o23 = __shfl_up_sync(kFull, incl23, d);
+				if (lane >= d) { incl01 += o01; incl23 += o23; }
+			}
+			const int incl[4] = { int(incl01 & 0xffffu), int(incl01 >> 16), int(incl23 & 0xffffu), int(incl23 >> 16) };
+			int beamIncl[4];
+			#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				beamIncl[i] = min(beamCarry[i] + incl[i], 65535);
 				beamCarry[i] = __shfl_sync(kFull, beamIncl[i], 31);
 				color.c[i] = adds16(adds16(color.c[i], beamIncl[i]), litWhite);
 			}

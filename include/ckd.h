@@ -42,7 +42,8 @@ typedef enum ckd_status {
  * ckd_create makes `device` the calling thread's current CUDA device and the context lives there.  The other ckd_* calls do
  * not switch devices (they are launch-rate sensitive): a process drives ONE device -- the deployment model is one process
  * per GPU (bench.py, tools/render_demo.py) -- or the caller makes the context's device current (cudaSetDevice) before using
- * a context that lives on another one.  ckd_last_error() is one string per process, overwritten by the latest failure. */
+ * a context that lives on another one.  ckd_last_error() returns the calling thread's latest failure (or, when this thread
+ * has had none, the latest failure of any thread). */
 int ckd_create(ckd_ctx **out_ctx, int res_x, int res_y, int device);
 void ckd_destroy(ckd_ctx *ctx);
 const char *ckd_last_error(void);

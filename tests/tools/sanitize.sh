@@ -3,10 +3,11 @@
 # memcheck (out-of-bounds / misaligned accesses) and racecheck (shared-memory hazards in the blur rings, the landscape's
 # transposition buffer, the LUT staging).  Logs go to gpurun_out/; summaries are copied to profiles/.
 #   tests/tools/sanitize.sh [per-tool timeout in seconds]
-T=${1:-420}
+T=${1:-900}
 OUT=gpurun_out
 mkdir -p $OUT
-TESTS="tests/test_gpu_post.py::test_post_case_matches_golden tests/test_gpu_effects.py::test_every_golden_effect_case tests/test_gpu_post.py::test_blend_chain_equals_sequential_blends"
+rm -f $OUT/sanitizer_summary.txt
+TESTS="tests/test_gpu_post.py::test_post_case_matches_golden tests/test_gpu_effects.py::test_every_golden_effect_case tests/test_gpu_post.py::test_blend_chain_equals_sequential_blends tests/test_gpu_post.py::test_old_blur_every_kernel_size_in_place"
 for tool in memcheck racecheck; do
 	timeout $T compute-sanitizer --tool $tool --error-exitcode 86 --log-file $OUT/sanitizer_$tool.log \
 		python -m pytest $TESTS -m gpu -q -x -p no:cacheprovider > $OUT/sanitizer_${tool}_pytest.log 2>&1
