@@ -464,8 +464,99 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 	// (horizontal), or 4 x 4 bytes, one image row each, 8 neighbouring columns per row (vertical).  A CTA has 64 to 512
 	// threads: item w is handled by thread w, w - blockDim.x, ...
 	constexpr unsigned kThreads = 32u << LOG2P;
+	// Full stages (all 64 steps inside the line, the thread's line inside the image) go through per-item bases computed once:
+	// an item's global address is base + p0*stepBytes, its ring address base + (p0 mod ring)*4, the four vertical copies 16 rows
+	// apart.  Everything else (the stages around the end of the line, the zero-filled prefetch past it) takes the generic code.
+	constexpr unsigned kItems = (kThreads >= 128) ? 1 : 128/kThreads;
+	size_t itemG[kItems];
+	unsigned itemS[kItems];
+	bool itemOk[kItems], itemMirror[kItems];
+	bool myItemsInside = true;                       // every item of this thread lies on a line of the image (else: generic code, which zero-fills)
+	#pragma unroll
+	for (unsigned it = 0; it < kItems; ++it)
+	{
+		const unsigned w = tid + it*kThreads;
+		if (VERT)
+		{
+			const unsigned col = w & 7;
+			itemG[it] = (size_t(w >> 3)*pitch + line0 + col)*4;
+			itemS[it] = col*kPitchH + (w >> 3)*4;
+			itemOk[it] = w < 128;
+			myItemsInside = myItemsInside && (w >= 128 || line0 + col < numLines);
+			itemMirror[it] = true;                       // rows (w >> 3) + 0 of a stage that starts the ring: < kMirror
+		}
+		else
+		{
+			itemG[it] = (size_t(line0 + (w >> 4))*pitch + (w & 15)*4)*4;
+			itemS[it] = (w >> 4)*kPitchH + (w & 15)*16;
+			itemOk[it] = w < 128;
+			myItemsInside = myItemsInside && (w >= 128 || line0 + (w >> 4) < numLines);
+			itemMirror[it] = (w & 15)*4 < kMirror;
+		}
+	}
+	const size_t stepBytes = VERT ? size_t(pitch)*4 : 4;
+	const unsigned sInBase = unsigned(__cvta_generic_to_shared(s_in)), sOutBase = unsigned(__cvta_generic_to_shared(s_out));
+	auto loadStageFull = [&](unsigned p0)
+	{
+		const unsigned ringOffs = (p0 & (kRing-1))*4;
+		#pragma unroll
+		for (unsigned it = 0; it < kItems; ++it)
+		{
+			if (!itemOk[it])
+				continue;
+			const uint8_t *g = pDest + itemG[it] + size_t(p0)*stepBytes;
+			const unsigned sa = sInBase + itemS[it] + ringOffs;
+			if (VERT)
+			{
+				#pragma unroll
+				for (unsigned k = 0; k < 4; ++k)
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa + k*64), "l"(g + size_t(k)*16*stepBytes) : "memory");
+				if (0 == ringOffs && itemMirror[it])
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa + kRing*4), "l"(g) : "memory");
+			}
+			else
+			{
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory");
+				if (0 == ringOffs && itemMirror[it])
+					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa + kRing*4), "l"(g) : "memory");
+			}
+		}
+	};
+	auto flushStageFull = [&](unsigned p0)
+	{
+		const unsigned ringOffs = (p0 & (kRing-1))*4;
+		#pragma unroll
+		for (unsigned it = 0; it < kItems; ++it)
+		{
+			if (!itemOk[it])
+				continue;
+			uint8_t *g = pDest + itemG[it] + size_t(p0)*stepBytes;
+			const unsigned sa = sOutBase + itemS[it] + ringOffs;
+			if (VERT)
+			{
+				uint32_t v[4];
+				#pragma unroll
+				for (unsigned k = 0; k < 4; ++k)
+					asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[k]) : "r"(sa + k*64) : "memory");
+				#pragma unroll
+				for (unsigned k = 0; k < 4; ++k)
+					*reinterpret_cast<uint32_t *>(g + size_t(k)*16*stepBytes) = v[k];
+			}
+			else
+			{
+				uint4 v;
+				asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
+				*reinterpret_cast<uint4 *>(g) = v;
+			}
+		}
+	};
 	auto loadStage = [&](unsigned p0)
 	{
+		if (p0 + kStage <= len && myItemsInside)
+		{
+			loadStageFull(p0);
+			return;
+		}
 		#pragma unroll
 		for (unsigned w = tid; w < 128; w += kThreads)
 		{
@@ -496,6 +587,11 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 	};
 	auto flushStage = [&](unsigned p0)
 	{
+		if (p0 + kStage <= len && myItemsInside)
+		{
+			flushStageFull(p0);
+			return;
+		}
 		#pragma unroll
 		for (unsigned w = tid; w < 128; w += kThreads)
 		{
@@ -762,6 +858,17 @@ __global__ void __launch_bounds__(32 << LOG2P) old_blur_blocked_kernel(uint8_t *
 		advance(min(te, len));
 		block(tb, min(te, len), BoolTag<false>());
 		retire(te);
+	}
+	// two blocks per iteration: the outputs of one block are the trailing-edge operands of the next, and with the pair spelled
+	// out they stay where they were computed instead of being copied at the loop's back edge
+	for (; tb + 2*kM <= len; tb += 2*kM)
+	{
+		advance(tb + kM);
+		block(tb, tb + kM, BoolTag<true>());
+		retire(tb + kM);
+		advance(tb + 2*kM);
+		block(tb + kM, tb + 2*kM, BoolTag<true>());
+		retire(tb + 2*kM);
 	}
 	for (; tb + kM <= len; tb += kM)
 	{
