@@ -16,6 +16,7 @@ for T in $TARGETS; do
     ball) CMD="python tools/effect_one.py ball"; PAT="regex:ball_kernel";;
     ball_beams) CMD="python tools/effect_one.py ball_beams"; PAT="regex:ball_kernel";;
     tunnel) CMD="python tools/effect_one.py tunnel"; PAT="regex:tunnel_kernel";;
+    chain_*) CMD="python tools/demo_one.py ${T#chain_}"; PAT="regex:blend_chain";;
     *) CMD="python tools/effect_one.py $T"; PAT="regex:raymarch_kernel";;
   esac
   $NCU -k $PAT -o $TMP/${TAG}_$T $CMD > $OUT/${TAG}_$T.log 2>&1
