@@ -348,7 +348,7 @@ def run_reference(args):
 # legs of our arm
 # ---------------------------------------------------------------------------------------------------------------
 
-def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
+def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu, lanes=2):
     """BASELINE config 5 with the gather.  Returns the sub-record (rank 0) or None."""
     import torch
     from cookiedough_b200 import capi, sharding
@@ -356,6 +356,7 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
     frame_bytes = RES_X * RES_Y * 4
     times = sharding.timeline_times(frames)
     skip = sharding.default_collector_skip(world)      # the library's default (hostapi passes it on when collector_skip is None)
+    lanes = max(1, min(4, lanes))                      # frames in flight per GPU (ckd_host.h: lanes)
     slots = min(64, max(8, 4 * world))   # every producer may run four frames ahead of the collector (33 MB per 4K slot in rank 0's HBM)
 
     # the ring lives on rank 0; its CUDA IPC handle travels once, over the control plane (torch.distributed)
@@ -378,22 +379,22 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
 
     seq = 0
     # warm-up pass (also the first list of checksums)
-    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=1, pop_mode=capi.GATHER_CHECKSUM, seq_base=seq, collector_skip=skip)
+    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=1, pop_mode=capi.GATHER_CHECKSUM, seq_base=seq, collector_skip=skip, lanes=lanes)
     ctx.sync()
     gather.status()
     warm_sums = gather.checksums(seq, frames) if rank == 0 else None
     seq += frames
     barrier()
 
-    launches0 = ctx.launch_count()
+    launches0 = host.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=passes, pop_mode=capi.GATHER_CHECKSUM, seq_base=seq, collector_skip=skip)
+    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=passes, pop_mode=capi.GATHER_CHECKSUM, seq_base=seq, collector_skip=skip, lanes=lanes)
     ev1.record()                        # CkdTimeline_Render ends with ckd_gather_flush: the stream waits for every push and pop
     torch.cuda.synchronize()
     gather.status()
     ms = reduce_max(dist, ev0.elapsed_time(ev1))
-    launches = reduce_sum(dist, ctx.launch_count() - launches0)
+    launches = reduce_sum(dist, host.launch_count() - launches0)
     sums = gather.checksums(seq, frames) if rank == 0 else None
     last_sums = gather.checksums(seq + (passes - 1) * frames, frames) if rank == 0 else None
     seq += passes * frames
@@ -404,7 +405,7 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
     barrier()
     t0 = time.perf_counter()
     host.timeline_render(times, rank=rank, world=world, gather=gather, passes=1, pop_mode=capi.GATHER_CHECKSUM | capi.GATHER_TO_HOST,
-                         host_ring=ring, seq_base=seq, collector_skip=skip)
+                         host_ring=ring, seq_base=seq, collector_skip=skip, lanes=lanes)
     ctx.sync()
     e2e_s = reduce_max(dist, time.perf_counter() - t0)
     gather.status()
@@ -415,7 +416,7 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
     barrier()
     eva, evb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eva.record()
-    host.timeline_render(times, rank=rank, world=world, gather=None, passes=1)
+    host.timeline_render(times, rank=rank, world=world, gather=None, passes=1, lanes=lanes)
     evb.record()
     torch.cuda.synchronize()
     nogather_ms = reduce_max(dist, eva.elapsed_time(evb))
@@ -430,7 +431,8 @@ def timeline_leg(host, ctx, dist, rank, world, frames, passes, with_cpu):
             "scaling": "strong", "n_gpus": world, "passes": passes,
             "sharding": ("frame i -> rank i mod N" if skip <= 1 else f"weighted round-robin (CkdTimeline_Owner, collector_skip = {skip}): rank 0, which collects and checksums every frame, renders 1 frame per {skip} rounds of the other ranks ({len(sharding.frames_for_rank(frames, 0, world, skip))} of {frames} frames)")
                         + "; every frame pushed to a slot ring in rank 0's HBM (ckd_gather_*: CUDA IPC mapping, copy-engine peer copies over NVLink, device-side ready/drained flags), checksummed there in order; no NCCL on the data path",
-            "collector_skip": skip,
+            "collector_skip": skip, "lanes_per_gpu": lanes,
+            "lanes_note": "each rank alternates its frames between two contexts on its GPU (own render targets and stream): the latency-bound kernels of one frame overlap the issue-bound ones of the other",
             "gathered_to_rank0_fps": fps, "value": px * passes / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_pass": ms / passes,
             "no_gather_fps": frames / (nogather_ms * 1e-3),
             "nvlink_bytes_per_frame": peer_bytes_timed / (frames * passes), "nvlink_gbs": peer_bytes_timed / (ms * 1e-3) / 1e9,
@@ -882,7 +884,7 @@ def run_ours(args):
     # ---- BASELINE config 5: the timeline with the gather (all ranks) ---------------------------------------------
     timeline = None
     if not args.no_timeline:
-        timeline = timeline_leg(host, ctx, dist, rank, world, args.frames, args.timeline_passes, with_cpu)
+        timeline = timeline_leg(host, ctx, dist, rank, world, args.frames, args.timeline_passes, with_cpu, args.timeline_lanes)
 
     # ---- BASELINE config 4: the post chain (rank 0) ---------------------------------------------------------------
     post_chain = post_chain_leg(ctx, with_cpu, hbm_peak) if rank == 0 and not args.no_post_chain else None
@@ -989,7 +991,7 @@ def run_timeline(args):
     host = hostapi.Host(RES_X, RES_Y, local, assets, demo=True)
     ctx = host.context()
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    rec = timeline_leg(host, ctx, dist, rank, world, args.frames, max(1, args.steps), rank == 0 and world == 1 and not args.no_cpu_baseline)
+    rec = timeline_leg(host, ctx, dist, rank, world, args.frames, max(1, args.steps), rank == 0 and world == 1 and not args.no_cpu_baseline, args.timeline_lanes)
     if rank == 0:
         line = {"metric": "Mpixel/s", "value": rec["value"], "unit": "Mpixel/s", "n_gpus": world, "steps": max(1, args.steps), "warmup": 1,
                 "ms_per_step": rec["ms_per_pass"], "fps": rec["gathered_to_rank0_fps"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -1020,6 +1022,7 @@ def main():
     ap.add_argument("--workload", default="effect-suite-4k", choices=["effect-suite-4k", "timeline-4k"],
                     help="timeline-4k: the 600-frame directors-cut timeline through Demo_Draw (BASELINE config 5) as the headline of its own line")
     ap.add_argument("--frames", type=int, default=600)
+    ap.add_argument("--timeline-lanes", type=int, default=2, help="contexts per GPU the timeline alternates its frames between (1 or 2)")
     ap.add_argument("--timeline-passes", type=int, default=2, help="timed passes over the timeline in the default line's `timeline` record")
     args = ap.parse_args()
     if args.workload == "timeline-4k":

@@ -379,6 +379,8 @@ extern "C" void ckd_destroy(ckd_ctx *ctx)
 	for (auto &ev : ctx->evBand)
 		if (ev) cudaEventDestroy(ev);
 	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+	if (ctx->ownedStream) cudaStreamDestroy(ctx->ownedStream);
+	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
 	if (ctx->evStart) cudaEventDestroy(ctx->evStart);
 	if (ctx->evStop) cudaEventDestroy(ctx->evStop);
 	if (ctx->d_pool) cudaFree(ctx->d_pool);
@@ -389,6 +391,54 @@ extern "C" int ckd_set_stream(ckd_ctx *ctx, void *cuda_stream)
 {
 	CKD_REQUIRE(ctx, "null context");
 	ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+	return CKD_OK;
+}
+
+extern "C" int ckd_own_stream(ckd_ctx *ctx)
+{
+	CKD_REQUIRE(ctx, "null context");
+	if (nullptr == ctx->ownedStream)
+		CKD_CUDA(cudaStreamCreateWithFlags(&ctx->ownedStream, cudaStreamNonBlocking));
+	ctx->stream = ctx->ownedStream;
+	return CKD_OK;
+}
+
+extern "C" int ckd_join(ckd_ctx *ctx, ckd_ctx *other)
+{
+	CKD_REQUIRE(ctx && other, "null context");
+	if (nullptr == other->evJoin)
+		CKD_CUDA(cudaEventCreateWithFlags(&other->evJoin, cudaEventDisableTiming));
+	CKD_CUDA(cudaEventRecord(other->evJoin, other->stream));
+	CKD_CUDA(cudaStreamWaitEvent(ctx->stream, other->evJoin, 0));
+	return CKD_OK;
+}
+
+extern "C" int ckd_clone_inputs(ckd_ctx *dst, const ckd_ctx *src)
+{
+	CKD_REQUIRE(dst && src && dst != src, "two different contexts are needed");
+	CKD_REQUIRE(dst->resX == src->resX && dst->resY == src->resY && dst->device == src->device, "the contexts must have the same resolution and device");
+	CKD_CUDA(cudaDeviceSynchronize()); // whatever still writes the source's inputs has to land first; this is a set-up call
+	for (int i = 0; i < CKD_IMG_COUNT; ++i)
+	{
+		const ckd_image_slot &from = src->images[i];
+		ckd_image_slot &to = dst->images[i];
+		if (to.d_pixels) { cudaFree(to.d_pixels); to.d_pixels = nullptr; }
+		to = from;
+		to.d_pixels = nullptr;
+		if (nullptr == from.d_pixels)
+			continue;
+		const size_t bytes = size_t(from.width)*from.height*from.bpp + 256;
+		CKD_CUDA(cudaMalloc(&to.d_pixels, bytes));
+		CKD_CUDA(cudaMemcpy(to.d_pixels, from.d_pixels, bytes, cudaMemcpyDeviceToDevice));
+	}
+	CKD_TRY(ckd_set_cos_lut(dst, src->h_cosLUT));
+	CKD_TRY(ckd_set_fast_cos_table(dst, src->h_fastCosTab));
+	if (nullptr != src->h_rsqrtTab)
+		CKD_TRY(ckd_set_rsqrt_table(dst, src->h_rsqrtTab, src->rsqrtLog2Bin));
+	const size_t mapBytes = size_t(src->resX)*src->resY*2*sizeof(int32_t);
+	CKD_CUDA(cudaMemcpy(dst->d_polarMap, src->d_polarMap, mapBytes, cudaMemcpyDeviceToDevice));
+	CKD_CUDA(cudaMemcpy(dst->d_polarInvMap, src->d_polarInvMap, mapBytes, cudaMemcpyDeviceToDevice));
+	dst->frameIndependent = src->frameIndependent;
 	return CKD_OK;
 }
 

@@ -31,7 +31,7 @@ namespace {
 
 constexpr unsigned kGatherMagic = 0x47444b43u; // "CKDG"
 constexpr int kMaxSlots = 64;
-constexpr int kMaxStaging = 4;
+constexpr int kMaxStaging = 8;                   // up to four frames rendering side by side (lanes) while as many are being copied
 constexpr size_t kControlBytes = 4096;         // ready[64], drained[64], status
 
 // control block at the start of the ring allocation (lives in the collector's HBM, mapped by every producer)
@@ -332,13 +332,14 @@ extern "C" int ckd_gather_set_timeout_ms(ckd_gather *g, unsigned timeout_ms)
 
 // a local frame to render sequence number q into: one of numStaging device frames, handed out round robin; the compute stream
 // waits (on the device) for the push that last read it
-extern "C" int ckd_gather_acquire(ckd_gather *g, uint32_t **out_d_frame)
+extern "C" int ckd_gather_acquire_on(ckd_gather *g, ckd_ctx *renderCtx, uint32_t **out_d_frame)
 {
-	CKD_REQUIRE(g && out_d_frame, "null argument");
+	CKD_REQUIRE(g && renderCtx && out_d_frame, "null argument");
+	CKD_REQUIRE(renderCtx->device == g->ctx->device && renderCtx->resX == g->ctx->resX && renderCtx->resY == g->ctx->resY, "the rendering context must match the gather's");
 	CKD_CUDA(cudaSetDevice(g->ctx->device));
 	if (0 == g->numStaging)
 	{
-		g->numStaging = 3;
+		g->numStaging = kMaxStaging;
 		for (int i = 0; i < g->numStaging; ++i)
 		{
 			CKD_CUDA(cudaMalloc(&g->d_staging[i], g->frameBytes + size_t(g->ctx->resX)*16)); // + 4 guard rows like every frame of the context
@@ -349,11 +350,17 @@ extern "C" int ckd_gather_acquire(ckd_gather *g, uint32_t **out_d_frame)
 	}
 	const int k = int(g->acquired % unsigned(g->numStaging));
 	if (g->stagingBusy[k])
-		CKD_CUDA(cudaStreamWaitEvent(g->ctx->stream, g->evPushed[k], 0));
+		CKD_CUDA(cudaStreamWaitEvent(renderCtx->stream, g->evPushed[k], 0));
 	g->currentStaging = k;
 	++g->acquired;
 	*out_d_frame = g->d_staging[k];
 	return CKD_OK;
+}
+
+extern "C" int ckd_gather_acquire(ckd_gather *g, uint32_t **out_d_frame)
+{
+	CKD_REQUIRE(g, "null argument");
+	return ckd_gather_acquire_on(g, g->ctx, out_d_frame);
 }
 
 // publishes the frame rendered into the staging frame of the last ckd_gather_acquire (or any device frame d_frame != NULL that
@@ -361,6 +368,13 @@ extern "C" int ckd_gather_acquire(ckd_gather *g, uint32_t **out_d_frame)
 extern "C" int ckd_gather_push(ckd_gather *g, const uint32_t *d_frame, unsigned long long seq)
 {
 	CKD_REQUIRE(g, "null argument");
+	return ckd_gather_push_on(g, g->ctx, d_frame, seq);
+}
+
+extern "C" int ckd_gather_push_on(ckd_gather *g, ckd_ctx *renderCtx, const uint32_t *d_frame, unsigned long long seq)
+{
+	CKD_REQUIRE(g && renderCtx, "null argument");
+	CKD_REQUIRE(renderCtx->device == g->ctx->device, "the rendering context must live on the gather's device");
 	CKD_CUDA(cudaSetDevice(g->ctx->device));
 	int k = -1;
 	if (nullptr == d_frame)
@@ -370,9 +384,15 @@ extern "C" int ckd_gather_push(ckd_gather *g, const uint32_t *d_frame, unsigned 
 		d_frame = g->d_staging[k];
 		g->currentStaging = -1;
 	}
+	else
+	{
+		// a staging frame handed out earlier (two frames in flight): find it again
+		for (int i = 0; i < g->numStaging; ++i)
+			if (g->d_staging[i] == d_frame) k = i;
+	}
 	const int slot = int(seq % unsigned(g->slots));
 	cudaEvent_t evRendered = (k >= 0) ? g->evRendered[k] : g->evAdhoc;
-	CKD_CUDA(cudaEventRecord(evRendered, g->ctx->stream));
+	CKD_CUDA(cudaEventRecord(evRendered, renderCtx->stream));
 	CKD_CUDA(cudaStreamWaitEvent(g->pushStream, evRendered, 0));
 	if (seq >= unsigned(g->slots))
 	{

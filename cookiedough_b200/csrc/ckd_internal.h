@@ -25,6 +25,8 @@ struct ckd_ctx {
 	int fxX = 0, fxY = 0;       // kFxMapResX, kFxMapResY
 	int numSMs = 148;
 	cudaStream_t stream = nullptr;
+	cudaStream_t ownedStream = nullptr;             // ckd_own_stream: a non-blocking stream that belongs to the context
+	cudaEvent_t evJoin = nullptr;                  // ckd_join: marks what has been enqueued on this context's stream
 	cudaEvent_t evStart = nullptr, evStop = nullptr;
 	cudaStream_t copyStream = nullptr;             // read-back overlapped with rendering (ckd_download_overlapped)
 	cudaEvent_t evRendered[2] = {}, evCopied[2] = {};

@@ -44,20 +44,82 @@ static bool Check(int rc, const char *what)
 	return false;
 }
 
+// Lanes: the host layer is a single context by construction (the reference is not re-entrant either).  For timeline rendering
+// a second context on the same device -- own render targets and stream, a copy of every input -- lets two frames be in flight
+// side by side; s_ctx is whichever lane the next X_Draw / Demo_Draw renders with.
+constexpr int kMaxLanes = 4;
+static ckd_ctx *s_lanes[kMaxLanes] = { nullptr, nullptr, nullptr, nullptr };
+static int s_device = 0;
+
 bool CkdHost_Create(int resX, int resY, int device)
 {
-	if (nullptr != s_ctx)
+	if (nullptr != s_lanes[0])
 		CkdHost_Destroy();
-	return Check(ckd_create(&s_ctx, resX, resY, device), "CkdHost_Create");
+	s_device = device;
+	if (!Check(ckd_create(&s_lanes[0], resX, resY, device), "CkdHost_Create"))
+		return false;
+	s_ctx = s_lanes[0];
+	return true;
 }
 
 void CkdHost_Destroy()
 {
-	ckd_destroy(s_ctx);
+	for (int i = kMaxLanes - 1; i >= 0; --i)
+	{
+		if (nullptr != s_lanes[i]) ckd_destroy(s_lanes[i]);
+		s_lanes[i] = nullptr;
+	}
 	s_ctx = nullptr;
 }
 
 ckd_ctx *CkdHost_Context() { return s_ctx; }
+ckd_ctx *CkdHost_LaneContext(int lane) { return (lane >= 0 && lane < kMaxLanes) ? s_lanes[lane] : nullptr; }
+
+// (re)creates the lanes 1..numLanes-1 as copies of the first one's inputs; call after every X_Create / Demo_Create and setter
+bool CkdHost_PrepareLanes(int numLanes)
+{
+	if (nullptr == s_lanes[0])
+	{
+		SetLastError("CkdHost_Create() has not been called");
+		return false;
+	}
+	if (numLanes < 1 || numLanes > kMaxLanes)
+	{
+		SetLastError("CkdHost_PrepareLanes: 1 to 4 lanes");
+		return false;
+	}
+	for (int i = 1; i < numLanes; ++i)
+	{
+		if (nullptr == s_lanes[i])
+		{
+			if (!Check(ckd_create(&s_lanes[i], ckd_res_x(s_lanes[0]), ckd_res_y(s_lanes[0]), s_device), "CkdHost_PrepareLanes")
+				|| !Check(ckd_own_stream(s_lanes[i]), "CkdHost_PrepareLanes"))
+				return false;
+		}
+		if (!Check(ckd_clone_inputs(s_lanes[i], s_lanes[0]), "CkdHost_PrepareLanes"))
+			return false;
+	}
+	return true;
+}
+
+bool CkdHost_SelectLane(int lane)
+{
+	if (lane < 0 || lane >= kMaxLanes || nullptr == s_lanes[lane])
+	{
+		SetLastError("CkdHost_SelectLane: no such lane");
+		return false;
+	}
+	s_ctx = s_lanes[lane];
+	return true;
+}
+
+unsigned long long CkdHost_LaunchCount()
+{
+	unsigned long long n = 0;
+	for (ckd_ctx *lane : s_lanes)
+		if (nullptr != lane) n += ckd_launch_count(lane);
+	return n;
+}
 void CkdHost_SetRocketSource(const char *path) { s_rocketSource = path ? path : ""; }
 void CkdHost_SetTime(double seconds) { s_timeSec = seconds; }
 

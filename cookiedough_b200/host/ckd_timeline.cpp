@@ -37,6 +37,7 @@ unsigned CkdTimeline_DefaultCollectorSkip(unsigned world) { return (world >= 4) 
 
 bool CkdTimeline_Render(const CkdTimelineJob *job)
 {
+	CkdHost_SelectLane(0);                           // (a no-op before CkdHost_Create: the check below reports that)
 	ckd_ctx *ctx = CkdHost_Context();
 	if (nullptr == ctx || nullptr == job || nullptr == job->times)
 	{
@@ -62,6 +63,18 @@ bool CkdTimeline_Render(const CkdTimelineJob *job)
 	if (!Ok(ckd_set_frame_independent(ctx, 1), "CkdTimeline_Render"))
 		return false;
 
+	// lanes: this rank's frames rotate through several contexts, each with its own stream (ckd_host.h)
+	const unsigned numLanes = (job->lanes >= 2 && job->lanes <= 4) ? job->lanes : 1;
+	if (numLanes > 1 && !CkdHost_PrepareLanes(int(numLanes)))   // copies lane 0's inputs, the flag above included
+	{
+		ckd_set_frame_independent(ctx, 0);
+		return false;
+	}
+	ckd_ctx *lanes[4] = { ctx, ctx, ctx, ctx };
+	for (unsigned i = 1; i < numLanes; ++i)
+		lanes[i] = CkdHost_LaneContext(int(i));
+	unsigned rendered = 0;
+
 	SetLastError("");
 	bool ok = true;
 	std::deque<PendingFrame> pending;                 // rank 0: copies to the host that are in flight
@@ -86,10 +99,14 @@ bool CkdTimeline_Render(const CkdTimelineJob *job)
 			const unsigned long long seq = job->seqBase + (unsigned long long)(pass)*job->numFrames + i;
 			if (CkdTimeline_Owner(i, job->world, job->collectorSkip) == job->rank)
 			{
+				ckd_ctx *lane = lanes[rendered % numLanes];
+				if (numLanes > 1)
+					CkdHost_SelectLane(int(rendered % numLanes));
+				++rendered;
 				uint32_t *d_frame = nullptr;
 				if (nullptr != gather)
 				{
-					ok = Ok(ckd_gather_acquire(gather, &d_frame), "CkdTimeline_Render: ckd_gather_acquire");
+					ok = Ok(ckd_gather_acquire_on(gather, lane, &d_frame), "CkdTimeline_Render: ckd_gather_acquire");
 					if (!ok) break;
 				}
 				CkdHost_SetDeviceTarget(d_frame);     // nullptr (no gather): the context's own frame
@@ -102,7 +119,7 @@ bool CkdTimeline_Render(const CkdTimelineJob *job)
 					break;
 				}
 				if (nullptr != gather)
-					ok = Ok(ckd_gather_push(gather, nullptr, seq), "CkdTimeline_Render: ckd_gather_push");
+					ok = Ok(ckd_gather_push_on(gather, lane, nullptr, seq), "CkdTimeline_Render: ckd_gather_push");
 			}
 			if (ok && collector)
 			{
@@ -134,6 +151,16 @@ bool CkdTimeline_Render(const CkdTimelineJob *job)
 	{
 		ok = Ok(ckd_gather_flush(gather), "CkdTimeline_Render: ckd_gather_flush") && ok;
 	}
+	if (numLanes > 1)
+	{
+		// the caller's stream (lane 0's) stands for the whole job: it waits for what the other lanes still have in flight
+		CkdHost_SelectLane(0);
+		for (unsigned i = 1; i < numLanes; ++i)
+		{
+			ok = Ok(ckd_join(ctx, lanes[i]), "CkdTimeline_Render: ckd_join") && ok;
+			ckd_set_frame_independent(lanes[i], 0);
+		}
+	}
 	ckd_set_frame_independent(ctx, 0);
 	return ok;
 }
@@ -142,12 +169,13 @@ extern "C" {
 
 // ctypes hook: the job as plain arguments
 int ckdhost_timeline_render(const double *times, unsigned numFrames, unsigned passes, unsigned rank, unsigned world, void *gather, int popMode,
-	uint32_t *const *hostRing, unsigned hostRingFrames, unsigned long long seqBase, float delta, unsigned collectorSkip)
+	uint32_t *const *hostRing, unsigned hostRingFrames, unsigned long long seqBase, float delta, unsigned collectorSkip, unsigned lanes)
 {
-	CkdTimelineJob job = { times, numFrames, passes, rank, world, static_cast<ckd_gather *>(gather), popMode, hostRing, hostRingFrames, seqBase, delta, collectorSkip };
+	CkdTimelineJob job = { times, numFrames, passes, rank, world, static_cast<ckd_gather *>(gather), popMode, hostRing, hostRingFrames, seqBase, delta, lanes, collectorSkip };
 	return CkdTimeline_Render(&job) ? 0 : -1;
 }
 unsigned ckdhost_timeline_owner(unsigned frame, unsigned world, unsigned collectorSkip) { return CkdTimeline_Owner(frame, world, collectorSkip); }
 unsigned ckdhost_timeline_default_skip(unsigned world) { return CkdTimeline_DefaultCollectorSkip(world); }
+unsigned long long ckdhost_launch_count() { return CkdHost_LaunchCount(); }
 
 } // extern "C"

@@ -47,7 +47,8 @@ def _lib():
     L.ckdhost_demo_draw.argtypes = [C.c_void_p, C.c_double, C.c_float]
     L.ckdhost_demo_destroy.argtypes = []
     L.ckdhost_timeline_render.argtypes = [C.POINTER(C.c_double), C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_int,
-                                          C.POINTER(C.c_void_p), C.c_uint, C.c_ulonglong, C.c_float, C.c_uint]
+                                          C.POINTER(C.c_void_p), C.c_uint, C.c_ulonglong, C.c_float, C.c_uint, C.c_uint]
+    L.ckdhost_launch_count.restype = C.c_ulonglong
     L.ckdhost_timeline_owner.argtypes = [C.c_uint, C.c_uint, C.c_uint]
     L.ckdhost_timeline_owner.restype = C.c_uint
     L.ckdhost_timeline_default_skip.argtypes = [C.c_uint]
@@ -165,19 +166,24 @@ class Host:
             raise capi.CkdError(f"Demo_Draw: {self.L.ckdhost_last_error().decode()}")
         return rc == 1
 
-    def timeline_render(self, times, rank=0, world=1, gather=None, passes=1, pop_mode=0, host_ring=None, seq_base=0, delta=1.6667, collector_skip=None):
+    def timeline_render(self, times, rank=0, world=1, gather=None, passes=1, pop_mode=0, host_ring=None, seq_base=0, delta=1.6667, collector_skip=None, lanes=1):
         """CkdTimeline_Render: Demo_Draw for the frames i % world == rank of `times`, each published to `gather` (capi.Gather);
         rank 0 also consumes every frame in order (pop_mode: capi.GATHER_CHECKSUM / GATHER_TO_HOST into host_ring, a list of
-        page-locked buffer addresses, or into the open sink when host_ring is None)"""
+        page-locked buffer addresses, or into the open sink when host_ring is None).  lanes=2: this rank's frames alternate between
+        two contexts with their own streams (two frames in flight side by side)"""
         assert self.demo
         arr = (C.c_double * len(times))(*times)
         ring = (C.c_void_p * len(host_ring))(*host_ring) if host_ring else None
         if collector_skip is None:      # the library's default for this many GPUs (only matters with a gather: rank 0 collects)
             collector_skip = self.L.ckdhost_timeline_default_skip(world) if gather is not None else 1
         rc = self.L.ckdhost_timeline_render(arr, len(times), passes, rank, world, gather.g if gather is not None else None, pop_mode,
-                                            ring, len(host_ring) if host_ring else 0, seq_base, C.c_float(delta), collector_skip)
+                                            ring, len(host_ring) if host_ring else 0, seq_base, C.c_float(delta), collector_skip, lanes)
         if rc != 0:
             raise capi.CkdError(f"CkdTimeline_Render: {self.L.ckdhost_last_error().decode()}")
+
+    def launch_count(self):
+        """kernels launched so far by every lane of the host layer (CkdHost_LaunchCount)"""
+        return int(self.L.ckdhost_launch_count())
 
     def fastcos(self, x, sine=False):
         """InitializeFastCosine + fastcosf / fastsinf over an array (ckd_host.h)"""

@@ -50,6 +50,14 @@ const char *ckd_last_error(void);
 const char *ckd_version(void);
 
 int ckd_set_stream(ckd_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = default stream */
+/* second context on the same device for frames in flight side by side (two frames of a timeline overlap their latency-bound
+ * kernels: blurs, casters): ckd_own_stream gives the context a non-blocking stream of its own (destroyed with the context),
+ * ckd_clone_inputs copies everything a context is configured with -- the uploaded images, the cosine / fast-cosine / RSQRTPS
+ * tables, the polar maps, the frame-independent flag -- from `src` into `dst` (same resolution, same device), and ckd_join makes
+ * `ctx`'s stream wait for everything enqueued on `other`'s stream so far. */
+int ckd_own_stream(ckd_ctx *ctx);
+int ckd_clone_inputs(ckd_ctx *dst, const ckd_ctx *src);
+int ckd_join(ckd_ctx *ctx, ckd_ctx *other);
 int ckd_sync(ckd_ctx *ctx);
 
 int ckd_res_x(const ckd_ctx *ctx);
@@ -340,6 +348,10 @@ int ckd_gather_acquire(ckd_gather *gather, uint32_t **out_d_frame);
  * d_frame == NULL: the frame of the last ckd_gather_acquire; otherwise any device frame that stays untouched until
  * ckd_gather_flush + ckd_sync.  Waits on the device (not the host) until the collector has drained slot seq % slots. */
 int ckd_gather_push(ckd_gather *gather, const uint32_t *d_frame, unsigned long long seq);
+/* the same for a frame rendered on another context of this process and device (ckd_own_stream / ckd_clone_inputs): the staging
+ * frame is handed out against, and the push ordered after, `render_ctx`'s stream.  Eight staging frames are handed out in turn. */
+int ckd_gather_acquire_on(ckd_gather *gather, ckd_ctx *render_ctx, uint32_t **out_d_frame);
+int ckd_gather_push_on(ckd_gather *gather, ckd_ctx *render_ctx, const uint32_t *d_frame, unsigned long long seq);
 /* collector: consume sequence number seq (call in order).  mode: 0 release the slot, CKD_GATHER_CHECKSUM, CKD_GATHER_TO_HOST
  * (h_dest page-locked), or both.  Enqueued on the gather's consumer stream. */
 int ckd_gather_pop(ckd_gather *gather, unsigned long long seq, int mode, void *h_dest);

@@ -69,6 +69,16 @@ void CkdHost_Flush();
 // default).  This is how the timeline runner below renders straight into the staging frames of the gather.
 void CkdHost_SetDeviceTarget(uint32_t *d_frame);
 
+// Lanes (timeline rendering): up to three more contexts on the same device -- render targets and stream of their own, a copy of
+// every input of the first (ckd_clone_inputs) -- so that several frames can be in flight side by side and the latency-bound
+// kernels of one (blurs, casters) overlap the issue-bound ones of another.  CkdHost_PrepareLanes(n) (re)creates lanes 1..n-1 from
+// the current state of lane 0 (call it after the X_Create / Demo_Create calls); CkdHost_SelectLane picks the context the next
+// X_Draw / Demo_Draw uses (lane 0 is the drop-in default).  CkdTimeline_Render does all of this itself when the job asks for lanes.
+bool CkdHost_PrepareLanes(int numLanes);
+bool CkdHost_SelectLane(int lane);
+ckd_ctx *CkdHost_LaneContext(int lane);
+unsigned long long CkdHost_LaunchCount();      // kernels launched by both lanes
+
 // ---- timeline rendering, frame-sharded over the GPUs of one box (BASELINE config 5).  One process per GPU calls
 //      this with its rank: it renders the frames i with i % world == rank through Demo_Draw -- times[i] is what the reference
 //      would get from the audio stream position, audio.cpp:175-178 -- and publishes each to the gather (ckd.h: a slot ring in
@@ -86,6 +96,7 @@ struct CkdTimelineJob
 	unsigned hostRingFrames;        //   deliver into the open frame sink (CkdSink_Acquire / CkdSink_Commit by frame index)
 	unsigned long long seqBase;
 	float delta;                    // Demo_Draw's delta argument
+	unsigned lanes;                 // 0 or 1: one frame at a time; 2..4: this rank's frames rotate through that many contexts (see Lanes above)
 	unsigned collectorSkip;         // 0 or 1: frame i -> rank i % world.  k > 1: rank 0, which also collects (and checksums / copies
 	                                //   out) every frame of every rank, renders only one frame per k rounds of the other ranks:
 	                                //   CkdTimeline_Owner(i, world, k).  Every rank must pass the same value.

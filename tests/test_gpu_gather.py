@@ -101,12 +101,12 @@ def test_a_wait_that_cannot_be_satisfied_times_out_instead_of_hanging(ctx_synth)
         g.close()
 
 
-def _run_world(world, frames, devices, to_host=False, slots=4, passes=1, collector_skip=1):
+def _run_world(world, frames, devices, to_host=False, slots=4, passes=1, collector_skip=1, lanes=1):
     with tempfile.TemporaryDirectory() as scratch:
         procs = []
         for rank in range(world):
             cmd = [sys.executable, WORKER, "--rank", str(rank), "--world", str(world), "--device", str(devices[rank % len(devices)]),
-                   "--dir", scratch, "--frames", str(frames), "--slots", str(slots), "--passes", str(passes), "--collector-skip", str(collector_skip)]
+                   "--dir", scratch, "--frames", str(frames), "--slots", str(slots), "--passes", str(passes), "--collector-skip", str(collector_skip), "--lanes", str(lanes)]
             if to_host:
                 cmd.append("--to-host")
             procs.append(subprocess.Popen(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
@@ -145,6 +145,9 @@ def test_gathered_timeline_does_not_depend_on_the_number_of_ranks():
     assert len(one["checksums"]) == frames and len({c for c in one["checksums"] if int(c) != 0}) >= frames - 2
     assert two["checksums"] == one["checksums"]
     assert three["checksums"] == one["checksums"] * 2            # two passes over the same timeline
+    # two lanes per rank (two frames in flight on two contexts of the same GPU): the same stream again, alone and sharded
+    assert _run_world(1, frames, devices[:1], lanes=2, to_host=True)["checksums"] == one["checksums"]
+    assert _run_world(2, frames, devices, lanes=2, passes=2)["checksums"] == one["checksums"] * 2
     # weighted sharding (the collector renders one frame per two rounds of the others): the same stream, fewer frames on rank 0
     weighted = _run_world(3, frames, devices, slots=3, collector_skip=2)
     assert weighted["checksums"] == one["checksums"]

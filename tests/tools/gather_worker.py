@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--to-host", action="store_true")
     ap.add_argument("--collector-skip", type=int, default=1)
+    ap.add_argument("--lanes", type=int, default=1)
     args = ap.parse_args()
 
     from cookiedough_b200 import capi, hostapi, sharding
@@ -70,7 +71,7 @@ def main():
     if args.rank == 0 and args.to_host:
         ring = [ctx.malloc_host(res_x * res_y * 4) for _ in range(3)]
     t0 = time.perf_counter()
-    host.timeline_render(times, rank=args.rank, world=args.world, gather=gather, passes=args.passes, pop_mode=mode, host_ring=ring, collector_skip=args.collector_skip)
+    host.timeline_render(times, rank=args.rank, world=args.world, gather=gather, passes=args.passes, pop_mode=mode, host_ring=ring, collector_skip=args.collector_skip, lanes=args.lanes)
     ctx.sync()
     elapsed = time.perf_counter() - t0
     gather.status()
