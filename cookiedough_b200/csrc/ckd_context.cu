@@ -146,6 +146,7 @@ static size_t AlignUp(size_t v, size_t a) { return (v + a - 1)/a*a; }
 extern "C" int ckd_set_cos_lut(ckd_ctx *ctx, const float *lut2049)
 {
 	CKD_REQUIRE(ctx && lut2049, "null argument");
+	ctx->inputsGen++;
 	memcpy(ctx->h_cosLUT, lut2049, sizeof(ctx->h_cosLUT));
 	std::vector<float2> pairs(kCkdCosTabSize);
 	for (int i = 0; i < kCkdCosTabSize; ++i)
@@ -157,6 +158,7 @@ extern "C" int ckd_set_cos_lut(ckd_ctx *ctx, const float *lut2049)
 extern "C" int ckd_set_fast_cos_table(ckd_ctx *ctx, const double *table1025)
 {
 	CKD_REQUIRE(ctx && table1025, "null argument");
+	ctx->inputsGen++;
 	memcpy(ctx->h_fastCosTab, table1025, sizeof(ctx->h_fastCosTab));
 	CKD_CUDA(cudaMemcpy(ctx->d_fastCosTab, table1025, sizeof(ctx->h_fastCosTab), cudaMemcpyHostToDevice));
 	return CKD_OK;
@@ -180,6 +182,7 @@ extern "C" int ckd_set_rsqrt_table(ckd_ctx *ctx, const uint32_t *table, int log2
 {
 	CKD_REQUIRE(ctx && table, "null argument");
 	CKD_REQUIRE(log2_bin >= 0 && log2_bin <= 23, "log2_bin out of range");
+	ctx->inputsGen++;
 	const size_t entries = size_t(2) << (23-log2_bin);
 	if (ctx->d_rsqrtTab) { cudaFree(ctx->d_rsqrtTab); ctx->d_rsqrtTab = nullptr; }
 	free(ctx->h_rsqrtTab);
@@ -208,6 +211,7 @@ extern "C" int ckd_get_rsqrt_table(ckd_ctx *ctx, uint32_t *out_table, size_t max
 extern "C" int ckd_set_polar_maps(ckd_ctx *ctx, const int32_t *map, const int32_t *inv_map)
 {
 	CKD_REQUIRE(ctx && map && inv_map, "null argument");
+	ctx->inputsGen++;
 	const size_t bytes = size_t(ctx->resX)*ctx->resY*2*sizeof(int32_t);
 	CKD_CUDA(cudaMemcpy(ctx->d_polarMap, map, bytes, cudaMemcpyHostToDevice));
 	CKD_CUDA(cudaMemcpy(ctx->d_polarInvMap, inv_map, bytes, cudaMemcpyHostToDevice));
@@ -417,6 +421,9 @@ extern "C" int ckd_clone_inputs(ckd_ctx *dst, const ckd_ctx *src)
 {
 	CKD_REQUIRE(dst && src && dst != src, "two different contexts are needed");
 	CKD_REQUIRE(dst->resX == src->resX && dst->resY == src->resY && dst->device == src->device, "the contexts must have the same resolution and device");
+	dst->frameIndependent = src->frameIndependent;
+	if (dst->clonedFrom == src && dst->clonedGen == src->inputsGen)
+		return CKD_OK;                     // nothing was uploaded or set on the source since the last copy
 	CKD_CUDA(cudaDeviceSynchronize()); // whatever still writes the source's inputs has to land first; this is a set-up call
 	for (int i = 0; i < CKD_IMG_COUNT; ++i)
 	{
@@ -438,7 +445,8 @@ extern "C" int ckd_clone_inputs(ckd_ctx *dst, const ckd_ctx *src)
 	const size_t mapBytes = size_t(src->resX)*src->resY*2*sizeof(int32_t);
 	CKD_CUDA(cudaMemcpy(dst->d_polarMap, src->d_polarMap, mapBytes, cudaMemcpyDeviceToDevice));
 	CKD_CUDA(cudaMemcpy(dst->d_polarInvMap, src->d_polarInvMap, mapBytes, cudaMemcpyDeviceToDevice));
-	dst->frameIndependent = src->frameIndependent;
+	dst->clonedFrom = src;
+	dst->clonedGen = src->inputsGen;
 	return CKD_OK;
 }
 
@@ -696,6 +704,7 @@ extern "C" int ckd_set_image(ckd_ctx *ctx, ckd_image slot, const void *h_pixels,
 	CKD_REQUIRE(ctx && h_pixels, "null argument");
 	CKD_REQUIRE(slot >= 0 && slot < CKD_IMG_COUNT, "bad image slot");
 	CKD_REQUIRE(width > 0 && height > 0 && (bytes_per_pixel == 1 || bytes_per_pixel == 4), "bad image geometry");
+	ctx->inputsGen++;
 	ckd_image_slot &s = ctx->images[slot];
 	if (s.d_pixels) { cudaFree(s.d_pixels); s.d_pixels = nullptr; }
 	const size_t bytes = size_t(width)*height*bytes_per_pixel;

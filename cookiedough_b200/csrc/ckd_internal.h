@@ -71,6 +71,9 @@ struct ckd_ctx {
 	unsigned long long tileLaunches = 0;
 	unsigned long long *d_checksumWork = nullptr; // ckd_frame_checksum scratch, allocated on first use
 	bool frameIndependent = false;    // ckd_set_frame_independent: no pixel of a frame may depend on an earlier frame
+	unsigned long long inputsGen = 1; // bumped by every setter of an image or table: lets ckd_clone_inputs skip what it has already copied
+	const ckd_ctx *clonedFrom = nullptr;
+	unsigned long long clonedGen = 0;
 
 	ckd_image_slot images[CKD_IMG_COUNT];
 

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--frames", type=int, default=600)
     ap.add_argument("--res", type=int, default=2160)
     ap.add_argument("--ring", type=int, default=6)
+    ap.add_argument("--lanes", type=int, default=2, help="contexts per GPU the rank's frames alternate between (two frames in flight)")
     ap.add_argument("--slots", type=int, default=0, help="frames of the gather's slot ring in rank 0's HBM (0: 4 per rank, at least 8)")
     args = ap.parse_args()
 
@@ -59,7 +60,7 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     # rank r renders the frames i % world == r and pushes them; rank 0 pops every frame in order into the open sink
-    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=1, pop_mode=capi.GATHER_CHECKSUM | capi.GATHER_TO_HOST, host_ring=None)
+    host.timeline_render(times, rank=rank, world=world, gather=gather, passes=1, pop_mode=capi.GATHER_CHECKSUM | capi.GATHER_TO_HOST, host_ring=None, lanes=args.lanes)
     ctx.sync()
     gather.status()
     if rank == 0:
