@@ -87,6 +87,42 @@ __device__ __forceinline__ unsigned overlay_chan(unsigned bottom, unsigned top)
 	return bottom < 128 ? (2*bottom*top/255) : (255 - 2*(255-bottom)*(255-top)/255);
 }
 
+// ---- the three colour channels of a pixel at once ---------------------------------------------------------------------------
+// SoftLightBlend and the Overlay channel both have the shape  B < 128 ? f(a, B) : 255 - f(255 - a, 255 - B)  with f = 2*a*B/256
+// (SoftLight, a = A/2 + 64) or 2*B*top/255 (Overlay).  255 - x of a byte is x ^ 0xff, so with m = 0xff in every byte whose B is
+// >= 128 (one PRMT: sign replication) both branches become  f(a ^ m, B ^ m) ^ m  and everything except the per-channel product
+// runs on all bytes of the word.  2*(B ^ m) <= 254 and a <= 255 keep a product below 2^16: its byte 1 is the >> 8, the /255 is
+// the usual multiply-shift (exact below 2^16).  Checked against the scalar forms over 2 M random pixel pairs and the byte edge
+// values before it went in; the golden and live post-op tests pin it on the device.
+__device__ __forceinline__ uint32_t sign_bytes(uint32_t x)
+{
+	uint32_t m;
+	asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(m) : "r"(x));
+	return m;
+}
+
+// (soft_light(R1, R2) << 16) | (soft_light(G1, G2) << 8) | soft_light(B1, B2), s = source pixel (A), d = destination pixel (B)
+__device__ __forceinline__ uint32_t soft_light3(uint32_t s, uint32_t d)
+{
+	const uint32_t m = sign_bytes(d);
+	const uint32_t a = (((s >> 1) & 0x7f7f7f7fu) + 0x40404040u) ^ m;   // A/2 + 64 per byte (<= 191: no carry), mirrored where B >= 128
+	const uint32_t b2 = ((d ^ m) << 1) & 0xfefefefeu;                  // 2*B' per byte (B' <= 127)
+	const uint32_t p0 = (a & 0xffu)*(b2 & 0xffu), p1 = ((a >> 8) & 0xffu)*((b2 >> 8) & 0xffu), p2 = ((a >> 16) & 0xffu)*((b2 >> 16) & 0xffu);
+	const uint32_t t = __byte_perm(__byte_perm(p0, p1, 0x0051), p2, 0x7510); // byte 1 of each product; p2's byte 3 is zero
+	return t ^ (m & 0x00ffffffu);
+}
+
+// (overlay_chan(R2, R1) << 16) | (overlay_chan(G2, G1) << 8) | overlay_chan(B2, B1), bottom = destination, top = source
+__device__ __forceinline__ uint32_t overlay3(uint32_t bottom, uint32_t top)
+{
+	const uint32_t m = sign_bytes(bottom);
+	const uint32_t b2 = ((bottom ^ m) << 1) & 0xfefefefeu, t = top ^ m;
+	const uint32_t q0 = ((b2 & 0xffu)*(t & 0xffu)*0x8081u) >> 23;      // x/255 for x < 2^16
+	const uint32_t q1 = (((b2 >> 8) & 0xffu)*((t >> 8) & 0xffu)*0x8081u) >> 23;
+	const uint32_t q2 = (((b2 >> 16) & 0xffu)*((t >> 16) & 0xffu)*0x8081u) >> 23;
+	return (q0 | (q1 << 8) | (q2 << 16)) ^ (m & 0x00ffffffu);
+}
+
 template <int OP> __device__ __forceinline__ uint32_t blend_px(uint32_t d, uint32_t s, const BlendParams &p)
 {
 	const unsigned A2 = d >> 24, R2 = (d >> 16) & 0xff, G2 = (d >> 8) & 0xff, B2 = d & 0xff;
@@ -105,15 +141,12 @@ template <int OP> __device__ __forceinline__ uint32_t blend_px(uint32_t d, uint3
 	if (OP == CKD_SUB32) return subs_u8x4(d, s); // util.cpp:188-190
 	if (OP == CKD_MIXOVER32)
 	{
-		// util.cpp:148-177
-		const unsigned iA1 = 0xff - A1;
-		unsigned R = ((R1*(0xff-iA1))>>8) + ((R2*iA1)>>8);
-		unsigned G = ((G1*(0xff-iA1))>>8) + ((G2*iA1)>>8);
-		unsigned B = ((B1*(0xff-iA1))>>8) + ((B2*iA1)>>8);
-		if (R > 255) R = 255;
-		if (G > 255) G = 255;
-		if (B > 255) B = 255;
-		return (R<<16)|(G<<8)|B;
+		// util.cpp:148-177: c = ((c1*(0xff - iA1)) >> 8) + ((c2*iA1) >> 8) with iA1 = 0xff - A1; the two weights add up to 255, so the
+		// sum stays <= 254 and the clamp at 255 of the reference cannot act.  R and B share a multiply (two 16-bit lanes).
+		const uint32_t ia = 0xffu - A1;
+		const uint32_t rb = ((((s & 0x00ff00ffu)*A1) >> 8) & 0x00ff00ffu) + ((((d & 0x00ff00ffu)*ia) >> 8) & 0x00ff00ffu);
+		const uint32_t g = ((G1*A1) >> 8) + ((G2*ia) >> 8);
+		return rb | (g << 8);
 	}
 	if (OP == CKD_EXCL32)
 	{
@@ -126,13 +159,13 @@ template <int OP> __device__ __forceinline__ uint32_t blend_px(uint32_t d, uint3
 	if (OP == CKD_SOFTLIGHT32)
 	{
 		// util.cpp:242-271
-		const unsigned R = soft_light(R1, R2), G = soft_light(G1, G2), B = soft_light(B1, B2);
-		return (A2<<24)|(R<<16)|(G<<8)|B;
+		return (d & 0xff000000u) | soft_light3(s, d);
 	}
 	if (OP == CKD_SOFTLIGHT32A || OP == CKD_SOFTLIGHT32AA)
 	{
 		// util.cpp:274-346: the lerp runs in *unsigned* 32-bit arithmetic; wrapped bits spill into the neighbouring fields
-		unsigned R = soft_light(R1, R2), G = soft_light(G1, G2), B = soft_light(B1, B2);
+		const uint32_t sl = soft_light3(s, d);
+		unsigned R = (sl >> 16) & 0xffu, G = (sl >> 8) & 0xffu, B = sl & 0xffu;
 		const unsigned a = (OP == CKD_SOFTLIGHT32A) ? A1 : p.u0;
 		R = R2 + (((R-R2)*a)>>8);
 		G = G2 + (((G-G2)*a)>>8);
@@ -144,12 +177,13 @@ template <int OP> __device__ __forceinline__ uint32_t blend_px(uint32_t d, uint3
 	if (OP == CKD_OVERLAY32)
 	{
 		// util.cpp:434-456
-		return (overlay_chan(R2, R1)<<16)|(overlay_chan(G2, G1)<<8)|overlay_chan(B2, B1);
+		return overlay3(d, s);
 	}
 	if (OP == CKD_OVERLAY32A)
 	{
 		// util.cpp:485-513
-		const unsigned nR = overlay_chan(R2, R1), nG = overlay_chan(G2, G1), nB = overlay_chan(B2, B1);
+		const uint32_t ov = overlay3(d, s);
+		const unsigned nR = (ov >> 16) & 0xffu, nG = (ov >> 8) & 0xffu, nB = ov & 0xffu;
 		const unsigned R = R2 + (((nR-R2)*A1)>>8);
 		const unsigned G = G2 + (((nG-G2)*A1)>>8);
 		const unsigned B = B2 + (((nB-B2)*A1)>>8);
@@ -163,13 +197,15 @@ template <int OP> __device__ __forceinline__ uint32_t blend_px(uint32_t d, uint3
 	}
 	if (OP == CKD_MULSRC32)
 	{
-		// util.cpp:605-618: (src*dest)>>8 per channel, alpha included
-		return ((A1*A2)>>8)<<24 | ((R1*R2)>>8)<<16 | ((G1*G2)>>8)<<8 | ((B1*B2)>>8);
+		// util.cpp:605-618: (src*dest)>>8 per channel, alpha included: byte 1 of each 16-bit product
+		return __byte_perm(__byte_perm(B1*B2, G1*G2, 0x0051), __byte_perm(R1*R2, A1*A2, 0x0051), 0x5410);
 	}
 	if (OP == CKD_MULSRC32A)
 	{
-		// util.cpp:620-634: (srcAlpha*dest)>>8 per channel
-		return ((A1*A2)>>8)<<24 | ((A1*R2)>>8)<<16 | ((A1*G2)>>8)<<8 | ((A1*B2)>>8);
+		// util.cpp:620-634: (srcAlpha*dest)>>8 per channel: two 16-bit lanes per multiply (a product is < 2^16: no carry between lanes)
+		const uint32_t rb = (((d & 0x00ff00ffu)*A1) >> 8) & 0x00ff00ffu;
+		const uint32_t ag = (((d >> 8) & 0x00ff00ffu)*A1) & 0xff00ff00u;
+		return rb | ag;
 	}
 	return d;
 }
