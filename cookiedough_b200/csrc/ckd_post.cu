@@ -568,12 +568,32 @@ __device__ __forceinline__ uint32_t polar_blend(uint32_t d, uint32_t s)
 
 // HALO: SoftLight32A(pDest, pHalo) (util.cpp:274-346) applied to the remapped pixel before it is stored -- the ball's halo layer
 // (ball.cpp:357-361) in the same pass instead of a second read-modify-write of the frame
-template <bool ALPHA, bool HALO> __global__ void __launch_bounds__(256) polar_blit_kernel(uint32_t *pDest, const uint32_t *__restrict__ pSrc, const int4 *__restrict__ pMap, unsigned numQuads, unsigned resX,
+// TILED: a warp covers 32 pixels x 4 rows instead of 128 pixels of one row (a block 64 x 16): the footprint of its gathers in the
+// source is a compact patch instead of a long arc, fewer distinct sectors per gather instruction (the kernel is L1TEX bound)
+template <bool ALPHA, bool HALO, int TILED> __global__ void __launch_bounds__(256) polar_blit_kernel(uint32_t *pDest, const uint32_t *__restrict__ pSrc, const int4 *__restrict__ pMap, unsigned numQuads, unsigned resX,
 	const uint4 *__restrict__ pHalo)
 {
-	const unsigned q = blockIdx.x*blockDim.x + threadIdx.x;
-	if (q >= numQuads)
-		return;
+	// TILED = 0: linear; else log2 of the quads a warp covers per row + 1 (5: 16 quads x 2 rows, 4: 8 x 4, 3: 4 x 8, 2: 2 x 16, 1: 1 x 32).
+	// Measured at 4K (profiles/r02_polar_variants.txt): linear 45.7 us, 8 x 4 37.5, 4 x 8 37.2, 2 x 16 39.6, 1 x 32 54.0
+	unsigned q;
+	if (TILED)
+	{
+		constexpr unsigned QW = 1u << (TILED > 0 ? TILED - 1 : 0), RW = 32u/QW; // quads per warp row, rows per warp
+		const unsigned quadsPerRow = resX >> 2, rows = numQuads/quadsPerRow;
+		const unsigned tilesX = (quadsPerRow + 2*QW - 1)/(2*QW);
+		const unsigned bx = blockIdx.x % tilesX, by = blockIdx.x / tilesX;
+		const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		const unsigned qx = bx*(2*QW) + (warp & 1)*QW + (lane & (QW-1)), y = by*(4*RW) + (warp >> 1)*RW + lane/QW;
+		if (qx >= quadsPerRow || y >= rows)
+			return;
+		q = y*quadsPerRow + qx;
+	}
+	else
+	{
+		q = blockIdx.x*blockDim.x + threadIdx.x;
+		if (q >= numQuads)
+			return;
+	}
 	const int4 m0 = __ldg(pMap + size_t(q)*2), m1 = __ldg(pMap + size_t(q)*2 + 1);
 	uint4 halo = make_uint4(0, 0, 0, 0);
 	if (HALO) halo = __ldg(pHalo + q);
@@ -615,6 +635,36 @@ template <bool ALPHA> __global__ void __launch_bounds__(256) polar_blit_kernel_1
 	pDest[i] = out;
 }
 
+constexpr int kPolarTile = 4; // a warp covers 8 quads (32 pixels) x 4 rows
+
+// grid of the tiled kernel for `rows` rows of quadsPerRow quads
+template <int T> static unsigned PolarTiles(unsigned quadsPerRow, unsigned rows)
+{
+	constexpr unsigned QW = 1u << (T - 1), RW = 32u/QW;
+	return ((quadsPerRow + 2*QW - 1)/(2*QW))*((rows + 4*RW - 1)/(4*RW));
+}
+
+// one remap of `rows` whole rows starting at the given pointers (the banded tail passes row bands)
+static void LaunchPolarRows(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, const int4 *pMap, unsigned resX, unsigned rows, bool alpha, const uint32_t *d_halo)
+{
+	const unsigned quadsPerRow = resX/4, numQuads = quadsPerRow*rows;
+	static const int variant = getenv("CKD_POLAR_VARIANT") ? atoi(getenv("CKD_POLAR_VARIANT")) : 0; // tuning: 2 linear, 4..8 tile shapes
+	const uint4 *halo = reinterpret_cast<const uint4 *>(d_halo);
+	#define CKD_POLAR(T, GRID) { if (halo) polar_blit_kernel<true, true, T><<<GRID, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, resX, halo); \
+		else if (alpha) polar_blit_kernel<true, false, T><<<GRID, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, resX, nullptr); \
+		else polar_blit_kernel<false, false, T><<<GRID, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, resX, nullptr); }
+	switch (variant)
+	{
+	case 2: CKD_POLAR(0, ckd_div_up(numQuads, 256)) break;
+	case 5: CKD_POLAR(3, PolarTiles<3>(quadsPerRow, rows)) break;
+	case 6: CKD_POLAR(2, PolarTiles<2>(quadsPerRow, rows)) break;
+	case 7: CKD_POLAR(1, PolarTiles<1>(quadsPerRow, rows)) break;
+	case 8: CKD_POLAR(5, PolarTiles<5>(quadsPerRow, rows)) break;
+	default: CKD_POLAR(kPolarTile, PolarTiles<kPolarTile>(quadsPerRow, rows)) break;
+	}
+	#undef CKD_POLAR
+}
+
 static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse, bool alpha)
 {
 	CKD_REQUIRE(ctx && d_dest && d_src, "null argument");
@@ -622,10 +672,9 @@ static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, in
 	CKD_REQUIRE(0 == (reinterpret_cast<uintptr_t>(d_dest) & 15), "destination must be 16-byte aligned");
 	const unsigned numQuads = unsigned(size_t(ctx->resX)*ctx->resY/4);
 	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap : ctx->d_polarMap);
-	const unsigned blocks = ckd_div_up(numQuads, 256);
 	ckd_prof_begin(ctx, alpha ? "polar_blit_a" : "polar_blit", (alpha ? 20.0 : 16.0)*ctx->resX*ctx->resY);
 	static const int variant = getenv("CKD_POLAR_VARIANT") ? atoi(getenv("CKD_POLAR_VARIANT")) : 0;
-	if (variant == 1)
+	if (variant == 1 || 0 != (ctx->resX & 3))
 	{
 		const unsigned numPixels = numQuads*4;
 		const int2 *pMap2 = reinterpret_cast<const int2 *>(pMap);
@@ -634,10 +683,8 @@ static int LaunchPolar(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, in
 		else
 			polar_blit_kernel_1px<false><<<ckd_div_up(numPixels, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap2, numPixels, unsigned(ctx->resX));
 	}
-	else if (alpha)
-		polar_blit_kernel<true, false><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX), nullptr);
 	else
-		polar_blit_kernel<false, false><<<blocks, 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX), nullptr);
+		LaunchPolarRows(ctx, d_dest, d_src, pMap, unsigned(ctx->resX), unsigned(ctx->resY), alpha, nullptr);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
 }
@@ -658,9 +705,8 @@ int ckd_polar_tail(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int in
 		if (fuseHalo)
 		{
 			CKD_REQUIRE(d_dest != d_src, "polar blit cannot run in place");
-			const unsigned numQuads = numPixels/4;
 			ckd_prof_begin(ctx, "polar_blit_a_halo", 24.0*numPixels);
-			polar_blit_kernel<true, true><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->resX), reinterpret_cast<const uint4 *>(d_softLightSrc));
+			LaunchPolarRows(ctx, d_dest, d_src, pMap, unsigned(ctx->resX), unsigned(ctx->resY), true, d_softLightSrc);
 			CKD_CHECK_LAUNCH(ctx);
 			return CKD_OK;
 		}
@@ -675,14 +721,8 @@ int ckd_polar_tail(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int in
 		if (y1 <= y0)
 			continue;
 		const size_t offset = size_t(y0)*ctx->resX, count = size_t(y1 - y0)*ctx->resX;
-		const unsigned numQuads = unsigned(count/4);
 		ckd_prof_begin(ctx, fuseHalo ? "polar_blit_a_halo" : alpha ? "polar_blit_a" : "polar_blit", (fuseHalo ? 24.0 : alpha ? 20.0 : 16.0)*double(count));
-		if (fuseHalo)
-			polar_blit_kernel<true, true><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX), reinterpret_cast<const uint4 *>(d_softLightSrc + offset));
-		else if (alpha)
-			polar_blit_kernel<true, false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX), nullptr);
-		else
-			polar_blit_kernel<false, false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest + offset, d_src, pMap + offset/2, numQuads, unsigned(ctx->resX), nullptr);
+		LaunchPolarRows(ctx, d_dest + offset, d_src, pMap + offset/2, unsigned(ctx->resX), unsigned(y1 - y0), alpha, fuseHalo ? d_softLightSrc + offset : nullptr);
 		CKD_CHECK_LAUNCH(ctx);
 		if (d_softLightSrc && !fuseHalo)
 			CKD_TRY(ckd_blend(ctx, CKD_SOFTLIGHT32A, d_dest + offset, d_softLightSrc + offset, unsigned(count), 0.f, 0));
@@ -707,7 +747,7 @@ extern "C" int ckd_polar_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t
 	const unsigned numQuads = unsigned(size_t(ctx->fxX)*ctx->fxY/4); // fxResX is a multiple of 4 (fx-blitter.h:18)
 	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap2x2 : ctx->d_polarMap2x2);
 	ckd_prof_begin(ctx, "polar_blit_2x2", 16.0*ctx->fxX*ctx->fxY);
-	polar_blit_kernel<false, false><<<ckd_div_up(numQuads, 256), 256, 0, ctx->stream>>>(d_dest, d_src, pMap, numQuads, unsigned(ctx->fxX), nullptr);
+	LaunchPolarRows(ctx, d_dest, d_src, pMap, unsigned(ctx->fxX), unsigned(ctx->fxY), false, nullptr);
 	CKD_CHECK_LAUNCH(ctx);
 	return CKD_OK;
 }
