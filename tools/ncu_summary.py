@@ -37,7 +37,7 @@ def bench_name(kernel):
     if "ball_kernel" in kernel:
         return "voxel_ball_beams" if re.search(r"ball_kernel<\(bool\)1>|ball_kernel<true>|ball_kernel<1>", kernel) else "voxel_ball"
     if "polar_blit" in kernel:
-        if re.search(r"<\(bool\)1, \(bool\)1>|<true, true>|<1, 1>", kernel):
+        if re.search(r"<\(bool\)1, \(bool\)1[,>]|<true, true[,>]|<1, 1[,>]", kernel):
             return "polar_blit_a_halo"
         return "polar_blit_a" if re.search(r"<\(bool\)1[,>]|<true[,>]|<1[,>]", kernel) else "polar_blit"
     if "old_blur" in kernel:
