@@ -744,8 +744,7 @@ extern "C" int ckd_polar_blit_2x2(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t
 	CKD_REQUIRE(d_dest != d_src, "polar blit cannot run in place");
 	CKD_REQUIRE(0 == (reinterpret_cast<uintptr_t>(d_dest) & 15), "destination must be 16-byte aligned");
 	CKD_TRY(ckd_ensure_polar_maps_2x2(ctx));
-	const unsigned numQuads = unsigned(size_t(ctx->fxX)*ctx->fxY/4); // fxResX is a multiple of 4 (fx-blitter.h:18)
-	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap2x2 : ctx->d_polarMap2x2);
+	const int4 *pMap = reinterpret_cast<const int4 *>(inverse ? ctx->d_polarInvMap2x2 : ctx->d_polarMap2x2); // fxResX is a multiple of 4 (fx-blitter.h:18)
 	ckd_prof_begin(ctx, "polar_blit_2x2", 16.0*ctx->fxX*ctx->fxY);
 	LaunchPolarRows(ctx, d_dest, d_src, pMap, unsigned(ctx->fxX), unsigned(ctx->fxY), false, nullptr);
 	CKD_CHECK_LAUNCH(ctx);
