@@ -56,3 +56,17 @@ def test_committed_counts_are_consistent():
         total = sum(k[c] for c in ("fadd", "fmul", "fdiv", "fsqrt", "frsqrt", "fcmp", "fminmax", "fcvt", "libm_calls"))
         assert abs(total - k["ops_per_fx_pixel"]) < 1e-6, name
         assert k["frame_identical_to_plain_oracle"] is True, name
+
+
+def test_bench_reads_the_reference_counted_denominators():
+    sys.path.insert(0, REPO)
+    import bench
+    ops, addmul, source = bench.flop_table()
+    assert "counted on the reference" in source
+    with open(os.path.join(REPO, "profiles", "r02_ref_fp_ops.json")) as f:
+        doc = json.load(f)
+    for name in bench.FLOP_FALLBACK:
+        assert ops[name] == doc["kernels"][name]["ops_per_fx_pixel"]
+        assert addmul[name] == doc["kernels"][name]["fadd"] + doc["kernels"][name]["fmul"]
+    # both arms of the bench describe the same workload
+    assert bench.suite_config() == {"workload": "effect-suite-4k", "res": [3840, 2160], "effects": [s[0] for s in bench.SUITE]}
