@@ -102,7 +102,7 @@ def flop_table():
 LIMITER = {
     "raymarch": "instruction issue: FMUL/FADD chains without FMA contraction (bit parity) + the non-FP instructions of every LUT lookup",
     "old_blur": "integer ALU pipe + the dependent chain of the saturating in-place recurrence; DRAM traffic = algorithmic bytes",
-    "voxel": "L2 gather latency of the height/colour map samples (warp per ray)",
+    "voxel": "L2 gather latency of the height/colour map samples (warp per ray; the landscape: issue slots + L1 look-ups of one full wave)",
     "polar_blit": "L1TEX: 16 four-byte texel gathers per thread fill the LSU queue (l1tex 75 %, lg/mio throttle; profiles/r02_notes.md); DRAM traffic = algorithmic bytes",
     "fx_blit_2x2": "L2 write-back of the 33 MB frame",
     "blend": "HBM / L2 bandwidth",

@@ -21,7 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-Wall,-Wno-unused-function",
-    "-Xptxas", "-v",
+    "-Xptxas", "-v", *os.environ.get("CKD_EXTRA_NVCC", "").split(),
 ]
 
 

@@ -369,7 +369,10 @@ extern "C" void ckd_destroy(ckd_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	for (auto &slot : ctx->images)
+	{
+		ckd_release_gather_texture(slot);
 		if (slot.d_pixels) cudaFree(slot.d_pixels);
+	}
 	if (ctx->d_rsqrtTab) cudaFree(ctx->d_rsqrtTab);
 	if (ctx->d_polarMap2x2) cudaFree(ctx->d_polarMap2x2);
 	if (ctx->d_checksumWork) cudaFree(ctx->d_checksumWork);
@@ -429,9 +432,12 @@ extern "C" int ckd_clone_inputs(ckd_ctx *dst, const ckd_ctx *src)
 	{
 		const ckd_image_slot &from = src->images[i];
 		ckd_image_slot &to = dst->images[i];
+		ckd_release_gather_texture(to);
 		if (to.d_pixels) { cudaFree(to.d_pixels); to.d_pixels = nullptr; }
 		to = from;
 		to.d_pixels = nullptr;
+		to.gatherArray = nullptr; // the twin is made from this context's own copy on first use
+		to.gatherTex = 0;
 		if (nullptr == from.d_pixels)
 			continue;
 		const size_t bytes = size_t(from.width)*from.height*from.bpp + 256;
@@ -706,6 +712,7 @@ extern "C" int ckd_set_image(ckd_ctx *ctx, ckd_image slot, const void *h_pixels,
 	CKD_REQUIRE(width > 0 && height > 0 && (bytes_per_pixel == 1 || bytes_per_pixel == 4), "bad image geometry");
 	ctx->inputsGen++;
 	ckd_image_slot &s = ctx->images[slot];
+	ckd_release_gather_texture(s);
 	if (s.d_pixels) { cudaFree(s.d_pixels); s.d_pixels = nullptr; }
 	const size_t bytes = size_t(width)*height*bytes_per_pixel;
 	CKD_CUDA(cudaMalloc(&s.d_pixels, bytes + 256)); // slack like the harness' loader
@@ -714,6 +721,41 @@ extern "C" int ckd_set_image(ckd_ctx *ctx, ckd_image slot, const void *h_pixels,
 	s.width = width; s.height = height; s.bpp = bytes_per_pixel;
 	s.firstPixel = 0;
 	memcpy(&s.firstPixel, h_pixels, std::min<size_t>(4, bytes));
+	return CKD_OK;
+}
+
+void ckd_release_gather_texture(ckd_image_slot &slot)
+{
+	if (slot.gatherTex) { cudaDestroyTextureObject(slot.gatherTex); slot.gatherTex = 0; }
+	if (slot.gatherArray) { cudaFreeArray(slot.gatherArray); slot.gatherArray = nullptr; }
+}
+
+// The voxel casters read a 2x2 footprint per map and step, along rays of any direction.  From linear memory a ray that runs
+// across the rows touches a different 128-byte line with every lane and tap (up to 32 tag look-ups per load, 8 loads per step);
+// a block-linear array read with tex2Dgather delivers the footprint in one request and keeps neighbouring rows in one tile.
+// Texels are single-channel (L8, or the BGRA word as one 32-bit channel), addressing wraps like the reference's '& mapAnd'.
+int ckd_gather_texture(ckd_ctx *ctx, int slot, cudaTextureObject_t *pTex)
+{
+	CKD_REQUIRE(ctx && pTex && slot >= 0 && slot < CKD_IMG_COUNT, "bad image slot");
+	ckd_image_slot &s = ctx->images[slot];
+	CKD_REQUIRE(s.d_pixels && (s.bpp == 1 || s.bpp == 4), "image not set");
+	if (!s.gatherTex)
+	{
+		const cudaChannelFormatDesc desc = cudaCreateChannelDesc(8*s.bpp, 0, 0, 0, cudaChannelFormatKindUnsigned);
+		CKD_CUDA(cudaMallocArray(&s.gatherArray, &desc, size_t(s.width), size_t(s.height), cudaArrayTextureGather));
+		const size_t pitch = size_t(s.width)*s.bpp;
+		CKD_CUDA(cudaMemcpy2DToArray(s.gatherArray, 0, 0, s.d_pixels, pitch, pitch, size_t(s.height), cudaMemcpyDeviceToDevice));
+		cudaResourceDesc res = {};
+		res.resType = cudaResourceTypeArray;
+		res.res.array.array = s.gatherArray;
+		cudaTextureDesc tex = {};
+		tex.addressMode[0] = tex.addressMode[1] = cudaAddressModeWrap;
+		tex.filterMode = cudaFilterModePoint;
+		tex.readMode = cudaReadModeElementType;
+		tex.normalizedCoords = 1;
+		CKD_CUDA(cudaCreateTextureObject(&s.gatherTex, &res, &tex, nullptr));
+	}
+	*pTex = s.gatherTex;
 	return CKD_OK;
 }
 

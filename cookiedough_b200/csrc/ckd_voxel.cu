@@ -86,6 +86,24 @@ __device__ __forceinline__ RawSample fetch_sample(const uint8_t *__restrict__ he
 	return r;
 }
 
+// the same texels through tex2Dgather (ckd_gather_texture; the landscape, whose 26 warps per SM are bound by L1 tag look-ups --
+// the tunnelscape at 15 warps per SM is not, and measured 2 % slower this way): the footprint of (U0, V0) is addressed by the corner its four texels
+// share, (U0+1, V0+1)/size -- exact in float for power-of-two maps, half a texel away from any rounding boundary -- and comes back
+// as .w = (U0,V0), .z = (U0+1,V0), .x = (U0,V0+1), .y = (U0+1,V0+1), with the reference's '& mapAnd' as wrap addressing
+__device__ __forceinline__ RawSample fetch_sample_tex(cudaTextureObject_t heightTex, cudaTextureObject_t colorTex, const uint32_t *__restrict__ fogGradient,
+	unsigned iStep, int curX, int curY, unsigned mapAnd, float invMapSize)
+{
+	const float u = (float((unsigned(curX) >> 8) & mapAnd) + 1.f)*invMapSize, v = (float((unsigned(curY) >> 8) & mapAnd) + 1.f)*invMapSize;
+	const uchar4 h = tex2Dgather<uchar4>(heightTex, u, v, 0);
+	const uint4 c = tex2Dgather<uint4>(colorTex, u, v, 0);
+	RawSample r;
+	r.h[0] = h.w; r.h[1] = h.z; r.h[2] = h.x; r.h[3] = h.y;
+	r.c[0] = c.w; r.c[1] = c.z; r.c[2] = c.x; r.c[3] = c.y;
+	r.fog = __ldg(fogGradient + (iStep >> 1));
+	r.fu = unsigned(curX) & 0xff; r.fv = unsigned(curY) & 0xff;
+	return r;
+}
+
 // ---- cspanISSE16 (cspan.h:47-78) --------------------------------------------------------------------------------------
 // 16.16 fixed-point ramp from colour A to colour B over 'length' pixels of which the last... 'drawLength' are drawn, with
 // the reference's pmaddwd / pmuldq quirks restated literally: the divisor and the deltas are read as
@@ -134,23 +152,20 @@ __device__ __forceinline__ uint32_t span_pixel(const SpanRamp &r, unsigned j)
 // CKD_SHORT_SPAN overrides it for sweeps)
 __constant__ unsigned c_shortSpan = 48;
 #define kShortSpan c_shortSpan
+// landscape: instruction estimates of the two span emitters (per pixel of the longest span / per batch of 32 pixels), see emit_tiled_spans
+__constant__ unsigned c_tiledPerLane = 12, c_tiledPerBatch = 45;
 
-// Emits the spans of one 32-step chunk into a line buffer.  Lane parameters: visible, pos (index of the span's first
-// pixel in the line), dir (+1/-1 index increment), length/drawLength and the two colours; 'limit' clips writes to the line.
-__device__ __forceinline__ void emit_spans(uint32_t *line, int limit, bool visible, int pos, int dir, unsigned length, unsigned drawLength, const Color16 &A, const Color16 &B)
+// ramp of a visible lane's span and whether it is 'plain': a ramp whose two end points -- evaluated without the 32-bit
+// wrap-around -- lie within [0, 2^24) cannot wrap or leave that range in between (it is linear): every channel value is then
+// byte 2 of its accumulator, the packusdw / packuswb clamps of span_pixel cannot act, and a pixel costs four additions (or
+// multiply-adds) and three byte permutes.  Anything else (the ball's over-bright colours, the pmaddwd quirks of steep ramps)
+// takes the literal path.
+__device__ __forceinline__ bool span_prepare(SpanRamp &ramp, bool visible, unsigned length, unsigned drawLength, const Color16 &A, const Color16 &B)
 {
-	const int lane = threadIdx.x & 31;
-	SpanRamp ramp;
-	if (visible)
-		ramp = span_setup(length, drawLength, A, B);
-
-	// A ramp whose two end points -- evaluated without the 32-bit wrap-around -- lie within [0, 2^24) cannot wrap or leave that
-	// range in between (it is linear): every channel value is then byte 2 of its accumulator, the packusdw / packuswb clamps of
-	// span_pixel cannot act, and a pixel costs four additions (or multiply-adds) and three byte permutes.  Anything else (the
-	// ball's over-bright colours, the pmaddwd quirks of steep ramps) takes the literal path.
 	bool plain = visible;
 	if (visible)
 	{
+		ramp = span_setup(length, drawLength, A, B);
 		#pragma unroll
 		for (int i = 0; i < 4; ++i)
 		{
@@ -158,6 +173,12 @@ __device__ __forceinline__ void emit_spans(uint32_t *line, int limit, bool visib
 			plain = plain && ramp.from[i] < (1u << 24) && last >= 0 && last < (1ll << 24);
 		}
 	}
+	return plain;
+}
+
+__device__ __forceinline__ void emit_prepared_spans(uint32_t *line, int limit, bool visible, int pos, int dir, unsigned drawLength, const SpanRamp &ramp, bool plain)
+{
+	const int lane = threadIdx.x & 31;
 
 	if (visible && drawLength <= kShortSpan)
 	{
@@ -220,6 +241,54 @@ __device__ __forceinline__ void emit_spans(uint32_t *line, int limit, bool visib
 	}
 }
 
+// Emits the spans of one 32-step chunk into a line buffer.  Lane parameters: visible, pos (index of the span's first
+// pixel in the line), dir (+1/-1 index increment), length/drawLength and the two colours; 'limit' clips writes to the line.
+__device__ __forceinline__ void emit_spans(uint32_t *line, int limit, bool visible, int pos, int dir, unsigned length, unsigned drawLength, const Color16 &A, const Color16 &B)
+{
+	SpanRamp ramp;
+	const bool plain = span_prepare(ramp, visible, length, drawLength, A, B);
+	emit_prepared_spans(line, limit, visible, pos, dir, drawLength, ramp, plain);
+}
+
+// The landscape's spans of one chunk tile an interval: a visible step draws [height, lowest height before it), so together the
+// visible steps cover [lowest after the chunk, lowest before it) without gaps or overlap.  emit_spans pays for the LONGEST span
+// of the chunk (every lane walks its own); here the lanes share the chunk's pixels instead -- lane k takes pixel lo + k, finds
+// the step that owns it with a binary search over the (monotone) running minimum and evaluates that step's ramp at its offset:
+// the cost follows the number of pixels on screen.  The caller picks whichever is cheaper for the chunk.
+//   m       = running minimum including this lane's step (= its height where the step is visible)
+//   [lo,hi) = the chunk's interval clipped to the line
+__device__ __forceinline__ void emit_tiled_spans(uint32_t *line, int lo, int hi, int m, const SpanRamp &ramp, unsigned plainMask)
+{
+	const int lane = threadIdx.x & 31;
+	for (int y0 = lo; y0 < hi; y0 += 32)
+	{
+		const int y = min(y0 + lane, hi - 1);
+		int owner = 0; // number of leading steps whose running minimum is still above y = the first step that reaches it
+		#pragma unroll
+		for (int s = 16; s; s >>= 1)
+		{
+			const int v = __shfl_sync(kFull, m, owner + s - 1);
+			if (v > y) owner += s;
+		}
+		const unsigned j = unsigned(y - __shfl_sync(kFull, m, owner));
+		SpanRamp r;
+		#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			r.from[i] = __shfl_sync(kFull, ramp.from[i], owner);
+			r.step[i] = __shfl_sync(kFull, ramp.step[i], owner);
+		}
+		uint32_t px;
+		if ((plainMask >> owner) & 1u)
+			px = __byte_perm(__byte_perm(r.from[0] + j*uint32_t(r.step[0]), r.from[1] + j*uint32_t(r.step[1]), 0x0062),
+				__byte_perm(r.from[2] + j*uint32_t(r.step[2]), r.from[3] + j*uint32_t(r.step[3]), 0x0062), 0x5410);
+		else
+			px = span_pixel(r, j);
+		if (y0 + lane < hi)
+			line[y] = px;
+	}
+}
+
 // warp exclusive prefix min / max with carry-in (lane i gets op(carry, v_0..v_{i-1})); returns the inclusive total via 'total'
 __device__ __forceinline__ int warp_excl_min(int v, int carry, int &total)
 {
@@ -261,8 +330,10 @@ __device__ __forceinline__ int adds16(int a, int b) { return min(a + b, 65535); 
 // Landscape -- landscape.cpp:56-192
 // -------------------------------------------------------------------------------------------------------------
 
-constexpr int kScapeColsPerBlock = 8;
+constexpr int kScapeColsPerBlock = 8;     // default columns (= warps) per CTA; the launch picks what fills the machine in whole waves
+constexpr int kScapeMaxColsPerBlock = 13;   // with two CTAs per SM in the launch bounds: 72 registers
 constexpr unsigned kScapeRayLength = 512; // landscape.cpp:43
+
 
 struct LandscapeFrame
 {
@@ -275,12 +346,13 @@ struct LandscapeFrame
 	uint32_t clearColor;      // s_pFogGradient[0]
 };
 
-__global__ void __launch_bounds__(kScapeColsPerBlock*32) landscape_kernel(uint32_t *__restrict__ pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
+__global__ void __launch_bounds__(kScapeMaxColsPerBlock*32, 2) landscape_kernel(uint32_t *__restrict__ pDest, cudaTextureObject_t heightTex, cudaTextureObject_t colorTex, const uint32_t *__restrict__ colorMap,
 	const uint32_t *__restrict__ fogGradient, const LandscapeFrame f, int lineStride)
 {
-	extern __shared__ uint32_t s_lines[]; // [kScapeColsPerBlock][lineStride]
+	extern __shared__ uint32_t s_lines[]; // [columns per CTA][lineStride]
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const unsigned iRay = blockIdx.x*kScapeColsPerBlock + warp;
+	const int colsPerBlock = int(blockDim.x >> 5);
+	const unsigned iRay = blockIdx.x*colsPerBlock + warp;
 	uint32_t *line = s_lines + warp*lineStride;
 
 	for (int y = lane; y < f.resY; y += 32)
@@ -321,7 +393,7 @@ __global__ void __launch_bounds__(kScapeColsPerBlock*32) landscape_kernel(uint32
 
 		// the samples of a chunk do not depend on the carry: the gathers of the NEXT chunk are issued before this chunk's scan
 		// and span stores (see tunnelscape_kernel), so their L2 latency overlaps the emission instead of heading every iteration
-		RawSample next = fetch_sample(heightMap, colorMap, fogGradient, lane, int(unsigned(f.fpX1) + (lane+1)*unsigned(fpDX)), int(unsigned(f.fpY1) + (lane+1)*unsigned(fpDY)), 1023u, 10u);
+		RawSample next = fetch_sample_tex(heightTex, colorTex, fogGradient, lane, int(unsigned(f.fpX1) + (lane+1)*unsigned(fpDX)), int(unsigned(f.fpY1) + (lane+1)*unsigned(fpDY)), 1023u, 1.f/1024.f);
 
 		for (unsigned base = 0; base < kScapeRayLength; base += 32)
 		{
@@ -330,7 +402,7 @@ __global__ void __launch_bounds__(kScapeColsPerBlock*32) landscape_kernel(uint32
 			if (base + 32 < kScapeRayLength)
 			{
 				const unsigned nStep = iStep + 32;
-				next = fetch_sample(heightMap, colorMap, fogGradient, nStep, int(unsigned(f.fpX1) + (nStep+1)*unsigned(fpDX)), int(unsigned(f.fpY1) + (nStep+1)*unsigned(fpDY)), 1023u, 10u);
+				next = fetch_sample_tex(heightTex, colorTex, fogGradient, nStep, int(unsigned(f.fpX1) + (nStep+1)*unsigned(fpDX)), int(unsigned(f.fpY1) + (nStep+1)*unsigned(fpDY)), 1023u, 1.f/1024.f);
 			}
 
 			const unsigned mapHeight = bilerp_u8(raw.h[0], raw.h[1], raw.h[2], raw.h[3], int(raw.fu), int(raw.fv));
@@ -356,22 +428,36 @@ __global__ void __launch_bounds__(kScapeColsPerBlock*32) landscape_kernel(uint32
 			const int drawnBefore = warp_excl_min(height, carryLastDrawn, newLastDrawn);
 
 			const bool visible = height < drawnBefore;
-			emit_spans(line, f.resY, visible, height, 1, unsigned(prevHeight - height), unsigned(drawnBefore - height), color, prevColor);
+			// spans: per lane (cost ~ the longest span of the chunk) or tiled over the lanes (cost ~ the chunk's pixels on screen)
+			const int lo = max(newLastDrawn, 0), hi = min(carryLastDrawn, f.resY);
+			if (hi > lo)
+			{
+				const unsigned drawLength = unsigned(drawnBefore - height);
+				SpanRamp ramp;
+				const bool plain = span_prepare(ramp, visible, unsigned(prevHeight - height), drawLength, color, prevColor);
+				const unsigned longest = __reduce_max_sync(kFull, visible ? drawLength : 0u);
+				if (longest*c_tiledPerLane > unsigned((hi - lo + 31) >> 5)*c_tiledPerBatch)
+					emit_tiled_spans(line, lo, hi, min(drawnBefore, height), ramp, __ballot_sync(kFull, plain));
+				else
+					emit_prepared_spans(line, f.resY, visible, height, 1, drawLength, ramp, plain);
+			}
 
 			carryLastDrawn = newLastDrawn;
 			carryLastHeight = __shfl_sync(kFull, height, 31);
 			carryLastColor = shfl_color(color, 31);
+			if (carryLastDrawn <= 0)
+				break; // the column is drawn up to the top of the screen: whatever else is visible lies above it
 		}
 	}
 
 	__syncthreads();
 
-	// write the kScapeColsPerBlock columns out: one 32-byte sector per row
-	const int x0 = blockIdx.x*kScapeColsPerBlock;
-	for (int i = threadIdx.x; i < f.resY*kScapeColsPerBlock; i += blockDim.x)
+	// write the CTA's columns out: consecutive threads take consecutive columns of a row (one 32-byte sector per row at 8 columns)
+	const int x0 = blockIdx.x*colsPerBlock;
+	const int c = int(threadIdx.x) % colsPerBlock;
+	if (x0 + c < f.resX)
 	{
-		const int y = i / kScapeColsPerBlock, c = i % kScapeColsPerBlock;
-		if (x0 + c < f.resX)
+		for (int y = int(threadIdx.x) / colsPerBlock; y < f.resY; y += 32)
 			pDest[size_t(y)*f.resX + x0 + c] = s_lines[c*lineStride + y];
 	}
 }
@@ -780,6 +866,60 @@ static int ApplyShortSpanOverride()
 		const unsigned v = unsigned(atoi(env));
 		CKD_CUDA(cudaMemcpyToSymbol(c_shortSpan, &v, sizeof(v)));
 	}
+	if (const char *env = getenv("CKD_TILED_LANE"))
+	{
+		const unsigned v = unsigned(atoi(env));
+		CKD_CUDA(cudaMemcpyToSymbol(c_tiledPerLane, &v, sizeof(v)));
+	}
+	if (const char *env = getenv("CKD_TILED_BATCH"))
+	{
+		const unsigned v = unsigned(atoi(env));
+		CKD_CUDA(cudaMemcpyToSymbol(c_tiledPerBatch, &v, sizeof(v)));
+	}
+	return CKD_OK;
+}
+
+// Columns (= warps) per landscape CTA.  A column's line buffer is resY pixels of shared memory, so the CTAs an SM holds are few
+// (three of 8 columns at 4K) and the grid easily ends in a nearly empty last wave: 3840 columns in CTAs of 8 are 480 CTAs on
+// 444 slots, the last 36 run alone.  The pick minimises waves x resident warps (what an instruction-bound kernel pays), with a
+// floor where a wave is latency bound anyway; at 4K on 148 SMs that is 13 columns: 296 CTAs, two per SM, one full wave.
+static int PickScapeColumns(ckd_ctx *ctx, int lineStride, int *pCols)
+{
+	if (ctx->scapeCols)
+	{
+		*pCols = ctx->scapeCols;
+		return CKD_OK;
+	}
+	int maxOptin = 0;
+	CKD_CUDA(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+	const int maxCols = std::min(kScapeMaxColsPerBlock, int(size_t(maxOptin)/(size_t(lineStride)*4)));
+	CKD_REQUIRE(maxCols >= 1, "the output is too tall for the landscape's shared-memory line buffer");
+	CKD_TRY(EnsureSmem(landscape_kernel, size_t(maxCols)*lineStride*4));
+	int best = 0;
+	long bestCost = 0;
+	if (const char *env = getenv("CKD_SCAPE_COLS")) // tuning override
+		best = std::max(1, std::min(maxCols, atoi(env)));
+	if (!best)
+	{
+		constexpr long kLatencyFloorWarps = 16;
+		for (int i = 0; i <= maxCols; ++i)
+		{
+			const int cols = (i == 0) ? std::min(kScapeColsPerBlock, maxCols) : maxCols + 1 - i; // the default first, then wide to narrow: ties keep the earlier one
+			int perSM = 0;
+			CKD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, landscape_kernel, cols*32, size_t(cols)*lineStride*4));
+			if (perSM < 1)
+				continue;
+			const long ctas = ckd_div_up(ctx->resX, cols);
+			const long slots = long(perSM)*ctx->numSMs;
+			const long waves = (ctas + slots - 1)/slots;
+			const long resident = std::min<long>(perSM, (ctas + ctx->numSMs - 1)/ctx->numSMs)*cols;
+			const long cost = waves*std::max(resident, kLatencyFloorWarps);
+			if (!best || cost < bestCost) { best = cols; bestCost = cost; }
+		}
+	}
+	CKD_REQUIRE(best >= 1, "no landscape launch shape fits this device");
+	ctx->scapeCols = best;
+	*pCols = best;
 	return CKD_OK;
 }
 
@@ -820,12 +960,15 @@ extern "C" int ckd_landscape_draw(ckd_ctx *ctx, const ckd_landscape_params *p, f
 	const bool warp = 0.f != p->warp_strength;
 	uint32_t *pWrite = warp ? ctx->d_renderTarget[0] : d_dest;
 
+	cudaTextureObject_t heightTex = 0, colorTex = 0;
+	CKD_TRY(ckd_gather_texture(ctx, CKD_IMG_SCAPE_HEIGHT, &heightTex));
+	CKD_TRY(ckd_gather_texture(ctx, CKD_IMG_SCAPE_COLOR, &colorTex));
 	const int lineStride = ctx->resY | 1;
-	const size_t smem = size_t(kScapeColsPerBlock)*lineStride*4;
-	CKD_TRY(EnsureSmem(landscape_kernel, smem));
+	int cols = 0;
+	CKD_TRY(PickScapeColumns(ctx, lineStride, &cols));
+	const size_t smem = size_t(cols)*lineStride*4;
 	ckd_prof_begin(ctx, "voxel_landscape", 4.0*ctx->resX*ctx->resY);
-	landscape_kernel<<<ckd_div_up(ctx->resX, kScapeColsPerBlock), kScapeColsPerBlock*32, smem, ctx->stream>>>(pWrite,
-		static_cast<const uint8_t *>(ctx->images[CKD_IMG_SCAPE_HEIGHT].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_SCAPE_COLOR].d_pixels),
+	landscape_kernel<<<ckd_div_up(ctx->resX, cols), cols*32, smem, ctx->stream>>>(pWrite, heightTex, colorTex, static_cast<const uint32_t *>(ctx->images[CKD_IMG_SCAPE_COLOR].d_pixels),
 		static_cast<const uint32_t *>(ctx->images[CKD_IMG_SCAPE_FOG].d_pixels), f, lineStride);
 	CKD_CHECK_LAUNCH(ctx);
 
