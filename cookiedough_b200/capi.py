@@ -170,6 +170,7 @@ def load():
         "ckd_landscape_draw": ([VP, C.POINTER(LandscapeParams), F, VP], _I),
         "ckd_tunnelscape_draw": ([VP, C.POINTER(TunnelscapeParams), F, VP], _I),
         "ckd_ball_draw": ([VP, C.POINTER(BallParams), F, VP], _I),
+        "ckd_ball_beam_tail": ([VP, VP, _I, _I, _I, C.c_uint32, F, _I], _I),
         "ckd_twister_draw": ([VP, C.POINTER(TwisterParams), F, VP], _I),
         "ckd_launch_count": ([VP], C.c_ulonglong),
         "ckd_set_fast_cos_table": ([VP, VP], _I), "ckd_get_fast_cos_table": ([VP, VP], _I),
@@ -331,6 +332,10 @@ class Context:
         else:
             rc = getattr(L, f"ckd_{effect}_draw")(h, C.byref(params), t, C.c_void_p(d_dest))
         self._check(rc)
+
+    def ball_beam_tail(self, d_rows, row_pixels, rows, first_remainder, beam_color, beam_alpha_min, raw_steps=False):
+        """the beam tail of vball_ray_beams alone (ball.cpp:168-203), one row per tail length; raw_steps: the float bits of curStep"""
+        self._check(self.L.ckd_ball_beam_tail(self.h, C.c_void_p(d_rows), row_pixels, rows, first_remainder, beam_color, C.c_float(beam_alpha_min), int(bool(raw_steps))))
 
     def read_frame(self, d_ptr=None):
         return self.download(d_ptr or self.frame(), (self.res_y, self.res_x))

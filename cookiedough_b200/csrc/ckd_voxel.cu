@@ -573,6 +573,92 @@ struct BallFrame
 	int clearLastPixel;       // ckd_set_frame_independent: the pixel the beam path never writes starts from 0 instead of history
 };
 
+// The tail of vball_ray_beams (ball.cpp:168-203): from the last drawn pixel to one short of the row's end the beam colour goes
+// out with an alpha that follows smoothstep(beamAlphaMin, luminosity, curStep), curStep accumulated in float pixel by pixel.
+// RAW (ckd_ball_beam_tail's check mode) writes the bits of curStep itself instead of the pixel.
+template <bool RAW>
+__device__ __forceinline__ void beam_tail(uint32_t *line, int resX, unsigned carryLastDrawn, uint32_t beamCol, float beamAlphaMin)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned lastDrawnHeight = carryLastDrawn;
+	const unsigned remainder = unsigned(resX - 1) - lastDrawnHeight;
+	beamCol &= 0xffffffu;
+
+	const unsigned beamR = beamCol >> 16, beamG = (beamCol >> 8) & 0xff, beamB = beamCol & 0xff;
+	const unsigned mulR = 4731u, mulG = 46871u, mulB = 13932u; // unsigned(0.0722f*65536.f) etc.
+	const unsigned luminosity = ((beamR*mulR) >> 16) + ((beamG*mulG) >> 16) + ((beamB*mulB) >> 16);
+	const float fLuminosity = float(luminosity);
+
+	if (remainder <= unsigned(resX))
+	{
+		// 'curStep += alphaStep' is a serial float accumulation (ball.cpp:195-203): pixel i needs the value after i rounded
+		// additions.  The first 32 pixels take them literally.  After that the chain is walked binade by binade: while the
+		// running value c stays within one binade its grid (ulp) is fixed, so fl(c + a) = c + (a rounded to that grid) -- a
+		// constant increment, once one addition has been made inside the binade (a tie of a's dropped bits rounds to even,
+		// which can make the first step of a binade differ; after it the values are even multiples and the tie always falls
+		// the same way).  So per binade: c (as it entered), c1 = fl(c + a), and from there c1 + (m-1)*inc with
+		// inc = fl(c1 + a) - c1; products and sums of grid multiples below 2^24 grid units are exact in float.  The step that
+		// leaves the binade is one real addition.  A dozen binades per ray (c runs from 32/(n-1) to 1) instead of one dependent
+		// FADD per pixel on every lane.
+		const float alphaStep = 1.f / float(remainder - 1);
+		const bool narrow = fabsf(beamAlphaMin) < 1.0e9f; // the alpha stays far inside int32: cvttss2si's 64-bit form and the 32-bit one agree
+		auto put = [&](unsigned i, float curStep)
+		{
+			if (RAW)
+			{
+				line[lastDrawnHeight + i] = __float_as_uint(curStep);
+				return;
+			}
+			const float fBeamAlpha = smoothstepf(beamAlphaMin, fLuminosity, curStep);
+			const unsigned beamAlpha = narrow ? unsigned(__float2int_rz(fBeamAlpha)) : f2u_x86(fBeamAlpha);
+			line[lastDrawnHeight + i] = beamCol | (beamAlpha << 24);
+		};
+
+		// pixels 0..31: the same 32 dependent additions on every lane; a lane keeps the value after `lane` of them, picked with
+		// a three-level select per group of 8 (predicates from the lane's low bits)
+		float cur = 0.f, mine = 0.f;
+		#pragma unroll
+		for (int grp = 0; grp < 4; ++grp)
+		{
+			float v[8];
+			v[0] = cur;
+			#pragma unroll
+			for (int j = 1; j < 8; ++j) v[j] = v[j-1] + alphaStep;
+			cur = v[7] + alphaStep;
+			const float s01 = (lane & 1) ? v[1] : v[0], s23 = (lane & 1) ? v[3] : v[2], s45 = (lane & 1) ? v[5] : v[4], s67 = (lane & 1) ? v[7] : v[6];
+			const float s03 = (lane & 2) ? s23 : s01, s47 = (lane & 2) ? s67 : s45;
+			const float sel = (lane & 4) ? s47 : s03;
+			if ((lane >> 3) == grp) mine = sel;
+		}
+		if (unsigned(lane) < remainder)
+			put(lane, mine);
+
+		unsigned k = 32;  // index of the next pixel
+		float c = cur;    // its value (identical on every lane)
+		while (k < remainder)
+		{
+			const float c1 = c + alphaStep, c2 = c1 + alphaStep;
+			const unsigned e = __float_as_uint(c) >> 23;
+			float base = c, inc = 0.f;
+			unsigned n = 1; // values of the chain within this binade
+			if ((__float_as_uint(c1) >> 23) == e)
+			{
+				inc = c2 - c1;
+				base = c1 - inc;
+				const float perUlp = __uint_as_float((277u - e) << 23); // 2^(150 - e): grid units per 1.0
+				const unsigned baseUnits = unsigned(__float2int_rz(base*perUlp)), incUnits = unsigned(__float2int_rz(inc*perUlp));
+				n = 1u + (0xffffffu - baseUnits)/incUnits;
+			}
+			n = min(n, remainder - k);
+			for (unsigned m = lane; m < n; m += 32)
+				put(k + m, (0 == m) ? c : base + float(m)*inc);
+			const unsigned last = n - 1;
+			c = ((0 == last) ? c : base + float(last)*inc) + alphaStep;
+			k += n;
+		}
+	}
+}
+
 // tables: heightProj[1024], projNorm0[1024], projNorm1[1024], projNorm2[1024] (ball.cpp:61-62)
 template <bool BEAMS>
 __global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
@@ -708,51 +794,7 @@ __global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest,
 			const uint32_t v = uint32_t(beamCarry[i]);
 			beamCol |= ((v > 32767u) ? 0u : min(v, 255u)) << (8*i); // v2cISSE16: packuswb
 		}
-		const unsigned lastDrawnHeight = carryLastDrawn;
-		const unsigned remainder = unsigned(f.resX - 1) - lastDrawnHeight;
-		beamCol &= 0xffffffu;
-
-		const unsigned beamR = beamCol >> 16, beamG = (beamCol >> 8) & 0xff, beamB = beamCol & 0xff;
-		const unsigned mulR = 4731u, mulG = 46871u, mulB = 13932u; // unsigned(0.0722f*65536.f) etc.
-		const unsigned luminosity = ((beamR*mulR) >> 16) + ((beamG*mulG) >> 16) + ((beamB*mulB) >> 16);
-		const float fLuminosity = float(luminosity);
-
-		if (remainder <= unsigned(f.resX))
-		{
-			// 'curStep += alphaStep' is a serial float accumulation (ball.cpp:195-203).  Lanes take 32-pixel blocks in turn: the
-			// running value enters a block through a shuffle, every lane then needs the value after 'lane' more additions --
-			// which lane 0 of the block produces serially (32 dependent FADDs) and hands out with shuffles.
-			const float alphaStep = 1.f / float(remainder - 1);
-			float blockStart = 0.f;
-			for (unsigned i0 = 0; i0 < remainder; i0 += 32)
-			{
-				// the same 32 dependent additions on every lane; a lane keeps the value after `lane` of them.  Picking it with a
-				// three-level select per group of 8 (predicates from the lane's low bits, hoisted) costs 16 instructions per 8
-				// additions instead of 24 with a compare and a select per addition.
-				float cur = blockStart, mine = blockStart;
-				#pragma unroll
-				for (int grp = 0; grp < 4; ++grp)
-				{
-					float v[8];
-					v[0] = cur;
-					#pragma unroll
-					for (int j = 1; j < 8; ++j) v[j] = v[j-1] + alphaStep;
-					cur = v[7] + alphaStep;
-					const float s01 = (lane & 1) ? v[1] : v[0], s23 = (lane & 1) ? v[3] : v[2], s45 = (lane & 1) ? v[5] : v[4], s67 = (lane & 1) ? v[7] : v[6];
-					const float s03 = (lane & 2) ? s23 : s01, s47 = (lane & 2) ? s67 : s45;
-					const float sel = (lane & 4) ? s47 : s03;
-					if ((lane >> 3) == grp) mine = sel;
-				}
-				blockStart = cur; // identical on every lane: all lanes run the same 32 additions
-				const unsigned i = i0 + lane;
-				if (i < remainder)
-				{
-					const float fBeamAlpha = smoothstepf(f.beamAlphaMin, fLuminosity, mine);
-					const unsigned beamAlpha = f2u_x86(fBeamAlpha);
-					line[lastDrawnHeight + i] = beamCol | (beamAlpha << 24);
-				}
-			}
-		}
+		beam_tail<false>(line, f.resX, carryLastDrawn, beamCol, f.beamAlphaMin);
 	}
 	else
 	{
@@ -760,6 +802,17 @@ __global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest,
 		for (int x = min(int(carryLastDrawn), f.resX) + lane; x < f.resX; x += 32)
 			line[x] = 0;
 	}
+}
+
+// one warp per row: the beam tail alone, row r with `firstRemainder + r` pixels left
+template <bool RAW>
+__global__ void __launch_bounds__(kRowsPerBlock*32) beam_tail_kernel(uint32_t *pDest, int rowPixels, int rows, unsigned firstRemainder, uint32_t beamCol, float beamAlphaMin)
+{
+	const unsigned row = blockIdx.x*kRowsPerBlock + (threadIdx.x >> 5);
+	if (row >= unsigned(rows))
+		return;
+	const unsigned remainder = firstRemainder + row;
+	beam_tail<RAW>(pDest + size_t(row)*rowPixels, rowPixels, unsigned(rowPixels - 1) - remainder, beamCol, beamAlphaMin);
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -1197,4 +1250,19 @@ extern "C" int ckd_twister_draw(ckd_ctx *ctx, const ckd_twister_params *p, float
 
 	CKD_CUDA(cudaMemcpyAsync(d_dest, ctx->images[CKD_IMG_TWISTER_BACKGROUND].d_pixels, size_t(ctx->resX)*ctx->resY*4, cudaMemcpyDeviceToDevice, ctx->stream));
 	return ckd_polar_tail(ctx, d_dest, ctx->d_renderTarget[0], 0, true, nullptr);
+}
+
+// The beam tail of vball_ray_beams on its own (ball.cpp:168-203), for `rows` rows of `row_pixels` pixels: row r is a ray whose
+// spans ended `first_remainder + r` pixels before the last pixel of the row.  What the tail does not write is left alone.
+// raw_steps != 0 stores the float bits of the accumulated smoothstep parameter instead of the pixel.
+extern "C" int ckd_ball_beam_tail(ckd_ctx *ctx, uint32_t *d_rows, int row_pixels, int rows, int first_remainder, uint32_t beam_color, float beam_alpha_min, int raw_steps)
+{
+	CKD_REQUIRE(ctx && d_rows, "null argument");
+	CKD_REQUIRE(row_pixels >= 1 && rows >= 1 && first_remainder >= 0 && first_remainder + rows - 1 <= row_pixels - 1, "the tails must fit their rows");
+	if (raw_steps)
+		beam_tail_kernel<true><<<ckd_div_up(rows, kRowsPerBlock), kRowsPerBlock*32, 0, ctx->stream>>>(d_rows, row_pixels, rows, unsigned(first_remainder), beam_color, beam_alpha_min);
+	else
+		beam_tail_kernel<false><<<ckd_div_up(rows, kRowsPerBlock), kRowsPerBlock*32, 0, ctx->stream>>>(d_rows, row_pixels, rows, unsigned(first_remainder), beam_color, beam_alpha_min);
+	CKD_CHECK_LAUNCH(ctx);
+	return CKD_OK;
 }

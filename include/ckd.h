@@ -318,6 +318,12 @@ typedef struct ckd_ball_params {         /* ball.cpp:82,285-286,318-319,322,331-
 	int low_beams;          /* geti(ball:BallLowBeams) */
 } ckd_ball_params;
 int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time, uint32_t *d_dest); /* Ball_Draw ball.cpp:452 */
+/* The beam tail of vball_ray_beams on its own (ball.cpp:168-203: beam colour with a smoothstep alpha whose parameter is a float
+ * accumulated pixel by pixel), for `rows` rows of `row_pixels` pixels in device memory: row r is a ray whose spans ended
+ * `first_remainder + r` pixels before the last pixel of its row.  Pixels the tail does not reach are left alone.  The ball
+ * kernel runs the same code per ray; this entry exists so that every tail length can be checked on its own: with raw_steps != 0
+ * it stores the float bits of the accumulated parameter (`curStep`, ball.cpp:195-203) instead of the pixels. */
+int ckd_ball_beam_tail(ckd_ctx *ctx, uint32_t *d_rows, int row_pixels, int rows, int first_remainder, uint32_t beam_color, float beam_alpha_min, int raw_steps);
 
 typedef struct ckd_twister_params {      /* torus-twister.cpp:100-101,173 */
 	float speed, shear_speed, blur; /* twister:Speed, twister::ShearSpeed (sic), twister:Blur */
