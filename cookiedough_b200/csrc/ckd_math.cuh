@@ -433,21 +433,26 @@ template <class Lut> __device__ __forceinline__ void rotZ(const Lut &lut, float 
 
 // 8-bit lerp used by every bilinear sampler (bilinear.h:34-125): ((a<<8) + (b-a)*f) >> 8, two channels per 32-bit word.
 // a*(256-f) + b*f is the same non-negative 16-bit value, so the packed form is exact.
-__device__ __forceinline__ uint32_t lerp8x2(uint32_t a, uint32_t b, uint32_t f)
+// lerp8x2_raw leaves the two results in bytes 1 and 3 of the word; the byte permutes below pick them up (one PRMT where a shift
+// and a mask would be two ALU instructions: the polar remap and the voxel casters are bound by that pipe / by issue slots).
+__device__ __forceinline__ uint32_t lerp8x2_raw(uint32_t a, uint32_t b, uint32_t f) { return a*(256u - f) + b*f; }
+__device__ __forceinline__ uint32_t odd_bytes(uint32_t x) { return __byte_perm(x, 0u, 0x4341); }            // (x >> 8) & 0x00ff00ff
+__device__ __forceinline__ uint32_t lerp8x2(uint32_t a, uint32_t b, uint32_t f) { return odd_bytes(lerp8x2_raw(a, b, f)); }
+// the same lerp on a whole packed pixel, every channel by the same f (Mix32-style blends, the A-variant of the polar blit)
+__device__ __forceinline__ uint32_t lerp8x4(uint32_t a, uint32_t b, uint32_t f)
 {
-	return ((a*(256u - f) + b*f) >> 8) & 0x00ff00ffu;
+	const uint32_t rb = lerp8x2_raw(a & 0x00ff00ffu, b & 0x00ff00ffu, f), ag = lerp8x2_raw(odd_bytes(a), odd_bytes(b), f);
+	return __byte_perm(rb, ag, 0x7351); // bytes: rb.1, ag.1, rb.3, ag.3
 }
 
 // bsamp32_16 / bsamp32_32 (bilinear.h:58-125) on packed ARGB: returns packed 8-bit channels
 __device__ __forceinline__ uint32_t bilerp_argb(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t fu, uint32_t fv)
 {
 	const uint32_t rb01 = lerp8x2(s0 & 0x00ff00ffu, s1 & 0x00ff00ffu, fu);
-	const uint32_t ag01 = lerp8x2((s0 >> 8) & 0x00ff00ffu, (s1 >> 8) & 0x00ff00ffu, fu);
+	const uint32_t ag01 = lerp8x2(odd_bytes(s0), odd_bytes(s1), fu);
 	const uint32_t rb23 = lerp8x2(s2 & 0x00ff00ffu, s3 & 0x00ff00ffu, fu);
-	const uint32_t ag23 = lerp8x2((s2 >> 8) & 0x00ff00ffu, (s3 >> 8) & 0x00ff00ffu, fu);
-	const uint32_t rb = lerp8x2(rb01, rb23, fv);
-	const uint32_t ag = lerp8x2(ag01, ag23, fv);
-	return rb | (ag << 8);
+	const uint32_t ag23 = lerp8x2(odd_bytes(s2), odd_bytes(s3), fu);
+	return __byte_perm(lerp8x2_raw(rb01, rb23, fv), lerp8x2_raw(ag01, ag23, fv), 0x7351);
 }
 
 // bsamp8 (bilinear.h:34-53); signed arithmetic shifts as in the reference

@@ -133,9 +133,7 @@ template <int OP> __device__ __forceinline__ uint32_t blend_px(uint32_t d, uint3
 		// (dest<<8 + alpha*(src-dest)) >> 8 in 16-bit lanes == (dest*(256-alpha) + src*alpha) >> 8  (util.cpp:92-95, 672-675, 808-810)
 		const uint32_t alpha = (OP == CKD_MIXSRC32) ? A1 : p.u0;
 		const uint32_t src = (OP == CKD_FADE32) ? p.u1 : s;
-		const uint32_t rb = lerp8x2(d & 0x00ff00ffu, src & 0x00ff00ffu, alpha);
-		const uint32_t ag = lerp8x2((d >> 8) & 0x00ff00ffu, (src >> 8) & 0x00ff00ffu, alpha);
-		return rb | (ag << 8);
+		return lerp8x4(d, src, alpha);
 	}
 	if (OP == CKD_ADD32) return adds_u8x4(d, s); // util.cpp:141-143
 	if (OP == CKD_SUB32) return subs_u8x4(d, s); // util.cpp:188-190
@@ -418,7 +416,7 @@ template <int OP> __device__ __forceinline__ uint32_t rect_px(uint32_t d, uint32
 	if (OP == kRectMixSrc)
 	{
 		const uint32_t a = s >> 24;
-		return lerp8x2(d & 0x00ff00ffu, s & 0x00ff00ffu, a) | (lerp8x2((d >> 8) & 0x00ff00ffu, (s >> 8) & 0x00ff00ffu, a) << 8);
+		return lerp8x4(d, s, a);
 	}
 	if (OP == kRectBlitAdd)
 		return adds_u8x4(d, s);
@@ -563,7 +561,7 @@ __device__ __forceinline__ uint32_t polar_blend(uint32_t d, uint32_t s)
 {
 	// Polar_Blit_TileA, polar.cpp:169-174: lerp every channel by the fetched alpha
 	const uint32_t a = s >> 24;
-	return lerp8x2(d & 0x00ff00ffu, s & 0x00ff00ffu, a) | (lerp8x2((d >> 8) & 0x00ff00ffu, (s >> 8) & 0x00ff00ffu, a) << 8);
+	return lerp8x4(d, s, a);
 }
 
 // HALO: SoftLight32A(pDest, pHalo) (util.cpp:274-346) applied to the remapped pixel before it is stored -- the ball's halo layer
