@@ -467,6 +467,9 @@ __global__ void __launch_bounds__(kScapeMaxColsPerBlock*32, 2) landscape_kernel(
 // -------------------------------------------------------------------------------------------------------------
 
 constexpr int kRowsPerBlock = 4;
+// the ball's rays one per CTA: measured at 4K 1 / 2 / 4 / 8 rays per CTA = 36.5 / 36.8 / 41.5 / 36.8 us (beams: 45.6 / 45.6 / 49.4 /
+// 45.0); the tunnelscape is the other way round (50.2 / 50.2 / 47.8 / 50.1), the twister does not care (37.2 / 37.9 / 37.6 / 37.3)
+constexpr int kBallRowsPerBlock = 1;
 
 struct TunnelscapeFrame
 {
@@ -661,13 +664,13 @@ __device__ __forceinline__ void beam_tail(uint32_t *line, int resX, unsigned car
 
 // tables: heightProj[1024], projNorm0[1024], projNorm1[1024], projNorm2[1024] (ball.cpp:61-62)
 template <bool BEAMS>
-__global__ void __launch_bounds__(kRowsPerBlock*32) ball_kernel(uint32_t *pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
+__global__ void __launch_bounds__(kBallRowsPerBlock*32) ball_kernel(uint32_t *pDest, const uint8_t *__restrict__ heightMap, const uint32_t *__restrict__ colorMap,
 	const uint32_t *__restrict__ auxMap /* beam mix or env map */, const int *__restrict__ tables, const int *__restrict__ rayDeltas, const BallFrame f)
 {
 	// spans go straight to the row in global memory (see tunnelscape_kernel); with beams the reference does not clear the
 	// render target (ball.cpp:352-363), so whatever no span and no beam pixel covers simply keeps its previous content
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const unsigned iRay = blockIdx.x*kRowsPerBlock + warp;
+	const unsigned iRay = blockIdx.x*kBallRowsPerBlock + warp;
 	if (iRay >= unsigned(f.resY))
 		return;
 	uint32_t *line = pDest + size_t(iRay)*f.resX;
@@ -1172,17 +1175,17 @@ extern "C" int ckd_ball_draw(ckd_ctx *ctx, const ckd_ball_params *p, float time,
 	CKD_CUDA(cudaMemcpyAsync(d_tables, tables, sizeof(int)*4096, cudaMemcpyHostToDevice, ctx->stream));
 	CKD_CUDA(cudaMemcpyAsync(d_rayDeltas, rayDeltas, sizeof(int)*2*ctx->resY, cudaMemcpyHostToDevice, ctx->stream));
 
-	const unsigned blocks = ckd_div_up(ctx->resY, kRowsPerBlock);
+	const unsigned blocks = ckd_div_up(ctx->resY, kBallRowsPerBlock);
 	if (hasBeams)
 	{
 		ckd_prof_begin(ctx, "voxel_ball_beams", 4.0*ctx->resX*ctx->resY);
-		ball_kernel<true><<<blocks, kRowsPerBlock*32, 0, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
+		ball_kernel<true><<<blocks, kBallRowsPerBlock*32, 0, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
 			static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_COLOR0].d_pixels), ctx->d_ballBeamMix, d_tables, d_rayDeltas, f);
 	}
 	else
 	{
 		ckd_prof_begin(ctx, "voxel_ball", 4.0*ctx->resX*ctx->resY);
-		ball_kernel<false><<<blocks, kRowsPerBlock*32, 0, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
+		ball_kernel<false><<<blocks, kBallRowsPerBlock*32, 0, ctx->stream>>>(ctx->d_renderTarget[0], ctx->d_ballHeightMix,
 			static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_COLOR1].d_pixels), static_cast<const uint32_t *>(ctx->images[CKD_IMG_BALL_ENV].d_pixels), d_tables, d_rayDeltas, f);
 	}
 	CKD_CHECK_LAUNCH(ctx);
