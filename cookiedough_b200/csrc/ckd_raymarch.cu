@@ -705,9 +705,20 @@ template <class Effect> int LaunchRaymarch(ckd_ctx *ctx, const Effect &effect, u
 	const RsqrtTab rsqrt = { ctx->d_rsqrtTab, ctx->rsqrtLog2Bin };
 	const TileQueue queue = MakeQueue(ctx, geom, tileRow0, tileRow1);
 	const unsigned tiles = queue.numTiles - queue.firstTile;
-	const int blocks = int(std::max(1u, std::min<unsigned>(ckd_div_up(tiles, kTileY), unsigned(ctx->numSMs)*8)));
+	// a persistent grid: exactly the CTAs the device holds at once.  A CTA beyond that would only start when an earlier one has
+	// found the queue empty -- to stage its 16 KB table and leave
+	const bool fast = nullptr != proof && proof->holds() && !forceExact;
+	static int residentPerSM[2] = { 0, 0 };
+	if (0 == residentPerSM[fast])
+	{
+		int n = 0;
+		if (fast) CKD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raymarch_kernel<Effect, true>, kTileX*kTileY, 0));
+		else CKD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raymarch_kernel<Effect, false>, kTileX*kTileY, 0));
+		residentPerSM[fast] = std::max(1, n);
+	}
+	const int blocks = int(std::max(1u, std::min<unsigned>(ckd_div_up(tiles, kTileY), unsigned(ctx->numSMs)*unsigned(residentPerSM[fast]))));
 	ckd_prof_begin(ctx, name, 4.0*kWarpTileX*kWarpTileY*tiles);
-	if (nullptr != proof && proof->holds() && !forceExact)
+	if (fast)
 		raymarch_kernel<Effect, true><<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(effect, d_fxmap, geom, ctx->d_cosLUT2, rsqrt, queue);
 	else
 		raymarch_kernel<Effect, false><<<blocks, dim3(kTileX, kTileY), 0, ctx->stream>>>(effect, d_fxmap, geom, ctx->d_cosLUT2, rsqrt, queue);
