@@ -370,7 +370,7 @@ extern "C" void ckd_destroy(ckd_ctx *ctx)
 	cudaDeviceSynchronize();
 	for (auto &slot : ctx->images)
 	{
-		ckd_release_gather_texture(slot);
+		ckd_release_footprint_texture(slot);
 		if (slot.d_pixels) cudaFree(slot.d_pixels);
 	}
 	if (ctx->d_rsqrtTab) cudaFree(ctx->d_rsqrtTab);
@@ -432,7 +432,7 @@ extern "C" int ckd_clone_inputs(ckd_ctx *dst, const ckd_ctx *src)
 	{
 		const ckd_image_slot &from = src->images[i];
 		ckd_image_slot &to = dst->images[i];
-		ckd_release_gather_texture(to);
+		ckd_release_footprint_texture(to);
 		if (to.d_pixels) { cudaFree(to.d_pixels); to.d_pixels = nullptr; }
 		to = from;
 		to.d_pixels = nullptr;
@@ -712,7 +712,7 @@ extern "C" int ckd_set_image(ckd_ctx *ctx, ckd_image slot, const void *h_pixels,
 	CKD_REQUIRE(width > 0 && height > 0 && (bytes_per_pixel == 1 || bytes_per_pixel == 4), "bad image geometry");
 	ctx->inputsGen++;
 	ckd_image_slot &s = ctx->images[slot];
-	ckd_release_gather_texture(s);
+	ckd_release_footprint_texture(s);
 	if (s.d_pixels) { cudaFree(s.d_pixels); s.d_pixels = nullptr; }
 	const size_t bytes = size_t(width)*height*bytes_per_pixel;
 	CKD_CUDA(cudaMalloc(&s.d_pixels, bytes + 256)); // slack like the harness' loader
@@ -724,7 +724,7 @@ extern "C" int ckd_set_image(ckd_ctx *ctx, ckd_image slot, const void *h_pixels,
 	return CKD_OK;
 }
 
-void ckd_release_gather_texture(ckd_image_slot &slot)
+void ckd_release_footprint_texture(ckd_image_slot &slot)
 {
 	if (slot.gatherTex) { cudaDestroyTextureObject(slot.gatherTex); slot.gatherTex = 0; }
 	if (slot.gatherArray) { cudaFreeArray(slot.gatherArray); slot.gatherArray = nullptr; }
@@ -734,7 +734,7 @@ void ckd_release_gather_texture(ckd_image_slot &slot)
 // across the rows touches a different 128-byte line with every lane and tap (up to 32 tag look-ups per load, 8 loads per step);
 // a block-linear array read with tex2Dgather delivers the footprint in one request and keeps neighbouring rows in one tile.
 // Texels are single-channel (L8, or the BGRA word as one 32-bit channel), addressing wraps like the reference's '& mapAnd'.
-int ckd_gather_texture(ckd_ctx *ctx, int slot, cudaTextureObject_t *pTex)
+int ckd_footprint_texture(ckd_ctx *ctx, int slot, cudaTextureObject_t *pTex)
 {
 	CKD_REQUIRE(ctx && pTex && slot >= 0 && slot < CKD_IMG_COUNT, "bad image slot");
 	ckd_image_slot &s = ctx->images[slot];

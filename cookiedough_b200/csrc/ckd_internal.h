@@ -17,7 +17,7 @@ struct ckd_image_slot {
 	void *d_pixels = nullptr;
 	int width = 0, height = 0, bpp = 0;
 	uint32_t firstPixel = 0; // host copy of the first 4 bytes (the voxel effects clear with s_pFogGradient[0])
-	// block-linear twin for the voxel casters' bilinear footprints (ckd_gather_texture), made on first use from d_pixels
+	// block-linear twin for the voxel casters' bilinear footprints (ckd_footprint_texture), made on first use from d_pixels
 	cudaArray_t gatherArray = nullptr;
 	cudaTextureObject_t gatherTex = 0;
 };
@@ -93,8 +93,8 @@ struct ckd_ctx {
 void ckd_prof_begin(ckd_ctx *ctx, const char *name, double algoBytes);
 void ckd_prof_end(ckd_ctx *ctx);
 
-int ckd_gather_texture(ckd_ctx *ctx, int slot, cudaTextureObject_t *pTex); // single-channel wrap-addressed texture over the image (8- or 32-bit texels) for tex2Dgather
-void ckd_release_gather_texture(ckd_image_slot &slot);
+int ckd_footprint_texture(ckd_ctx *ctx, int slot, cudaTextureObject_t *pTex); // single-channel wrap-addressed texture over the image (8- or 32-bit texels) for tex2Dgather
+void ckd_release_footprint_texture(ckd_image_slot &slot);
 int ckd_ensure_polar_maps_2x2(ckd_ctx *ctx);
 int ckd_ensure_copy_stream(ckd_ctx *ctx);         // copy stream + its events, created on first use
 int ckd_polar_tail(ckd_ctx *ctx, uint32_t *d_dest, const uint32_t *d_src, int inverse, bool alpha, const uint32_t *d_softLightSrc); // Polar_Blit[A] (+ halo) as a frame's last stage: banded when a read-back is armed

@@ -86,7 +86,7 @@ __device__ __forceinline__ RawSample fetch_sample(const uint8_t *__restrict__ he
 	return r;
 }
 
-// the same texels through tex2Dgather (ckd_gather_texture; the landscape, whose 26 warps per SM are bound by L1 tag look-ups --
+// the same texels through tex2Dgather (ckd_footprint_texture; the landscape, whose 26 warps per SM are bound by L1 tag look-ups --
 // the tunnelscape at 15 warps per SM is not, and measured 2 % slower this way): the footprint of (U0, V0) is addressed by the corner its four texels
 // share, (U0+1, V0+1)/size -- exact in float for power-of-two maps, half a texel away from any rounding boundary -- and comes back
 // as .w = (U0,V0), .z = (U0+1,V0), .x = (U0,V0+1), .y = (U0+1,V0+1), with the reference's '& mapAnd' as wrap addressing
@@ -1017,8 +1017,8 @@ extern "C" int ckd_landscape_draw(ckd_ctx *ctx, const ckd_landscape_params *p, f
 	uint32_t *pWrite = warp ? ctx->d_renderTarget[0] : d_dest;
 
 	cudaTextureObject_t heightTex = 0, colorTex = 0;
-	CKD_TRY(ckd_gather_texture(ctx, CKD_IMG_SCAPE_HEIGHT, &heightTex));
-	CKD_TRY(ckd_gather_texture(ctx, CKD_IMG_SCAPE_COLOR, &colorTex));
+	CKD_TRY(ckd_footprint_texture(ctx, CKD_IMG_SCAPE_HEIGHT, &heightTex));
+	CKD_TRY(ckd_footprint_texture(ctx, CKD_IMG_SCAPE_COLOR, &colorTex));
 	const int lineStride = ctx->resY | 1;
 	int cols = 0;
 	CKD_TRY(PickScapeColumns(ctx, lineStride, &cols));
