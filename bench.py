@@ -204,10 +204,8 @@ def bind_to_gpu_numa(local):
 
 
 def dist_setup(n_gpus):
-    # NCCL_DEBUG is left as the caller set it.  Without one, NCCL still prints its version banner on stdout, where this script owes
-    # exactly one JSON line: the banner is sent to stderr (NCCL_DEBUG_FILE), not switched off.
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # NCCL_DEBUG is left as the caller set it.  NCCL prints its version banner on fd 1 either way (NCCL_DEBUG_FILE only redirects the
+    # levels above VERSION): main() has moved fd 1 to stderr and kept the real stdout for the one JSON line (claim_stdout).
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -320,7 +318,7 @@ def run_reference(args):
     R = reference_at(RES_Y)
     if R is None:
         base["unavailable"] = "oracle/_ref (compiled reference) is not present in this checkout"
-        print(json.dumps(base))
+        emit(base)
         return 0
     out = R.frame()
 
@@ -340,7 +338,7 @@ def run_reference(args):
                  "run": {"suite_passes_per_step": 1, "cpu_model": cpu_model()},
                  "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": threads, "kind": "reference", "sample": sample, "cpu_model": cpu_model()},
                  "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(base))
+    emit(base)
     return 0
 
 
@@ -736,9 +734,9 @@ def run_ours(args):
         # profiling target (tools/ncu_round.sh): only the device-resident passes above, so that a launch list taken under ncu
         # holds exactly the launches `value` and `kernels[*].share` are made of
         if rank == 0:
-            print(json.dumps({"metric": "Mpixel/s", "value": world * PIXELS_PER_PASS * passes_per_step * args.steps / (elapsed_ms * 1e-3) / 1e6, "unit": "Mpixel/s",
+            emit({"metric": "Mpixel/s", "value": world * PIXELS_PER_PASS * passes_per_step * args.steps / (elapsed_ms * 1e-3) / 1e6, "unit": "Mpixel/s",
                               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "gpu_launches": launches,
-                              "config": suite_config(), "note": "--device-only: device-resident leg only (profiling target), not a bench line"}))
+                              "config": suite_config(), "note": "--device-only: device-resident leg only (profiling target), not a bench line"})
         for c in ctxs[1:]:
             c.close()
         host.close()
@@ -929,7 +927,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline, "parity": parity,
             "timeline": timeline, "post_chain_4k": post_chain, "config1_720p": config1,
         }
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -949,7 +947,7 @@ def timeline_reference(args):
     R = reference_at(RES_Y, demo=True)
     if R is None:
         base["unavailable"] = "oracle/_ref (compiled reference) is not present in this checkout"
-        print(json.dumps(base))
+        emit(base)
         return 0
     threads = use_all_host_threads()
     times = sharding.timeline_times(args.frames)
@@ -972,7 +970,7 @@ def timeline_reference(args):
                  "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": threads, "kind": "reference", "cpu_model": cpu_model(),
                                   "sample": f"every {stride}th frame of the {args.frames}-frame timeline ({len(sample)} frames per step) through the reference's Demo_Draw at {RES_X}x{RES_Y}"},
                  "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(base))
+    emit(base)
     return 0
 
 
@@ -998,7 +996,7 @@ def run_timeline(args):
                 "dtype": "f32+u8", "data": "synthetic", "config": {"workload": "timeline-4k", "frames": args.frames, "res": [RES_X, RES_Y]},
                 "e2e": dict(rec["e2e"], h2d_bytes_per_step=0, d2h_bytes_per_step=rec["e2e"]["d2h_bytes_per_pass"]),
                 "gpu_launches": rec["gpu_launches"], "timeline": rec, "cpu_baseline": rec.get("cpu_baseline")}
-        print(json.dumps(line))
+        emit(line)
     host.close()
     if dist is not None:
         dist.barrier()
@@ -1006,7 +1004,28 @@ def run_timeline(args):
     return 0
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout owes the driver exactly one JSON line.  Libraries write there too (NCCL's version banner at N > 1 comes out on fd 1
+    whatever NCCL_DEBUG_FILE says), so the real stdout is set aside for emit() and fd 1 -- for this process and everything it
+    loads -- becomes stderr."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(record):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(record) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

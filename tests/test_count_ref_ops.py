@@ -70,3 +70,17 @@ def test_bench_reads_the_reference_counted_denominators():
         assert addmul[name] == doc["kernels"][name]["fadd"] + doc["kernels"][name]["fmul"]
     # both arms of the bench describe the same workload
     assert bench.suite_config() == {"workload": "effect-suite-4k", "res": [3840, 2160], "effects": [s[0] for s in bench.SUITE]}
+
+
+def test_bench_stdout_carries_only_the_result_line():
+    """bench.py owes the driver exactly one JSON line on stdout; whatever else the process or a library writes to fd 1 (NCCL's
+    version banner at N > 1) must come out on stderr"""
+    import json
+    import subprocess
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); "
+            "os.write(1, b'NCCL version x.y\\n'); print('chatter'); bench.emit({'value': 1})") % REPO
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1 and json.loads(lines[0]) == {"value": 1}
+    assert "NCCL version x.y" in r.stderr and "chatter" in r.stderr
